@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of the knnQueryBatch hot path on BASELINE.json's metric config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A "step" is one pass of the hot path over one batch of synthetic queries (config 2: 10 000
+queries x 128-D against 1 000 000 x 128-D, l2sqr, k = 10).  Ours: `value` is measured with the
+queries already resident in HBM (CUDA events on the launching stream, max over ranks);
+`e2e` is the same batch through the C ABI with HOST buffers (H2D + kernels + D2H inside the
+timed region).  N > 1 (torchrun, one rank per GPU): the database is row-sharded, every rank
+scans its shard, the per-shard (key, id) lists are all-gathered over NCCL/NVLink and merged on
+device (strong scaling of the fixed 1 M-row workload).
+`--impl reference` times the reference's own CPU implementation (oracle/_ref: the unmodified
+NMSLIB sources, OpenMP over queries on all host cores) on a bounded query sample of the same
+workload.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "queries/sec (k=10, exact & HNSW recall@10>=0.95) at 1/2/4/8 B200 vs CPU"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(name: str, n: int | None, nq: int | None):
+    from nmslib_zig_b200 import synth
+    space, method, dtype, dist, n0, dim, nq0, k, _, _ = synth.CONFIGS[name]
+    data, queries = synth.make(name, n, nq)
+    return dict(name=name, space=space, method=method, dtype=dtype, dist=dist, dim=dim, k=k, data=data,
+                queries=queries, n=data.shape[0], nq=queries.shape[0])
+
+
+def ref_space(space):  # l2sqr is not a registered reference space: same ranking as l2
+    return "l2" if space == "l2sqr" else space
+
+
+def time_reference(w, sample: int, steps: int, warmup: int):
+    """The reference's CPU path on `sample` queries per step, OpenMP over queries on all cores."""
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    q = w["queries"][:sample]
+    if O.ref_available():
+        kind = "reference"
+        ref = O.RefIndex(ref_space(w["space"]), "seq_search").add(w["data"]).build("")
+        run = lambda: ref.knn(q, w["k"], threads=threads)
+    else:
+        kind = "port"
+        run = lambda: O.seq_knn(w["space"], w["data"], q, w["k"], threads=threads)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": sample / dt, "unit": "queries/s", "cores": threads, "kind": kind,
+            "sample": f"{sample} of {w['nq']} queries x all {w['n']} rows per step, {steps} steps"
+                      + (" (space l2: l2sqr is not registered in the reference; same ranking + one sqrtf)"
+                         if w["space"] == "l2sqr" else ""),
+            "ms_per_step": dt * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--n", type=int, default=None, help="override database rows (debug)")
+    ap.add_argument("--nq", type=int, default=None, help="override query count (debug)")
+    ap.add_argument("--cpu-sample", type=int, default=1024)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = workload(args.workload, args.n, args.nq)
+        sample = min(args.cpu_sample // 2, w["nq"])
+        base = time_reference(w, sample, max(1, args.steps), max(0, args.warmup))
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{w['name']}: seq_search {w['space']} {w['n']}x{w['dim']}, "
+                                       f"{w['nq']} queries, k={w['k']}", "space": w["space"], "k": w["k"]},
+                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import nmslib_zig_b200 as nb
+
+    if not torch.cuda.is_available() or not nb.device_available():
+        raise SystemExit("bench.py: no CUDA device -- the query path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    nb.set_device(local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    w = workload(args.workload, args.n, args.nq)
+    n, nq, dim, k = w["n"], w["nq"], w["dim"], w["k"]
+    u8 = w["dtype"] == "DenseUInt8Vector"
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    idx = nb.Index(w["space"], None, w["method"], w["dtype"], w["dist"])
+    idx.setShard(lo)                                   # keys carry GLOBAL positions (tie order)
+    shard_ids = np.arange(lo, hi, dtype=np.int32)
+    (idx.addUInt8Batch if u8 else idx.addDenseBatch)(w["data"][lo:hi], shard_ids)
+    idx.buildIndex()
+    idx.prepare()
+
+    q_host = torch.from_numpy(w["queries"]).pin_memory()
+    d_q = q_host.to(dev, non_blocking=False)
+    d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    d_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    d_keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    if dist_on:
+        g_keys = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+        g_ids = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
+        o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        o_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        idx.knnDevice(d_q.data_ptr(), nq, dim, k, d_ids.data_ptr(), d_dists.data_ptr(), d_keys.data_ptr(),
+                      stream.cuda_stream)
+        if dist_on:
+            dist.all_gather_into_tensor(g_keys, d_keys)
+            dist.all_gather_into_tensor(g_ids, d_ids)
+            idx.mergeTopk(g_keys.data_ptr(), g_ids.data_ptr(), world, nq, k, o_ids.data_ptr(), o_dists.data_ptr(),
+                          stream.cuda_stream)
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    st0 = idx.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st1 = idx.stats()
+    ms_per_step = ms / args.steps
+    value = nq / (ms_per_step * 1e-3)
+    launches = int(st1["kernel_launches"] - st0["kernel_launches"]) + (args.steps if dist_on else 0)
+    scan_ms = (st1["scan_ms_sum"] - st0["scan_ms_sum"]) / max(1, st1["scan_count"] - st0["scan_count"])
+
+    # ---- end to end through the public API: pinned host queries in, host results out ----
+    q_np = q_host.numpy()
+    if not dist_on:
+        def step_e2e():
+            return idx.knnQueryBatch(q_np, k)
+        d2h = nq * k * 8 + nq * 4
+    else:
+        h_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+        h_dists = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            d_q.copy_(q_host, non_blocking=True)
+            step_device()
+            if rank == 0:
+                h_ids.copy_(o_ids, non_blocking=True)
+                h_dists.copy_(o_dists, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        d2h = nq * k * 8
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if dist_on:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks = load_peaks()
+        flops = 2.0 * nq * (hi - lo) * dim                     # 2*Q*N*D per launch (this rank's shard)
+        achieved = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
+        tf32_peak = peaks["bf16_tflops"] / 2.0                 # TF32 dense = 1/2 bf16 (measured bf16 burst / 2)
+        cpu = None
+        if world == 1:
+            base = time_reference(w, min(args.cpu_sample, nq), 3, 1)
+            cpu = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8" if u8 else "f32", "data": "synthetic",
+            "config": {"workload": f"{w['name']}: {w['method']} {w['space']} {n}x{dim}, {nq} queries, k={k}",
+                       "space": w["space"], "k": k, "rows_per_gpu": hi - lo,
+                       "parallelism": f"row-sharded x{world}" + (" + NCCL all-gather + device k-way merge" if dist_on else ""),
+                       "l2_policy": f"inputs larger than L2 ({(hi - lo) * dim * (1 if u8 else 4) / 1e6:.0f} MB scanned per step)"},
+            "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(q_np.nbytes), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf32_peak, "traffic": None, "kernel": "scan",
+                         "kernel_ms": scan_ms,
+                         "peak_src": f"{peaks['src']} bf16 burst {peaks['bf16_tflops']} TF/s / 2 (TF32 dense)"},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    idx.deinit()
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""Build libnmslib_b200.so in-tree with nvcc for sm_100a (no JIT cache, no torch dependency).
+
+    python -m nmslib_zig_b200.build [--force] [--verbose]
+
+The shared library links cudart statically, so it dlopen()s on a machine without a GPU
+(the CPU-side tests check that it loads and exports every symbol of include/nmslib_b200.h).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIBDIR = PKG / "lib"
+LIB = LIBDIR / "libnmslib_b200.so"
+STAMP = LIBDIR / ".build_stamp"
+
+SOURCES = ["scan_exact.cu", "topk_merge.cu", "hnsw_search.cu", "engine.cu", "hnsw_format.cpp", "c_abi.cpp"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (cand == "nvcc" or Path(cand).exists()):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in sorted(CSRC.iterdir()) + [PKG.parent / "include" / "nmslib_b200.h", Path(__file__)]:
+        if f.is_file():
+            h.update(f.name.encode())
+            h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    LIBDIR.mkdir(exist_ok=True)
+    digest = _digest()
+    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text() == digest:
+        return LIB
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    env = dict(os.environ)
+    env.pop("CXX", None)  # the image's CXX wrapper is not a host compiler nvcc can use
+    env.pop("CC", None)
+    for src in SOURCES:
+        obj = LIBDIR / (src.rsplit(".", 1)[0] + ".o")
+        objs.append(str(obj))
+        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)))
+    failed = False
+    for src, p in procs:
+        out = p.communicate()[0].decode(errors="replace")
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- nvcc failed on {src} ---\n{out}\n")
+        elif verbose or out.strip():
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
+            "-cudart", "static", "-Xcompiler", "-fPIC"]
+    subprocess.run(link, check=True, env=env)
+    STAMP.write_text(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(p)

@@ -1,0 +1,579 @@
+// engine.cu -- host orchestration of the device query path (see engine.h).
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+
+namespace nb200 {
+
+namespace {
+constexpr int kErrInvalid = 2, kErrOOM = 3, kErrIncompat = 5, kErrTooLarge = 6, kErrBuild = 8, kErrQuery = 9;
+thread_local int g_default_device = -1;
+}  // namespace
+
+int default_device() {
+  if (g_default_device >= 0) return g_default_device;
+  const char* lr = getenv("LOCAL_RANK");
+  int d = lr ? atoi(lr) : 0;
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) == cudaSuccess && cnt > 0) d = d % cnt;
+  return d;
+}
+void set_default_device(int d) { g_default_device = d; }
+bool device_available() {
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return cnt > 0;
+}
+
+cudaError_t DevBuf::ensure(size_t bytes, bool zero_new, cudaStream_t s) {
+  if (bytes <= cap) return cudaSuccess;
+  if (p) {
+    cudaError_t e = cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (e != cudaSuccess) return e;
+  }
+  size_t want = round_up(bytes, 256);
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    return e;
+  }
+  cap = want;
+  if (zero_new) return cudaMemsetAsync(p, 0, want, s);
+  return cudaSuccess;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+cudaError_t PinBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return cudaSuccess;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = round_up(bytes, 4096);
+  cudaError_t e = cudaMallocHost(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    return e;
+  }
+  cap = want;
+  return cudaSuccess;
+}
+void PinBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
+Engine::Engine(Space space, Method method, bool is_u8, int device)
+    : space_(space), method_(method), is_u8_(is_u8), device_(device) {}
+
+Engine::~Engine() {
+  if (stream_ || d_db_.p) cudaSetDevice(device_);
+  for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
+                    &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
+                    &d_out_counts_})
+    b->release();
+  for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_}) b->release();
+  for (auto& e : ev_)
+    if (e) cudaEventDestroy(e);
+  for (auto& pr : scan_ev_)
+    for (auto& e : pr)
+      if (e) cudaEventDestroy(e);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+Status Engine::check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return Status::OK();
+  std::string m = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e);
+  cudaGetLastError();
+  return Status::Err(e == cudaErrorMemoryAllocation ? kErrOOM : kErrQuery, m);
+}
+
+// ------------------------------------------------------------------------------------ ingest
+Status Engine::add_rows(const void* rows, size_t count, size_t elem_count, const int32_t* ids) {
+  if (!rows || count == 0 || elem_count == 0) return Status::Err(kErrInvalid, "empty batch");
+  if (is_u8_ && elem_count != 128)  // space_l2sqr_sift.cc:137 CHECK (SIFT_DIM)
+    return Status::Err(13, "SIFT vectors must have 128 elements");
+  if (dim_ == 0) dim_ = (int)elem_count;
+  if ((size_t)dim_ != elem_count)
+    return Status::Err(kErrInvalid, "vector length " + std::to_string(elem_count) + " != index dimension " +
+                                        std::to_string(dim_));
+  if (n_ + count > 0xFFFFFFF0ull) return Status::Err(kErrTooLarge, "more than 2^32 rows in one shard");
+  if (is_u8_) {
+    const uint8_t* src = static_cast<const uint8_t*>(rows);
+    h_u8_.insert(h_u8_.end(), src, src + count * elem_count);
+  } else {
+    const float* src = static_cast<const float*>(rows);
+    h_f32_.insert(h_f32_.end(), src, src + count * elem_count);
+  }
+  for (size_t i = 0; i < count; ++i) h_ids_.push_back(ids ? ids[i] : (int32_t)i);  // nmslib_c.cpp:768
+  n_ += count;
+  data_dirty_ = true;
+  if (method_ == METHOD_HNSW && !graph_.empty()) {
+    graph_ = HnswGraph();  // the graph no longer describes the data
+    graph_dirty_ = true;
+  }
+  return Status::OK();
+}
+
+Status Engine::add_row_ptrs(const void* const* ptrs, size_t count, size_t elem_count, const int32_t* ids) {
+  if (!ptrs || count == 0) return Status::Err(kErrInvalid, "empty pointer batch");
+  for (size_t i = 0; i < count; ++i) {
+    if (!ptrs[i]) return Status::Err(1, "null data pointer in batch");
+    int32_t id = ids ? ids[i] : (int32_t)i;
+    Status s = add_rows(ptrs[i], 1, elem_count, &id);
+    if (!s.ok()) return s;
+  }
+  return Status::OK();
+}
+
+void Engine::reset() {
+  h_f32_.clear();
+  h_u8_.clear();
+  h_ids_.clear();
+  n_ = 0;
+  dim_ = 0;
+  built_ = false;
+  graph_ = HnswGraph();
+  data_dirty_ = graph_dirty_ = true;
+  n_dev_ = 0;
+}
+
+float Engine::host_distance(size_t a, size_t b) const {
+  if (is_u8_) {
+    const uint8_t *x = row_u8(a), *y = row_u8(b);
+    int32_t nx = 0, ny = 0, dot = 0;
+    for (int i = 0; i < dim_; ++i) {
+      nx += (int)x[i] * x[i];
+      ny += (int)y[i] * y[i];
+      dot += (int)x[i] * y[i];
+    }
+    return (float)(nx + ny - 2 * dot);
+  }
+  const float *x = row_f32(a), *y = row_f32(b);
+  float s = 0.f, n1 = 0.f, n2 = 0.f;
+  for (int i = 0; i < dim_; ++i) {
+    if (space_ == SPACE_L2 || space_ == SPACE_L2SQR) {
+      float d = x[i] - y[i];
+      s += d * d;
+    } else {
+      s += x[i] * y[i];
+      n1 += x[i] * x[i];
+      n2 += y[i] * y[i];
+    }
+  }
+  switch (space_) {
+    case SPACE_L2: return std::sqrt(s);
+    case SPACE_L2SQR: return s;
+    case SPACE_NEGDOT: return -s;
+    default: {
+      const float eps = 2.0f * 1.17549435e-38f;
+      float nsp = (n1 < eps || n2 < eps) ? 0.f : std::max(-1.f, std::min(1.f, s / std::sqrt(n1) / std::sqrt(n2)));
+      return std::max(0.f, 1.f - nsp);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ state
+void Engine::mark_built(const std::vector<std::string>& index_params) {
+  index_params_ = index_params;
+  built_ = true;
+}
+
+// Hnsw::SetQueryTimeParams (hnsw.cc:474-507): ef / efSearch are synonyms (default 20 in the
+// reference, 200 through its C ABI), algoType in {old, v1merge, hybrid}, searchMethod ignored;
+// anything else is an error.  SeqSearch::SetQueryTimeParams is a no-op (seqsearch.h:44).
+Status Engine::set_query_params(const std::vector<std::string>& params) {
+  if (method_ != METHOD_HNSW) return Status::OK();
+  bool has_ef = false, has_efs = false;
+  size_t ef = 20;  // the reference's own default once the user sets query-time params
+  for (const std::string& p : params) {
+    size_t eq = p.find('=');
+    if (eq == std::string::npos) return Status::Err(kErrInvalid, "malformed parameter '" + p + "'");
+    std::string name = p.substr(0, eq), val = p.substr(eq + 1);
+    if (name == "ef" || name == "efSearch") {
+      (name == "ef" ? has_ef : has_efs) = true;
+      std::stringstream ss(val);
+      double v = 0;
+      if (!(ss >> v) || v < 1) return Status::Err(kErrInvalid, "bad value for " + name);
+      ef = (size_t)v;
+    } else if (name == "algoType") {
+      std::string low = val;
+      std::transform(low.begin(), low.end(), low.begin(), ::tolower);
+      if (low != "old" && low != "v1merge" && low != "hybrid")
+        return Status::Err(kErrInvalid, "algoType should be one of: old, v1merge, hybrid");
+    } else if (name == "searchMethod") {
+    } else {
+      return Status::Err(kErrInvalid, "unknown query-time parameter '" + name + "'");
+    }
+  }
+  if (has_ef && has_efs) return Status::Err(kErrInvalid, "ef and efSearch are synonyms: specify only one");
+  if (ef > (size_t)hnsw_max_ef())
+    return Status::Err(kErrTooLarge, "efSearch above " + std::to_string(hnsw_max_ef()) + " is not supported");
+  ef_ = ef;
+  ef_user_set_ = true;
+  return Status::OK();
+}
+
+Status Engine::adopt_graph(HnswGraph&& g) {
+  if (method_ != METHOD_HNSW) return Status::Err(kErrIncompat, "graph import needs method hnsw");
+  if (is_u8_) return Status::Err(kErrIncompat, "the optimized HNSW index holds float vectors only");
+  const int want = (space_ == SPACE_COSINE) ? 3 : (space_ == SPACE_NEGDOT) ? 4 : 0;
+  const bool l2 = (space_ == SPACE_L2 || space_ == SPACE_L2SQR) && (g.dist_func == 1 || g.dist_func == 2);
+  if (!l2 && g.dist_func != want)
+    return Status::Err(kErrIncompat, "HNSW file distance type " + std::to_string(g.dist_func) +
+                                         " does not match the index space");
+  graph_ = std::move(g);
+  // the file carries the (for cosine: normalised) vectors and the external ids
+  dim_ = graph_.dim;
+  n_ = graph_.total;
+  h_f32_ = graph_.vectors;
+  h_ids_ = graph_.ext_ids;
+  graph_.vectors.clear();
+  graph_.vectors.shrink_to_fit();
+  data_dirty_ = graph_dirty_ = true;
+  built_ = true;
+  return Status::OK();
+}
+
+Status Engine::import_graph(const std::string& path) {
+  HnswGraph g;
+  Status s = read_hnsw_file(path, &g);
+  if (!s.ok()) return s;
+  return adopt_graph(std::move(g));
+}
+
+void Engine::scan_begin(cudaStream_t s) {
+  scan_cur_ = scan_head_;
+  scan_head_ = (scan_head_ + 1) % kScanRing;
+  if (!scan_ev_[scan_cur_][0]) {
+    cudaEventCreate(&scan_ev_[scan_cur_][0]);
+    cudaEventCreate(&scan_ev_[scan_cur_][1]);
+  }
+  scan_pending_[scan_cur_] = false;
+  cudaEventRecord(scan_ev_[scan_cur_][0], s);
+}
+void Engine::scan_end(cudaStream_t s) {
+  cudaEventRecord(scan_ev_[scan_cur_][1], s);
+  scan_pending_[scan_cur_] = true;
+}
+
+Stats Engine::stats() {
+  for (int i = 0; i < kScanRing; ++i) {
+    if (!scan_pending_[i] || cudaEventQuery(scan_ev_[i][1]) != cudaSuccess) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, scan_ev_[i][0], scan_ev_[i][1]) == cudaSuccess) {
+      stats_.last_scan_ms = ms;
+      stats_.scan_ms_sum += ms;
+      ++stats_.scan_count;
+    }
+    scan_pending_[i] = false;
+  }
+  cudaGetLastError();
+  return stats_;
+}
+
+int Engine::finalize_kind() const {
+  if (is_u8_) return FIN_INT;
+  // l2 + seq_search reports the root; l2 + hnsw reports the squared distance
+  if (space_ == SPACE_L2 && method_ == METHOD_SEQ) return FIN_SQRT;
+  return FIN_FLOAT;
+}
+
+// ------------------------------------------------------------------------------------ upload
+Status Engine::prepare() {
+  if (!device_available()) return Status::Err(kErrQuery, "no CUDA device available (there is no CPU fallback)");
+  Status s = check_cuda(cudaSetDevice(device_), "cudaSetDevice");
+  if (!s.ok()) return s;
+  if (!stream_) {
+    s = check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!s.ok()) return s;
+    for (auto& e : ev_) {
+      s = check_cuda(cudaEventCreate(&e), "cudaEventCreate");
+      if (!s.ok()) return s;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_) == cudaSuccess) sm_count_ = prop.multiProcessorCount;
+  }
+  if (data_dirty_) {
+    s = upload_data();
+    if (!s.ok()) return s;
+  }
+  if (method_ == METHOD_HNSW && graph_dirty_) {
+    s = upload_graph();
+    if (!s.ok()) return s;
+  }
+  return Status::OK();
+}
+
+Status Engine::upload_data() {
+  if (n_ == 0) {
+    n_dev_ = 0;
+    data_dirty_ = false;
+    return Status::OK();
+  }
+  const int stage = scan_exact_stage_words();
+  const int bn = scan_exact_block_points();
+  // HBM layout: row-major [n_pad][row_words] 32-bit words, rows zero padded to a whole
+  // pipeline stage (64 B) and the row count to a whole tile, so no kernel needs edge code.
+  row_words_ = (int)round_up(is_u8_ ? (size_t)dim_ / 4 : (size_t)dim_, stage);
+  if (is_u8_ && dim_ % 4) return Status::Err(kErrInvalid, "uint8 dimension must be a multiple of 4");
+  const size_t n_pad = round_up(n_, bn);
+  const size_t row_bytes = (size_t)row_words_ * 4;
+  Status s = check_cuda(d_db_.ensure(n_pad * row_bytes), "cudaMalloc(data)");
+  if (!s.ok()) return s;
+  s = check_cuda(cudaMemsetAsync(d_db_.p, 0, n_pad * row_bytes, stream_), "memset(data)");
+  if (!s.ok()) return s;
+  const size_t src_row = is_u8_ ? (size_t)dim_ : (size_t)dim_ * 4;
+  const void* src = is_u8_ ? (const void*)h_u8_.data() : (const void*)h_f32_.data();
+  s = check_cuda(cudaMemcpy2DAsync(d_db_.p, row_bytes, src, src_row, src_row, n_, cudaMemcpyHostToDevice, stream_),
+                 "H2D(data)");
+  if (!s.ok()) return s;
+  s = check_cuda(d_ids_.ensure(n_ * 4), "cudaMalloc(ids)");
+  if (!s.ok()) return s;
+  s = check_cuda(cudaMemcpyAsync(d_ids_.p, h_ids_.data(), n_ * 4, cudaMemcpyHostToDevice, stream_), "H2D(ids)");
+  if (!s.ok()) return s;
+  if (space_ == SPACE_COSINE || is_u8_) {
+    s = check_cuda(d_aux_.ensure(n_pad * 4), "cudaMalloc(aux)");
+    if (!s.ok()) return s;
+    s = check_cuda(launch_row_aux(is_u8_, d_db_.p, (int)n_, row_words_, d_aux_.p, stream_), "row_aux");
+    if (!s.ok()) return s;
+    ++stats_.kernel_launches;
+  }
+  s = check_cuda(cudaStreamSynchronize(stream_), "upload sync");
+  if (!s.ok()) return s;
+  n_dev_ = n_;
+  data_dirty_ = false;
+  stats_.device_bytes = d_db_.cap + d_ids_.cap + d_aux_.cap;
+  return Status::OK();
+}
+
+Status Engine::upload_graph() {
+  if (graph_.empty())
+    return Status::Err(kErrBuild,
+                       "hnsw index has no graph: import one built by the reference (nmslib_b200_import_hnsw / "
+                       "nmslib_load_index); graph construction stays on the reference CPU code");
+  if (graph_.total != n_) return Status::Err(kErrBuild, "HNSW graph / data size mismatch");
+  const HnswGraph& g = graph_;
+  Status s = check_cuda(d_links0_.ensure(std::max<size_t>(g.links0.size(), 1) * 4), "cudaMalloc(links0)");
+  if (!s.ok()) return s;
+  s = check_cuda(d_links0_cnt_.ensure((size_t)g.total * 4), "cudaMalloc(links0_cnt)");
+  if (!s.ok()) return s;
+  s = check_cuda(d_upper_.ensure(std::max<size_t>(g.upper.size(), 1) * 4), "cudaMalloc(upper)");
+  if (!s.ok()) return s;
+  s = check_cuda(d_upper_off_.ensure((size_t)g.total * 8), "cudaMalloc(upper_off)");
+  if (!s.ok()) return s;
+  cudaMemcpyAsync(d_links0_.p, g.links0.data(), g.links0.size() * 4, cudaMemcpyHostToDevice, stream_);
+  cudaMemcpyAsync(d_links0_cnt_.p, g.links0_cnt.data(), (size_t)g.total * 4, cudaMemcpyHostToDevice, stream_);
+  if (!g.upper.empty())
+    cudaMemcpyAsync(d_upper_.p, g.upper.data(), g.upper.size() * 4, cudaMemcpyHostToDevice, stream_);
+  cudaMemcpyAsync(d_upper_off_.p, g.upper_off.data(), (size_t)g.total * 8, cudaMemcpyHostToDevice, stream_);
+  // visited epoch arrays: one per resident warp slot (VisitedListPool, hnsw.h:598-639)
+  hnsw_slots_ = sm_count_ * 16;  // 16 warps per SM in flight
+  const size_t vstride = round_up((size_t)g.total, 16);
+  s = check_cuda(d_visited_.ensure(vstride * hnsw_slots_), "cudaMalloc(visited)");
+  if (!s.ok()) return s;
+  cudaMemsetAsync(d_visited_.p, 0, vstride * hnsw_slots_, stream_);
+  s = check_cuda(d_epoch_.ensure((size_t)hnsw_slots_ * 4), "cudaMalloc(epoch)");
+  if (!s.ok()) return s;
+  cudaMemsetAsync(d_epoch_.p, 0, (size_t)hnsw_slots_ * 4, stream_);
+  s = check_cuda(d_counters_.ensure(16), "cudaMalloc(counters)");
+  if (!s.ok()) return s;
+  cudaMemsetAsync(d_counters_.p, 0, 16, stream_);
+  s = check_cuda(cudaStreamSynchronize(stream_), "graph upload sync");
+  if (!s.ok()) return s;
+  graph_dirty_ = false;
+  stats_.device_bytes = d_db_.cap + d_ids_.cap + d_aux_.cap + d_links0_.cap + d_links0_cnt_.cap + d_upper_.cap +
+                        d_upper_off_.cap + d_visited_.cap;
+  return Status::OK();
+}
+
+// ------------------------------------------------------------------------------------ query
+Status Engine::stage_queries_device(const void* src, bool src_on_device, size_t nq, size_t elem_count,
+                                    cudaStream_t stream) {
+  const size_t bq = scan_exact_block_queries();
+  const size_t q_pad = round_up(nq, bq);
+  const size_t row_bytes = (size_t)row_words_ * 4;
+  const size_t old_cap = d_q_.cap;
+  Status s = check_cuda(d_q_.ensure(q_pad * row_bytes), "cudaMalloc(queries)");
+  if (!s.ok()) return s;
+  if (d_q_.cap != old_cap) {  // new buffer: zero it once so that the padding columns stay zero
+    s = check_cuda(cudaMemsetAsync(d_q_.p, 0, d_q_.cap, stream), "memset(queries)");
+    if (!s.ok()) return s;
+  }
+  const size_t src_row = is_u8_ ? elem_count : elem_count * 4;
+  return check_cuda(cudaMemcpy2DAsync(d_q_.p, row_bytes, src, src_row, src_row, nq,
+                                      src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream),
+                    "copy(queries)");
+}
+
+Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d_dists, uint64_t* d_keys,
+                   int32_t* d_counts, cudaStream_t stream) {
+  Status s;
+  if (method_ == METHOD_HNSW) {
+    HnswDeviceGraph g;
+    g.vectors = d_db_.as<float>();
+    g.links0 = d_links0_.as<int32_t>();
+    g.links0_cnt = d_links0_cnt_.as<int32_t>();
+    g.upper = d_upper_.as<int32_t>();
+    g.upper_off = d_upper_off_.as<int64_t>();
+    g.ext_ids = d_ids_.as<int32_t>();
+    g.n = (int)n_dev_;
+    g.dim = dim_;
+    g.row_words = row_words_;
+    g.maxM = graph_.maxM;
+    g.maxM0 = graph_.maxM0;
+    g.maxlevel = graph_.maxlevel;
+    g.enterpoint = (int)graph_.enterpoint;
+    g.dist_kind = graph_.dist_func == 3 ? 1 : graph_.dist_func == 4 ? 2 : 0;
+    s = check_cuda(d_keys_.ensure(nq * k * 8), "cudaMalloc(keys)");
+    if (!s.ok()) return s;
+    uint64_t* keys = d_keys ? d_keys : d_keys_.as<uint64_t>();
+    scan_begin(stream);
+    s = check_cuda(launch_hnsw_search(g, static_cast<const float*>(dq), (int)nq, (int)k, (int)ef_,
+                                      d_visited_.as<uint8_t>(), d_epoch_.as<int>(), hnsw_slots_, keys,
+                                      d_counters_.as<unsigned long long>(), stream),
+                   "hnsw_search");
+    scan_end(stream);
+    if (!s.ok()) return s;
+    // internal positions -> external ids (Object::id of data_rearranged_, hnsw_distfunc_opt.cc:280)
+    s = check_cuda(launch_merge_topk(keys, nullptr, 1, 0, k, (int)nq, (int)k, FIN_FLOAT, d_ids_.as<int32_t>(), 0,
+                                     nullptr, d_ids, d_dists, d_counts, stream),
+                   "finalize");
+    stats_.kernel_launches += 2;
+    return s;
+  }
+
+  // ---- sequential search ----
+  const int bq = scan_exact_block_queries(), bn = scan_exact_block_points();
+  const int n_tiles = (int)((n_dev_ + bn - 1) / bn);
+  const int q_blocks = (int)((nq + bq - 1) / bq);
+  int want = (2 * sm_count_ + q_blocks - 1) / q_blocks;  // aim at >= 2 CTAs per SM worth of work
+  int n_split = std::max(1, std::min(want, n_tiles));
+  const int max_split = std::max(1, merge_topk_max_items() / (int)k);
+  n_split = std::min(n_split, max_split);
+  const int tiles_per_split = (n_tiles + n_split - 1) / n_split;
+  n_split = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+
+  int mode;
+  switch (space_) {
+    case SPACE_L2:
+    case SPACE_L2SQR: mode = SCAN_L2; break;
+    case SPACE_COSINE: mode = SCAN_COSINE; break;
+    case SPACE_NEGDOT: mode = SCAN_NEGDOT; break;
+    default: mode = SCAN_SIFT; break;
+  }
+  const void* q_aux = nullptr;
+  if (mode == SCAN_COSINE || mode == SCAN_SIFT) {
+    s = check_cuda(d_qaux_.ensure(round_up(nq, bq) * 4), "cudaMalloc(qaux)");
+    if (!s.ok()) return s;
+    s = check_cuda(launch_row_aux(is_u8_, dq, (int)nq, row_words_, d_qaux_.p, stream), "query_aux");
+    if (!s.ok()) return s;
+    q_aux = d_qaux_.p;
+    ++stats_.kernel_launches;
+  }
+  s = check_cuda(d_partial_.ensure(nq * (size_t)n_split * k * 8), "cudaMalloc(partial)");
+  if (!s.ok()) return s;
+  scan_begin(stream);
+  s = check_cuda(launch_scan_exact(mode, d_db_.p, dq, d_aux_.p, q_aux, (int)n_dev_, (int)nq, row_words_, (int)k,
+                                   pos_base_, d_partial_.as<uint64_t>(), n_split, tiles_per_split, stream),
+                 "scan_exact");
+  scan_end(stream);
+  if (!s.ok()) return s;
+  s = check_cuda(launch_merge_topk(d_partial_.as<uint64_t>(), nullptr, n_split, k, (size_t)n_split * k, (int)nq,
+                                   (int)k, finalize_kind(), d_ids_.as<int32_t>(), pos_base_, d_keys, d_ids, d_dists,
+                                   d_counts, stream),
+                 "merge_topk");
+  stats_.kernel_launches += 2;
+  return s;
+}
+
+Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, size_t k, int32_t* d_ids,
+                          float* d_dists, uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream) {
+  if (!built_) return Status::Err(kErrBuild, "Index not built");
+  if (nq == 0 || k == 0) return Status::Err(kErrInvalid, "empty query batch or k == 0");
+  Status s = prepare();
+  if (!s.ok()) return s;
+  if (n_dev_ == 0) return Status::Err(kErrQuery, "index holds no data");
+  if (elem_count != (size_t)dim_)  // the reference CHECKs equal lengths (space_lp.cc:29) -> error 9
+    return Status::Err(kErrQuery, "query length " + std::to_string(elem_count) + " != index dimension " +
+                                      std::to_string(dim_));
+  if (method_ == METHOD_SEQ && k > (size_t)scan_exact_max_k())
+    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported yet");
+  if (method_ == METHOD_HNSW && k > (size_t)hnsw_max_ef()) return Status::Err(kErrTooLarge, "k too large for hnsw");
+  cudaStream_t st = stream ? stream : stream_;
+  s = stage_queries_device(d_queries, true, nq, elem_count, st);
+  if (!s.ok()) return s;
+  s = run(d_q_.p, nq, k, d_ids, d_dists, d_keys, d_counts, st);
+  if (s.ok()) stats_.queries += nq;
+  if (s.ok() && method_ == METHOD_SEQ) stats_.distance_evals += (uint64_t)nq * n_dev_;
+  return s;
+}
+
+Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_t k, const int32_t** ids,
+                        const float** dists, const int32_t** counts) {
+  if (!built_) return Status::Err(kErrBuild, "Index not built");
+  if (!queries || nq == 0 || k == 0) return Status::Err(kErrInvalid, "empty query batch or k == 0");
+  Status s = prepare();
+  if (!s.ok()) return s;
+  if (n_dev_ == 0) return Status::Err(kErrQuery, "index holds no data");
+  if (elem_count != (size_t)dim_)
+    return Status::Err(kErrQuery, "query length " + std::to_string(elem_count) + " != index dimension " +
+                                      std::to_string(dim_));
+  if (method_ == METHOD_SEQ && k > (size_t)scan_exact_max_k())
+    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported yet");
+  if (method_ == METHOD_HNSW && k > (size_t)hnsw_max_ef()) return Status::Err(kErrTooLarge, "k too large for hnsw");
+
+  const size_t out_n = nq * k;
+  if (!(s = check_cuda(d_out_ids_.ensure(out_n * 4), "cudaMalloc(out ids)")).ok()) return s;
+  if (!(s = check_cuda(d_out_dists_.ensure(out_n * 4), "cudaMalloc(out dists)")).ok()) return s;
+  if (!(s = check_cuda(d_out_counts_.ensure(nq * 4), "cudaMalloc(out counts)")).ok()) return s;
+  if (!(s = check_cuda(h_out_ids_.ensure(out_n * 4), "cudaMallocHost(ids)")).ok()) return s;
+  if (!(s = check_cuda(h_out_dists_.ensure(out_n * 4), "cudaMallocHost(dists)")).ok()) return s;
+  if (!(s = check_cuda(h_out_counts_.ensure(nq * 4), "cudaMallocHost(counts)")).ok()) return s;
+
+  cudaEventRecord(ev_[0], stream_);
+  s = stage_queries_device(queries, false, nq, elem_count, stream_);
+  if (!s.ok()) return s;
+  cudaEventRecord(ev_[1], stream_);
+  s = run(d_q_.p, nq, k, d_out_ids_.as<int32_t>(), d_out_dists_.as<float>(), nullptr, d_out_counts_.as<int32_t>(),
+          stream_);
+  if (!s.ok()) return s;
+  cudaEventRecord(ev_[2], stream_);
+  cudaMemcpyAsync(h_out_ids_.p, d_out_ids_.p, out_n * 4, cudaMemcpyDeviceToHost, stream_);
+  cudaMemcpyAsync(h_out_dists_.p, d_out_dists_.p, out_n * 4, cudaMemcpyDeviceToHost, stream_);
+  cudaMemcpyAsync(h_out_counts_.p, d_out_counts_.p, nq * 4, cudaMemcpyDeviceToHost, stream_);
+  cudaEventRecord(ev_[3], stream_);
+  s = check_cuda(cudaStreamSynchronize(stream_), "query batch");
+  if (!s.ok()) return s;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ev_[1], ev_[2]) == cudaSuccess) stats_.last_kernel_ms = ms;
+  if (cudaEventElapsedTime(&ms, ev_[0], ev_[3]) == cudaSuccess) stats_.last_total_ms = ms;
+  stats_.queries += nq;
+  if (method_ == METHOD_SEQ) stats_.distance_evals += (uint64_t)nq * n_dev_;
+  else {
+    unsigned long long c[2] = {0, 0};
+    if (cudaMemcpy(c, d_counters_.p, 16, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      stats_.distance_evals = c[0];
+      stats_.hnsw_expansions = c[1];
+    }
+  }
+  *ids = h_out_ids_.as<int32_t>();
+  *dists = h_out_dists_.as<float>();
+  *counts = h_out_counts_.as<int32_t>();
+  return Status::OK();
+}
+
+}  // namespace nb200

@@ -1,0 +1,176 @@
+// engine.h -- host side of the nmslib_b200 query engine (one Engine per index handle).
+//
+// The Engine owns the host copy of the data set (what the reference keeps as an
+// ObjectVector, nmslib_c.cpp:146), its HBM-resident mirror, the optional HNSW graph and
+// the per-batch scratch, and turns one nmslib_knn_query_batch call into ONE device
+// submission: H2D queries -> kernels -> D2H (id, distance) lists.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nb200 {
+
+enum Method : int { METHOD_SEQ = 0, METHOD_HNSW = 1 };
+
+struct Status {
+  int code = 0;  // nmslib_error_t value
+  std::string msg;
+  bool ok() const { return code == 0; }
+  static Status OK() { return Status(); }
+  static Status Err(int c, std::string m) {
+    Status s;
+    s.code = c;
+    s.msg = std::move(m);
+    return s;
+  }
+};
+
+// growable device / pinned-host buffers
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes, bool zero_new = false, cudaStream_t s = nullptr);
+  void release();
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+// Host image of the reference's optimized HNSW index (hnsw.cc:774-806)
+struct HnswGraph {
+  uint32_t total = 0;
+  int dim = 0;
+  int maxM = 0, maxM0 = 0, maxlevel = 0;
+  uint32_t enterpoint = 0;
+  int dist_func = 0;  // 1 L2Sqr16Ext, 2 L2SqrExt, 3 NormCosine, 4 NegativeDotProduct
+  std::vector<float> vectors;      // [total][dim] (cosine: unit norm)
+  std::vector<int32_t> ext_ids;    // [total]
+  std::vector<int32_t> links0;     // [total][maxM0]
+  std::vector<int32_t> links0_cnt; // [total]
+  std::vector<int32_t> upper;      // concatenated raw upper-level lists
+  std::vector<int64_t> upper_off;  // [total], -1 = level 0 only
+  bool empty() const { return total == 0; }
+};
+Status read_hnsw_file(const std::string& path, HnswGraph* out);
+// vectors / ext_ids: [total][dim] and [total] (the Engine keeps them outside the graph)
+Status write_hnsw_file(const std::string& path, const HnswGraph& g, const float* vectors,
+                       const int32_t* ext_ids);
+
+struct Stats {
+  uint64_t queries = 0, kernel_launches = 0, distance_evals = 0, hnsw_expansions = 0;
+  double last_kernel_ms = 0, last_total_ms = 0, last_scan_ms = 0, scan_ms_sum = 0;
+  uint64_t scan_count = 0;
+  uint64_t fallback_queries = 0, device_bytes = 0;
+};
+
+class Engine {
+ public:
+  Engine(Space space, Method method, bool is_u8, int device);
+  ~Engine();
+
+  // ---- ingest (host copy) ----
+  Status add_rows(const void* rows, size_t count, size_t elem_count, const int32_t* ids);
+  Status add_row_ptrs(const void* const* ptrs, size_t count, size_t elem_count, const int32_t* ids);
+  void reset();
+  size_t size() const { return n_; }
+  int dim() const { return dim_; }
+  bool is_u8() const { return is_u8_; }
+  Space space() const { return space_; }
+  Method method() const { return method_; }
+  const float* row_f32(size_t pos) const { return h_f32_.data() + pos * (size_t)dim_; }
+  const uint8_t* row_u8(size_t pos) const { return h_u8_.data() + pos * (size_t)dim_; }
+  int32_t ext_id(size_t pos) const { return h_ids_[pos]; }
+  float host_distance(size_t a, size_t b) const;  // Space::IndexTimeDistance (space.h:136-142)
+
+  // ---- index state ----
+  void mark_built(const std::vector<std::string>& index_params);
+  bool built() const { return built_; }
+  Status set_query_params(const std::vector<std::string>& params);  // hnsw.cc:474-507
+  Status import_graph(const std::string& path);
+  Status adopt_graph(HnswGraph&& g);
+  const HnswGraph& graph() const { return graph_; }
+  void set_pos_base(uint32_t b) { pos_base_ = b; }
+  Status prepare();  // lazy upload; idempotent
+
+  // ---- queries ----
+  // host in / host out: ids/dists are [nq][k] staging arrays owned by the engine
+  Status knn_host(const void* queries, size_t nq, size_t elem_count, size_t k, const int32_t** ids,
+                  const float** dists, const int32_t** counts);
+  // device in / device out
+  Status knn_device(const void* d_queries, size_t nq, size_t elem_count, size_t k, int32_t* d_ids,
+                    float* d_dists, uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream);
+
+  Stats stats();  // also resolves the dominant-kernel event pair if it has completed
+  int device() const { return device_; }
+  std::mutex& mutex() { return mu_; }
+  size_t ef() const { return ef_; }
+  int finalize_kind() const;
+
+ private:
+  Status check_cuda(cudaError_t e, const char* what);
+  Status upload_data();
+  Status upload_graph();
+  Status run(const void* d_queries_padded, size_t nq, size_t k, int32_t* d_ids, float* d_dists,
+             uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream);
+  Status stage_queries_device(const void* src, bool src_on_device, size_t nq, size_t elem_count,
+                              cudaStream_t stream);
+
+  Space space_;
+  Method method_;
+  bool is_u8_;
+  int device_;
+  int dim_ = 0;        // elements per vector
+  int row_words_ = 0;  // padded 32-bit words per device row
+  uint32_t pos_base_ = 0;
+  size_t n_ = 0;
+  bool built_ = false;
+  bool data_dirty_ = true, graph_dirty_ = true;
+  std::vector<std::string> index_params_;
+  size_t ef_ = 200;  // nmslib_c.cpp:330 default through the C ABI
+  bool ef_user_set_ = false;
+
+  std::vector<float> h_f32_;
+  std::vector<uint8_t> h_u8_;
+  std::vector<int32_t> h_ids_;
+  HnswGraph graph_;
+
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  // ring of (start, stop) event pairs around the dominant kernel; resolved lazily in stats()
+  static constexpr int kScanRing = 64;
+  cudaEvent_t scan_ev_[kScanRing][2] = {};
+  bool scan_pending_[kScanRing] = {};
+  int scan_head_ = 0;
+  int scan_cur_ = 0;
+  void scan_begin(cudaStream_t s);
+  void scan_end(cudaStream_t s);
+  DevBuf d_db_, d_aux_, d_ids_;
+  size_t n_dev_ = 0;
+  DevBuf d_links0_, d_links0_cnt_, d_upper_, d_upper_off_, d_visited_, d_epoch_, d_counters_;
+  int hnsw_slots_ = 0;
+  DevBuf d_q_, d_qaux_, d_partial_, d_keys_, d_out_ids_, d_out_dists_, d_out_counts_;
+  PinBuf h_out_ids_, h_out_dists_, h_out_counts_, h_q_;
+  Stats stats_;
+  std::mutex mu_;
+  int sm_count_ = 148;
+};
+
+int default_device();
+void set_default_device(int d);
+bool device_available();
+
+}  // namespace nb200

@@ -1,0 +1,395 @@
+// hnsw_search.cu -- K3: batched HNSW beam search, one warp per query.
+//
+// Replaces Hnsw<float>::Search(KNNQuery*) on the optimized flat index: the greedy
+// descent through the upper layers and the level-0 best-first beam of
+// Hnsw::SearchV1Merge (src/method/hnsw_distfunc_opt.cc:152-283), its SortArrBI beam
+// (include/sort_arr_bi.h:30-216), the VisitedList epoch array (include/method/hnsw.h:568-591)
+// and the inline distance kernels (hnsw_distfunc_opt_impl_inline.h:42-173, hnsw.cc:70-81).
+//
+// Beam rule kept from V1Merge: W is an ascending array of capacity max(ef, k) with a
+// "used" flag per item; while cur < min(|W|, ef): expand the first unused item; every
+// unvisited neighbour is evaluated; it is accepted iff d < worst(W) (frozen at the start
+// of the expansion) or |W| < ef; accepted items are merged into W (truncating at the
+// capacity); cur rewinds to the smallest insertion index; the answer is W[0..k).
+// For ef >= 1000 the reference switches to SearchOld (hnsw.cc:724); for k <= ef that
+// algorithm keeps the same ef-closest set and stops at the same point, so this kernel
+// serves both (tests/test_hnsw_parity.py checks ef = 1000 against the reference).
+//
+// Memory behaviour: per evaluated neighbour the warp gathers one vector with 128-bit
+// loads (lane c reads float4 c, c+32, ...), four neighbours in flight per warp; the
+// level-0 adjacency row (maxM0 ints) is one coalesced 128-byte read.  The kernel is
+// bound by HBM random-gather bandwidth, not FLOPs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nb200 {
+namespace {
+
+constexpr int WARPS = 4;          // warps (queries in flight) per block
+constexpr int MAX_EF = 2048;      // beam capacity limit (shared memory)
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int USED_BIT = 0x80000000;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+template <int KIND>
+__device__ __forceinline__ void acc4(const float4& x, const float4& q, float& s) {
+  if constexpr (KIND == 0) {
+    float d0 = x.x - q.x, d1 = x.y - q.y, d2 = x.z - q.z, d3 = x.w - q.w;
+    s = fmaf(d0, d0, s);
+    s = fmaf(d1, d1, s);
+    s = fmaf(d2, d2, s);
+    s = fmaf(d3, d3, s);
+  } else {
+    s = fmaf(x.x, q.x, s);
+    s = fmaf(x.y, q.y, s);
+    s = fmaf(x.z, q.z, s);
+    s = fmaf(x.w, q.w, s);
+  }
+}
+template <int KIND>
+__device__ __forceinline__ float fin_dist(float s) {
+  if constexpr (KIND == 0) return s;                                            // L2Sqr(16)Ext
+  else if constexpr (KIND == 1) return fmaxf(0.f, 1.f - fmaxf(-1.f, fminf(1.f, s)));  // NormCosine hnsw.cc:78-81
+  else return -s;                                                               // NegativeDotProduct :70-73
+}
+
+// distances of up to four nodes (t[g] valid for g < cnt) to the query in shared memory
+template <int KIND>
+__device__ __forceinline__ void eval4(const float* __restrict__ vectors, int row_words,
+                                      const float4* __restrict__ q4, const int t[4], int cnt, int lane,
+                                      float out[4]) {
+  const int rw4 = row_words >> 2;
+  const float4* x0 = reinterpret_cast<const float4*>(vectors + (size_t)t[0] * row_words);
+  const float4* x1 = reinterpret_cast<const float4*>(vectors + (size_t)t[cnt > 1 ? 1 : 0] * row_words);
+  const float4* x2 = reinterpret_cast<const float4*>(vectors + (size_t)t[cnt > 2 ? 2 : 0] * row_words);
+  const float4* x3 = reinterpret_cast<const float4*>(vectors + (size_t)t[cnt > 3 ? 3 : 0] * row_words);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (cnt == 4) {
+#pragma unroll 2
+    for (int c = lane; c < rw4; c += 32) {
+      const float4 a0 = __ldg(x0 + c), a1 = __ldg(x1 + c), a2 = __ldg(x2 + c), a3 = __ldg(x3 + c);
+      const float4 q = q4[c];
+      acc4<KIND>(a0, q, s0);
+      acc4<KIND>(a1, q, s1);
+      acc4<KIND>(a2, q, s2);
+      acc4<KIND>(a3, q, s3);
+    }
+  } else {
+#pragma unroll 2
+    for (int c = lane; c < rw4; c += 32) {
+      const float4 q = q4[c];
+      const float4 a0 = __ldg(x0 + c);
+      acc4<KIND>(a0, q, s0);
+      if (cnt > 1) {
+        const float4 a1 = __ldg(x1 + c);
+        acc4<KIND>(a1, q, s1);
+      }
+      if (cnt > 2) {
+        const float4 a2 = __ldg(x2 + c);
+        acc4<KIND>(a2, q, s2);
+      }
+    }
+  }
+  out[0] = fin_dist<KIND>(warp_sum(s0));
+  out[1] = fin_dist<KIND>(warp_sum(s1));
+  out[2] = fin_dist<KIND>(warp_sum(s2));
+  out[3] = fin_dist<KIND>(warp_sum(s3));
+}
+
+// ascending bitonic sort of one 64-bit key per lane
+__device__ __forceinline__ uint64_t warp_sort64(uint64_t v, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const uint64_t o = __shfl_xor_sync(FULL, v, stride);
+      const bool up = (lane & size) == 0;
+      const bool lower = (lane & stride) == 0;
+      const bool take_min = (lower == up);
+      v = take_min ? (v < o ? v : o) : (v < o ? o : v);
+    }
+  }
+  return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(WARPS * 32)
+hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq, int k, int ef, int cap,
+                   int cap_r, uint8_t* __restrict__ visited, size_t visited_stride,
+                   int* __restrict__ slot_epoch, uint64_t* __restrict__ out_keys,
+                   unsigned long long* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t per_warp = (size_t)g.row_words * 4 + (size_t)cap_r * 8 + 32 * 4;
+  unsigned char* base = smem_raw + per_warp * warp;
+  float* qv = reinterpret_cast<float*>(base);                       // row_words
+  float* wkey = qv + g.row_words;                                   // cap_r
+  int* wdat = reinterpret_cast<int*>(wkey + cap_r);                 // cap_r (bit 31 = used)
+  int* pbuf = wdat + cap_r;                                         // 32
+  const float4* q4 = reinterpret_cast<const float4*>(qv);
+
+  const int slot = blockIdx.x * WARPS + warp;
+  const int n_slots = gridDim.x * WARPS;
+  uint8_t* vis = visited + (size_t)slot * visited_stride;
+  unsigned long long n_eval = 0, n_exp = 0;
+
+  for (int qi = slot; qi < nq; qi += n_slots) {
+    // ---- visited epoch (VisitedList::reset, hnsw.h:575-582) ----
+    int epoch = 0;
+    if (lane == 0) epoch = slot_epoch[slot] + 1;
+    epoch = __shfl_sync(FULL, epoch, 0);
+    if (epoch > 255) {
+      uint4 z = make_uint4(0, 0, 0, 0);
+      for (size_t o = (size_t)lane * 16; o < visited_stride; o += 32 * 16) *reinterpret_cast<uint4*>(vis + o) = z;
+      epoch = 1;
+    }
+    if (lane == 0) slot_epoch[slot] = epoch;
+    const uint8_t ep = (uint8_t)epoch;
+    __syncwarp();
+
+    // ---- stage the query (cosine: NormalizeVect, hnsw.h:486-497) ----
+    const float* qsrc = queries + (size_t)qi * g.row_words;
+    float ss = 0.f;
+    for (int c = lane; c < g.row_words; c += 32) {
+      const float v = qsrc[c];
+      qv[c] = v;
+      ss = fmaf(v, v, ss);
+    }
+    if constexpr (KIND == 1) {
+      ss = warp_sum(ss);
+      if (ss != 0.f) {
+        const float sc = 1.f / sqrtf(ss);
+        for (int c = lane; c < g.row_words; c += 32) qv[c] *= sc;
+      }
+    }
+    __syncwarp();
+
+    // ---- greedy descent through the upper layers (hnsw_distfunc_opt.cc:168-198) ----
+    int cur_node = g.enterpoint;
+    float cur_dist;
+    {
+      int t[4] = {cur_node, 0, 0, 0};
+      float d[4];
+      eval4<KIND>(g.vectors, g.row_words, q4, t, 1, lane, d);
+      cur_dist = d[0];
+      ++n_eval;
+    }
+    for (int level = g.maxlevel; level > 0; --level) {
+      bool changed = true;
+      while (changed) {
+        changed = false;
+        const int32_t* lk = g.upper + g.upper_off[cur_node] + (size_t)(level - 1) * (g.maxM + 1);
+        const int size = lk[0];
+        for (int b0 = 0; b0 < size; b0 += 32) {
+          const int nb = (b0 + lane < size) ? lk[1 + b0 + lane] : -1;
+          unsigned mask = __ballot_sync(FULL, nb >= 0);
+          float my_d = __int_as_float(0x7F800000);
+          while (mask) {
+            int t[4], src[4], cnt = 0;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              src[gq] = 0;
+              t[gq] = 0;
+              if (mask) {
+                src[gq] = __ffs(mask) - 1;
+                mask &= mask - 1;
+                ++cnt;
+              }
+            }
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
+            float d[4];
+            eval4<KIND>(g.vectors, g.row_words, q4, t, cnt, lane, d);
+            n_eval += cnt;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq)
+              if (gq < cnt && lane == src[gq]) my_d = d[gq];
+          }
+          // sequential "if (d < curdist)" over j == first minimum over the list
+          uint64_t best = ((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)lane;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(FULL, best, o);
+            best = other < best ? other : best;
+          }
+          const int bl = (int)(best & 31u);
+          const float bd = __shfl_sync(FULL, my_d, bl);
+          const int bn = __shfl_sync(FULL, nb, bl);
+          if (bn >= 0 && bd < cur_dist) {
+            cur_dist = bd;
+            cur_node = bn;
+            changed = true;
+          }
+        }
+      }
+    }
+
+    // ---- level-0 beam (hnsw_distfunc_opt.cc:200-274) ----
+    int n_w = 1, cur = 0;
+    if (lane == 0) {
+      wkey[0] = cur_dist;
+      wdat[0] = cur_node;
+      vis[cur_node] = ep;
+    }
+    __syncwarp();
+
+    while (cur < min(n_w, ef)) {
+      const int node = wdat[cur] & ~USED_BIT;
+      __syncwarp();
+      if (lane == 0) wdat[cur] |= USED_BIT;
+      ++cur;
+      ++n_exp;
+      const float top_key = wkey[n_w - 1];
+      const bool grow = n_w < ef;
+      __syncwarp();
+      const int size = g.links0_cnt[node];
+      for (int b0 = 0; b0 < size; b0 += 32) {
+        const int nb = (b0 + lane < size) ? g.links0[(size_t)node * g.maxM0 + b0 + lane] : -1;
+        bool fresh = false;
+        if (nb >= 0) {
+          fresh = vis[nb] != ep;
+          if (fresh) vis[nb] = ep;
+        }
+        unsigned mask = __ballot_sync(FULL, fresh);
+        float my_d = __int_as_float(0x7F800000);
+        while (mask) {
+          int t[4], src[4], cnt = 0;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            src[gq] = 0;
+            t[gq] = 0;
+            if (mask) {
+              src[gq] = __ffs(mask) - 1;
+              mask &= mask - 1;
+              ++cnt;
+            }
+          }
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
+          float d[4];
+          eval4<KIND>(g.vectors, g.row_words, q4, t, cnt, lane, d);
+          n_eval += cnt;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq)
+            if (gq < cnt && lane == src[gq]) my_d = d[gq];
+        }
+        const bool accept = fresh && (my_d < top_key || grow);
+        const int m = __popc(__ballot_sync(FULL, accept));
+        if (m == 0) continue;
+
+        // sort the accepted candidates; lane i < m ends with the i-th smallest
+        uint64_t item = accept ? (((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)nb) : KEY_MAX;
+        item = warp_sort64(item, lane);
+        const float d_i = f32_from_ordered((uint32_t)(item >> 32));
+        const int t_i = (int)(uint32_t)item;
+        // p_i = number of beam items with key <= d_i (new items go after equal old ones)
+        int p_i = n_w;
+        if (lane < m) {
+          int lo = 0, hi = n_w;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (wkey[mid] <= d_i) lo = mid + 1; else hi = mid;
+          }
+          p_i = lo;
+        }
+        pbuf[lane] = lane < m ? p_i : 0x7FFFFFFF;
+        __syncwarp();
+        const int p0 = pbuf[0];
+        // shift the tail of the beam, highest chunk first
+        if (p0 < n_w) {
+          for (int cb = ((n_w - 1) >> 5) << 5; cb >= ((p0 >> 5) << 5); cb -= 32) {
+            const int a = cb + lane;
+            const bool valid = a < n_w && a >= p0;
+            float ka = 0.f;
+            int da = 0, c = 0;
+            if (valid) {
+              ka = wkey[a];
+              da = wdat[a];
+              for (int i = 0; i < m; ++i) c += (pbuf[i] <= a) ? 1 : 0;
+            }
+            __syncwarp();
+            if (valid && a + c < cap) {
+              wkey[a + c] = ka;
+              wdat[a + c] = da;
+            }
+            __syncwarp();
+          }
+        }
+        if (lane < m && p_i + lane < cap) {
+          wkey[p_i + lane] = d_i;
+          wdat[p_i + lane] = t_i;
+        }
+        n_w = min(cap, n_w + m);
+        if (p0 < cur) cur = p0;  // p_0 + 0 is the smallest insertion index (sort_arr_bi.h:159-199)
+        __syncwarp();
+      }
+      // advance to the first unused item (hnsw_distfunc_opt.cc:272)
+      while (cur < n_w) {
+        const int a = cur + lane;
+        const bool unused = a < n_w && !(wdat[a] & USED_BIT);
+        const unsigned um = __ballot_sync(FULL, unused);
+        if (um) {
+          cur += __ffs(um) - 1;
+          break;
+        }
+        cur += 32;
+      }
+      if (cur > n_w) cur = n_w;
+    }
+
+    // ---- W[0..k) -> keys (hnsw_distfunc_opt.cc:276-281) ----
+    __syncwarp();
+    for (int e = lane; e < k; e += 32) {
+      uint64_t key = KEY_MAX;
+      if (e < n_w) key = make_key(f32_ordered(wkey[e]), (uint32_t)(wdat[e] & ~USED_BIT));
+      out_keys[(size_t)qi * k + e] = key;
+    }
+    __syncwarp();
+  }
+  if (counters && lane == 0) {
+    atomicAdd(&counters[0], n_eval);
+    atomicAdd(&counters[1], n_exp);
+  }
+}
+
+}  // namespace
+
+int hnsw_max_ef() { return MAX_EF; }
+int hnsw_warps_per_block() { return WARPS; }
+
+cudaError_t launch_hnsw_search(const HnswDeviceGraph& g, const float* queries, int nq, int k, int ef,
+                               uint8_t* visited, int* slot_epoch, int slots, uint64_t* out_keys,
+                               unsigned long long* counters, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  const int cap = ef > k ? ef : k;
+  if (cap > MAX_EF) return cudaErrorInvalidValue;
+  const int cap_r = (cap + 31) / 32 * 32;
+  const size_t per_warp = (size_t)g.row_words * 4 + (size_t)cap_r * 8 + 32 * 4;
+  const size_t smem = per_warp * WARPS;
+  int blocks = slots / WARPS;
+  const int need = (nq + WARPS - 1) / WARPS;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  const size_t vstride = round_up((size_t)g.n, 16);
+  cudaError_t e;
+#define NB_HNSW(KIND)                                                                                    \
+  e = cudaFuncSetAttribute(hnsw_search_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e != cudaSuccess) return e;                                                                        \
+  hnsw_search_kernel<KIND><<<blocks, WARPS * 32, smem, stream>>>(g, queries, nq, k, ef, cap, cap_r, visited, \
+                                                                 vstride, slot_epoch, out_keys, counters);
+  switch (g.dist_kind) {
+    case 0: NB_HNSW(0); break;
+    case 1: NB_HNSW(1); break;
+    case 2: NB_HNSW(2); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef NB_HNSW
+  return cudaGetLastError();
+}
+
+}  // namespace nb200

@@ -1,0 +1,56 @@
+// kernels.h -- host-callable launchers of the nmslib_b200 CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nb200 {
+
+// accumulate/epilogue flavours of the exact scan kernel
+enum ScanMode : int { SCAN_L2 = 0, SCAN_NEGDOT = 1, SCAN_COSINE = 2, SCAN_SIFT = 3 };
+
+// ---- scan_exact.cu -------------------------------------------------------------------
+// db: [n_pad][row_words] words (float32 or packed uint8), rows beyond n are zero padding up
+// to a multiple of scan_exact_block_points(); queries alike, padded to a multiple of
+// scan_exact_block_queries().  row_words must be a multiple of scan_exact_stage_words().
+// partial: [nq][n_split][k] keys, each split's list ascending, KEY_MAX padded.
+cudaError_t launch_scan_exact(int mode, const void* db, const void* queries, const void* db_aux,
+                              const void* q_aux, int n, int nq, int row_words, int k, uint32_t pos_base,
+                              uint64_t* partial, int n_split, int tiles_per_split, cudaStream_t stream);
+int scan_exact_max_k();
+int scan_exact_block_queries();
+int scan_exact_block_points();
+int scan_exact_stage_words();
+cudaError_t launch_row_aux(bool is_u8, const void* rows, int n, int row_words, void* out, cudaStream_t stream);
+
+// ---- topk_merge.cu -------------------------------------------------------------------
+// Merge `lists` ascending key lists per query into the k best and finalise them.
+// key(l, q, e) = keys[l * list_stride + q * query_stride + e]; ids_in (same layout) is
+// optional -- when NULL the id is ext_ids[pos - pos_base] (ext_ids NULL: id = pos).
+// Outputs are [nq][k]; out_keys / out_counts may be NULL.
+cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int lists, size_t list_stride,
+                              size_t query_stride, int nq, int k, int finalize, const int32_t* ext_ids,
+                              uint32_t pos_base, uint64_t* out_keys, int32_t* out_ids, float* out_dists,
+                              int32_t* out_counts, cudaStream_t stream);
+int merge_topk_max_items();
+
+// ---- hnsw_search.cu ------------------------------------------------------------------
+struct HnswDeviceGraph {
+  const float* vectors;      // [n][row_words] (cosine: unit-norm rows, as the reference stores them)
+  const int32_t* links0;     // [n][maxM0]
+  const int32_t* links0_cnt; // [n]
+  const int32_t* upper;      // concatenated upper-level lists: per level (maxM+1) ints, count first
+  const int64_t* upper_off;  // [n] offset into `upper`, -1 when the node lives on level 0 only
+  const int32_t* ext_ids;    // [n]
+  int n, dim, row_words, maxM, maxM0, maxlevel, enterpoint;
+  int dist_kind;             // 0 squared L2, 1 cosine on unit vectors, 2 negative dot product
+};
+// One warp per query.  visited: [slots][n] epoch bytes, epochs: [slots] current epoch.
+// out_keys: [nq][k] (ordered(distance) << 32 | internal position), counters: [2] atomics
+// (distance evaluations, expansions), may be NULL.
+cudaError_t launch_hnsw_search(const HnswDeviceGraph& g, const float* queries, int nq, int k, int ef,
+                               uint8_t* visited, int* slot_epoch, int slots, uint64_t* out_keys,
+                               unsigned long long* counters, cudaStream_t stream);
+int hnsw_max_ef();
+int hnsw_warps_per_block();
+
+}  // namespace nb200

@@ -1,0 +1,124 @@
+// topk_merge.cu -- K4: k-way merge of sorted (distance, position) key lists + result
+// finalisation.  Replaces the per-thread queue merge of SeqSearch (seqsearch.cc:151-175),
+// and extract_knn_results (nmslib_c.cpp:293-328: pop, reverse, cast to float, external id).
+// It is used three ways: (1) to combine the per-split lists of one scan launch, (2) to
+// combine the per-GPU lists after the NVLink all-gather, (3) with lists == 1
+// as the plain "decode keys -> (id, float distance)" finaliser.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nb200 {
+namespace {
+
+constexpr int MAX_ITEMS = 8192;  // keys per query that one CTA sorts in shared memory
+
+__device__ __forceinline__ float decode_dist(uint64_t key, int finalize) {
+  const uint32_t hi = (uint32_t)(key >> 32);
+  if (finalize == FIN_INT) return (float)i32_from_ordered(hi);   // nmslib_c.cpp:317 int -> float
+  const float v = f32_from_ordered(hi);
+  return finalize == FIN_SQRT ? sqrtf(v) : v;                    // distcomp_lp.cc:368-371
+}
+
+__global__ void merge_topk_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ ids_in,
+                                  int lists, size_t list_stride, size_t query_stride, int nq, int k,
+                                  int items_pow2, int finalize, const int32_t* __restrict__ ext_ids,
+                                  uint32_t pos_base, uint64_t* __restrict__ out_keys,
+                                  int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
+                                  int32_t* __restrict__ out_counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
+  int32_t* sid = reinterpret_cast<int32_t*>(sk + items_pow2);
+  const int q = blockIdx.x;
+  const int items = lists * k;
+
+  for (int t = threadIdx.x; t < items_pow2; t += blockDim.x) {
+    uint64_t key = KEY_MAX;
+    int32_t id = -1;
+    if (t < items) {
+      const int l = t / k, e = t - l * k;
+      const size_t off = (size_t)l * list_stride + (size_t)q * query_stride + e;
+      key = keys[off];
+      if (ids_in) id = ids_in[off];
+    }
+    sk[t] = key;
+    sid[t] = id;
+  }
+  __syncthreads();
+
+  if (lists > 1) {  // bitonic sort, ascending
+    for (int size = 2; size <= items_pow2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = threadIdx.x; t < items_pow2 / 2; t += blockDim.x) {
+          const int lo = 2 * t - (t & (stride - 1));
+          const int hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const uint64_t a = sk[lo], b = sk[hi];
+          if ((a > b) == up) {
+            sk[lo] = b;
+            sk[hi] = a;
+            const int32_t ia = sid[lo];
+            sid[lo] = sid[hi];
+            sid[hi] = ia;
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+  int local_cnt = 0;
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    const uint64_t key = e < items_pow2 ? sk[e] : KEY_MAX;
+    const size_t o = (size_t)q * k + e;
+    int32_t id = -1;
+    float d = __int_as_float(0x7F800000);
+    if (key != KEY_MAX) {
+      ++local_cnt;
+      d = decode_dist(key, finalize);
+      if (ids_in) id = sid[e];
+      else {
+        const uint32_t pos = (uint32_t)key;
+        id = ext_ids ? ext_ids[pos - pos_base] : (int32_t)pos;
+      }
+    }
+    if (out_keys) out_keys[o] = key;
+    if (out_ids) out_ids[o] = id;
+    if (out_dists) out_dists[o] = d;
+  }
+  if (out_counts) {
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    if (local_cnt) atomicAdd(&total, local_cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) out_counts[q] = total;
+  }
+}
+
+}  // namespace
+
+int merge_topk_max_items() { return MAX_ITEMS; }
+
+cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int lists, size_t list_stride,
+                              size_t query_stride, int nq, int k, int finalize, const int32_t* ext_ids,
+                              uint32_t pos_base, uint64_t* out_keys, int32_t* out_ids, float* out_dists,
+                              int32_t* out_counts, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  const int items = lists * k;
+  if (items > MAX_ITEMS) return cudaErrorInvalidValue;
+  int p2 = 1;
+  while (p2 < items) p2 <<= 1;
+  int threads = p2 / 2;
+  if (threads < 32) threads = 32;
+  if (threads > 256) threads = 256;
+  const size_t smem = (size_t)p2 * 12 + 16;
+  cudaError_t e =
+      cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_ITEMS * 12 + 16));
+  if (e != cudaSuccess) return e;
+  merge_topk_kernel<<<nq, threads, smem, stream>>>(keys, ids_in, lists, list_stride, query_stride, nq, k, p2,
+                                                   finalize, ext_ids, pos_base, out_keys, out_ids, out_dists,
+                                                   out_counts);
+  return cudaGetLastError();
+}
+
+}  // namespace nb200

@@ -1,0 +1,61 @@
+"""Shared checkers for the parity tests."""
+from __future__ import annotations
+
+import numpy as np
+
+RTOL = 1e-5   # BASELINE.json north_star: ids exact except at ties within 1e-5 relative distance
+ATOL = 1e-6   # +1e-6 absolute for values near 0 (the reference's cosine clamps at 0)
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    with np.errstate(invalid="ignore"):
+        return both_inf | (np.abs(a - b) <= rtol * np.abs(b) + atol)
+
+
+def assert_knn_matches(ids, dists, counts, ref_ids, ref_dists, ref_counts, *, exact=False, dist_of=None,
+                       what=""):
+    """Tie-aware comparison of two kNN answers.
+
+    exact=True  (integer spaces): distances bit-equal; ids equal except inside groups of EQUAL
+                distance (the reference orders ties by heap address).
+    exact=False (float spaces): |d - d_ref| <= RTOL*|d_ref| + ATOL; ids equal except inside groups
+                of distances that are within that tolerance of each other.
+    dist_of(q, id) -> distance, optional: used to validate an id that the reference list does not
+                contain at all (possible only in the tie group cut by k).
+    """
+    ids, ref_ids = np.asarray(ids), np.asarray(ref_ids)
+    dists, ref_dists = np.asarray(dists), np.asarray(ref_dists)
+    nq = ref_ids.shape[0]
+    assert np.array_equal(np.asarray(counts).reshape(-1), np.asarray(ref_counts).reshape(-1)), f"{what}: counts differ"
+    rtol, atol = (0.0, 0.0) if exact else (RTOL, ATOL)
+    for q in range(nq):
+        c = int(ref_counts[q])
+        d, r = dists[q, :c], ref_dists[q, :c]
+        ok = close(d, r, rtol, atol)
+        assert ok.all(), f"{what}: query {q} distances differ: ours {d[~ok][:4]} ref {r[~ok][:4]}"
+        assert np.all(np.diff(d.astype(np.float64)) >= 0), f"{what}: query {q} distances not ascending"
+        i_ours, i_ref = ids[q, :c], ref_ids[q, :c]
+        for j in np.nonzero(i_ours != i_ref)[0]:
+            # (a) a swap inside a tie group of the reference list
+            where = np.nonzero(i_ref == i_ours[j])[0]
+            if where.size and close(r[where[0]], r[j], rtol, atol):
+                continue
+            # (b) a different member of the tie group that k cuts through
+            if c > 0 and close(r[j], r[c - 1], rtol, atol) and not where.size:
+                if dist_of is not None:
+                    assert close(dist_of(q, int(i_ours[j])), r[j], rtol, atol), \
+                        f"{what}: query {q} rank {j}: id {i_ours[j]} is not tied with the reference's k-th"
+                continue
+            raise AssertionError(f"{what}: query {q} rank {j}: id {i_ours[j]} != reference {i_ref[j]} "
+                                 f"(d={d[j]!r}, ref d={r[j]!r})")
+
+
+def recall(ids, exact_ids):
+    """|approx ∩ exact| / |exact| (eval_metrics.h:112-128), averaged over queries."""
+    hits = 0
+    for a, e in zip(np.asarray(ids), np.asarray(exact_ids)):
+        hits += len(set(a[a >= 0].tolist()) & set(e[e >= 0].tolist()))
+    return hits / float(np.sum(np.asarray(exact_ids) >= 0))

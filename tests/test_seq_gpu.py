@@ -1,0 +1,211 @@
+"""Parity of the CUDA sequential-search path (through the C ABI, host buffers in / host buffers
+out) against the golden fixtures produced by the reference and against the oracle on seeded
+inputs.  Integer space: bit-exact.  Float spaces: ids exact except within ties of 1e-5 relative
+(+1e-6 absolute) distance -- helpers.RTOL / ATOL."""
+import glob
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import nmslib_zig_b200 as nb
+from helpers import assert_knn_matches
+from nmslib_zig_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+SEQ_CASES = sorted(Path(p).stem for p in glob.glob(str(GOLDEN / "seq_*.npz")))
+
+
+def make_index(space, data, ids=None, method="seq_search"):
+    u8 = space == "l2sqr_sift"
+    idx = nb.Index(space, None, method, "DenseUInt8Vector" if u8 else "DenseVector", "Int" if u8 else "Float")
+    (idx.addUInt8Batch if u8 else idx.addDenseBatch)(data, ids)
+    idx.buildIndex()
+    return idx
+
+
+def check_against_oracle(space, data, queries, k, ids=None, what=""):
+    idx = make_index(space, data, ids)
+    r = idx.knnQueryBatch(queries, k)
+    oi, od, oc = O.seq_knn(space, data, queries, k, ids)
+    ids_arr = np.arange(len(data)) if ids is None else np.asarray(ids)
+    pos_of = {int(v): i for i, v in enumerate(ids_arr)}
+    dist_of = lambda q, i: O.pair_distance(space, data[pos_of[i]], queries[q])
+    assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, exact=(space == "l2sqr_sift"), dist_of=dist_of,
+                       what=what or space)
+    idx.deinit()
+    return r
+
+
+@pytest.mark.parametrize("case", SEQ_CASES)
+def test_matches_reference_golden(case):
+    g = np.load(GOLDEN / f"{case}.npz")
+    space, k = str(g["space"]), int(g["k"])
+    idx = make_index(space, g["data"], g["ids"])
+    r = idx.knnQueryBatch(g["queries"], k)
+    ref_d = g["ref_dists"]
+    if space == "l2sqr":  # golden distances come from the reference's l2
+        ref_d = (ref_d.astype(np.float64) ** 2).astype(np.float32)
+    pos_of = {int(v): i for i, v in enumerate(g["ids"])}
+    dist_of = lambda q, i: O.pair_distance(space, g["data"][pos_of[i]], g["queries"][q])
+    assert_knn_matches(r.ids, r.distances, r.sizes, g["ref_ids"], ref_d, g["ref_counts"],
+                       exact=(space == "l2sqr_sift"), dist_of=dist_of, what=case)
+    # the single-query entry (lib.zig knnQuery -> get_size + fill) is a batch of one
+    one = idx.knnQuery(g["queries"][0], k)
+    assert np.array_equal(one.ids, r.ids[0, : r.sizes[0]]) and np.array_equal(one.distances, r.distances[0, : r.sizes[0]])
+    idx.deinit()
+
+
+def test_reference_own_test_vectors_through_seq_search():
+    """lib.zig:1292-1299 assertions (ids[0] == 10, distances[0] ~ 0, k = 2)."""
+    idx = make_index("l2", np.eye(4, dtype=np.float32)[:3], [10, 20, 30])
+    r = idx.knnQuery(np.array([1, 0, 0, 0], np.float32), 2)
+    assert len(r.ids) == 2 and r.ids[0] == 10 and abs(r.distances[0]) < 1e-4
+    assert abs(r.distances[1] - np.sqrt(2.0)) < 1e-5
+    idx.deinit()
+
+
+@pytest.mark.parametrize("space,n,dim,nq,k", [
+    ("l2", 10_000, 128, 1_000, 10),          # BASELINE config 1 at full size
+    ("l2", 3_001, 19, 77, 7),                # ragged: dim % 4 != 0, n % 128 != 0, nq % 128 != 0
+    ("l2sqr", 20_000, 128, 300, 10),
+    ("cosinesimil", 5_000, 960, 64, 10),     # GIST-shaped dim
+    ("cosinesimil", 4_000, 33, 130, 25),
+    ("negdotprod", 6_000, 768, 96, 100),     # config-5 shape: k = 100
+    ("negdotprod", 2_000, 5, 40, 3),
+])
+def test_float_spaces_match_oracle(space, n, dim, nq, k):
+    if space == "negdotprod" and dim == 768:
+        data, q = synth.embedding_like(n, dim, 9), synth.embedding_like(nq, dim, 10)
+    elif space == "l2sqr":
+        data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
+    elif dim == 960:
+        data, q = synth.gist_like(n, dim, 5), synth.gist_like(nq, dim, 6)
+    else:
+        data, q = synth.uniform(n, dim, 1) - 0.25, synth.uniform(nq, dim, 2) - 0.25
+    ids = (np.arange(n, dtype=np.int32) * 3 + 11)
+    check_against_oracle(space, data, q, k, ids, what=f"{space} {n}x{dim} q{nq} k{k}")
+
+
+@pytest.mark.parametrize("n,nq,k", [(50_000, 256, 10), (1_000, 3, 1), (129, 129, 100)])
+def test_sift_uint8_bit_exact(n, nq, k):
+    data, q = synth.sift_like_u8(n, 7), synth.sift_like_u8(nq, 8)
+    r = check_against_oracle("l2sqr_sift", data, q, k, what=f"sift {n} q{nq} k{k}")
+    assert r.distances.dtype == np.float32 and np.all(r.distances == np.round(r.distances))
+
+
+def test_sift_extreme_values_do_not_overflow():
+    """max distance 128*255^2 = 8 323 200 < 2^24 stays exact as float."""
+    data = np.zeros((300, 128), np.uint8)
+    data[1::2] = 255
+    q = np.stack([np.zeros(128, np.uint8), np.full(128, 255, np.uint8)])
+    r = check_against_oracle("l2sqr_sift", data, q, 300)
+    assert r.distances[0, -1] == 128 * 255 * 255
+
+
+def test_duplicates_zero_rows_and_tie_order():
+    """Exact ties resolve by insertion position, like the reference does in practice:
+    with position ids the answer must equal the oracle's id for id, not just up to ties."""
+    d = synth.uniform(1000, 16, 21)
+    d[500:520] = d[10:30]
+    d[700] = 0.0
+    q = np.concatenate([d[10:20], np.zeros((1, 16), np.float32)])
+    for space in ("l2", "l2sqr", "negdotprod", "cosinesimil"):
+        idx = make_index(space, d)
+        r = idx.knnQueryBatch(q, 8)
+        oi, od, oc = O.seq_knn(space, d, q, 8)
+        assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, what=f"ties/{space}")
+        if space in ("l2", "l2sqr"):
+            assert np.array_equal(r.ids[:10, 0], np.arange(10, 20))          # the earlier duplicate wins
+            assert np.array_equal(r.ids[:10, 1], np.arange(500, 510))
+        idx.deinit()
+    du = synth.sift_like_u8(600, 23)
+    du[300:340] = du[0:40]
+    idx = make_index("l2sqr_sift", du)
+    r = idx.knnQueryBatch(du[:16], 5)
+    oi, od, oc = O.seq_knn("l2sqr_sift", du, du[:16], 5)
+    assert np.array_equal(r.ids, oi) and np.array_equal(r.distances, od)      # bit-exact incl. tie order
+    idx.deinit()
+
+
+def test_k_larger_than_n_and_tiny_indexes():
+    d = synth.uniform(7, 5, 31)
+    q = synth.uniform(3, 5, 32)
+    r = check_against_oracle("l2", d, q, 10)
+    assert np.all(r.sizes == 7)
+    assert np.all(r.ids[:, 7:] == -1)
+    check_against_oracle("cosinesimil", d[:1], q, 4)
+
+
+def test_incremental_add_reset_and_repeat_batches():
+    d = synth.uniform(2_000, 24, 41)
+    q = synth.uniform(50, 24, 42)
+    idx = make_index("l2", d[:1000])
+    r1 = idx.knnQueryBatch(q, 5)
+    oi, od, oc = O.seq_knn("l2", d[:1000], q, 5)
+    assert_knn_matches(r1.ids, r1.distances, r1.sizes, oi, od, oc, what="first half")
+    idx.addDenseBatch(d[1000:], np.arange(1000, 2000, dtype=np.int32))       # re-upload on next query
+    r2 = idx.knnQueryBatch(q, 5)
+    oi, od, oc = O.seq_knn("l2", d, q, 5)
+    assert_knn_matches(r2.ids, r2.distances, r2.sizes, oi, od, oc, what="both halves")
+    r3 = idx.knnQueryBatch(q[:7], 5)                                         # smaller batch reuses scratch
+    assert np.array_equal(r3.ids, r2.ids[:7])
+    idx.reset()
+    assert idx.dataQty() == 0
+    idx.addDenseBatch(d[:10])
+    idx.buildIndex()
+    assert idx.knnQueryBatch(q[:2], 3).sizes.tolist() == [3, 3]
+    idx.deinit()
+
+
+def test_query_errors_like_the_reference():
+    d = synth.uniform(100, 8, 51)
+    idx = make_index("l2", d)
+    with pytest.raises(nb.NmslibError) as e:
+        idx.knnQueryBatch(synth.uniform(4, 9, 52), 3)        # length mismatch: CHECK in space_lp.cc:29 -> error 9
+    assert e.value.name == "QueryExecutionFailed"
+    with pytest.raises(nb.NmslibError) as e:
+        idx.knnQuery(d[0], 0)
+    assert e.value.name == "InvalidArgument"
+    idx.deinit()
+    unbuilt = nb.Index("l2", None, "seq_search")
+    unbuilt.addDenseBatch(d)
+    unbuilt.built = True                                     # bypass the host-side auto build (lib.zig:890)
+    with pytest.raises(nb.NmslibError) as e:
+        unbuilt.knnQueryBatch(d[:2], 3)
+    assert e.value.name == "IndexBuildFailed"                # nmslib_c.cpp:963-967
+    unbuilt.deinit()
+
+
+def test_stats_report_our_kernels_ran():
+    d = synth.uniform(3000, 32, 61)
+    idx = make_index("l2", d)
+    idx.knnQueryBatch(d[:100], 5)
+    s = idx.stats()
+    assert s["kernel_launches"] >= 2 and s["queries"] == 100 and s["distance_evals"] == 100 * 3000
+    assert s["last_kernel_ms"] > 0 and s["last_total_ms"] >= s["last_kernel_ms"] and s["device_bytes"] > 0
+    idx.deinit()
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 at full size (1 M x 128, 10 K queries, k = 10, l2sqr): size-independent
+    properties + an oracle check on a query sample."""
+    data, q = synth.make("c2")
+    q[:64] = data[1000:1064]                                  # planted exact matches
+    idx = make_index("l2sqr", data)
+    r = idx.knnQueryBatch(q, 10)
+    assert np.all(r.sizes == 10)
+    assert np.all(np.diff(r.distances, axis=1) >= 0)          # sortedness
+    assert np.all(r.distances[:64, 0] == 0) and np.array_equal(r.ids[:64, 0], np.arange(1000, 1064))
+    assert np.all(r.distances == np.round(r.distances))       # integer-valued inputs -> integer distances
+    for row in r.ids[::97]:
+        assert len(set(row.tolist())) == 10                   # no id twice
+    sample = np.arange(0, 10_000, 313)
+    oi, od, oc = O.seq_knn("l2sqr", data, q[sample], 10)
+    assert_knn_matches(r.ids[sample], r.distances[sample], r.sizes[sample], oi, od, oc, what="c2 sample")
+    perm = np.random.default_rng(0).permutation(2048)         # permutation invariance of the batch
+    r2 = idx.knnQueryBatch(q[:2048][perm], 10)
+    assert np.array_equal(r2.ids, r.ids[:2048][perm]) and np.array_equal(r2.distances, r.distances[:2048][perm])
+    idx.deinit()
