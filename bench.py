@@ -194,7 +194,10 @@ def main():
         g_ids = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
         o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
         o_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated non-default stream: the C ABI treats a NULL stream as "the engine's own stream", and CUDA
+    # events only see the stream they are recorded on
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
 
     def step_device():
         idx.knnDevice(d_q.data_ptr(), nq, dim, k, d_ids.data_ptr(), d_dists.data_ptr(), d_keys.data_ptr(),

@@ -77,15 +77,19 @@ void PinBuf::release() {
 }
 
 Engine::Engine(Space space, Method method, bool is_u8, int device)
-    : space_(space), method_(method), is_u8_(is_u8), device_(device) {}
+    : space_(space), method_(method), is_u8_(is_u8), device_(device) {
+  const char* fe = getenv("NB200_FORCE_EXACT");  // debugging / A-B switch: CUDA-core exact scan only
+  force_exact_ = fe && fe[0] == '1';
+}
 
 Engine::~Engine() {
   if (stream_ || d_db_.p) cudaSetDevice(device_);
   for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
                     &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
-                    &d_out_counts_})
+                    &d_out_counts_, &d_bias_, &d_db_unit_, &d_flags_, &d_qa_, &d_cand_, &d_cand_cnt_, &d_cand_thr_,
+                    &d_tc_keys_, &d_cert_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_})
     b->release();
-  for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_}) b->release();
+  for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_}) b->release();
   for (auto& e : ev_)
     if (e) cudaEventDestroy(e);
   for (auto& pr : scan_ev_)
@@ -328,7 +332,8 @@ Status Engine::upload_data() {
   const int bn = scan_exact_block_points();
   // HBM layout: row-major [n_pad][row_words] 32-bit words, rows zero padded to a whole
   // pipeline stage (64 B) and the row count to a whole tile, so no kernel needs edge code.
-  row_words_ = (int)round_up(is_u8_ ? (size_t)dim_ / 4 : (size_t)dim_, stage);
+  // float rows are padded to 128 bytes (one TMA / UMMA swizzle row of the tensor-core scan)
+  row_words_ = (int)round_up(is_u8_ ? (size_t)dim_ / 4 : (size_t)dim_, is_u8_ ? stage : tc_kblock_words());
   if (is_u8_ && dim_ % 4) return Status::Err(kErrInvalid, "uint8 dimension must be a multiple of 4");
   const size_t n_pad = round_up(n_, bn);
   const size_t row_bytes = (size_t)row_words_ * 4;
@@ -352,11 +357,39 @@ Status Engine::upload_data() {
     if (!s.ok()) return s;
     ++stats_.kernel_launches;
   }
+  x_max_ = 0.f;
+  if (!is_u8_ && method_ == METHOD_SEQ) {
+    // operands of the tensor-core scan: bias (|x|^2 or 0, +inf on padding rows), the unit-norm copy
+    // for cosine, max operand-row norm and the "is TF32-exact" flag (both feed the certificate)
+    const int mode = space_ == SPACE_COSINE ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
+    if (!(s = check_cuda(d_bias_.ensure(n_pad * 4), "cudaMalloc(bias)")).ok()) return s;
+    if (!(s = check_cuda(d_flags_.ensure(16), "cudaMalloc(flags)")).ok()) return s;
+    if (!(s = check_cuda(cudaMemsetAsync(d_flags_.p, 0, 16, stream_), "memset(flags)")).ok()) return s;
+    float* unit = nullptr;
+    if (mode == SCAN_COSINE) {
+      if (!(s = check_cuda(d_db_unit_.ensure(n_pad * row_bytes), "cudaMalloc(unit rows)")).ok()) return s;
+      if (!(s = check_cuda(cudaMemsetAsync(d_db_unit_.p, 0, n_pad * row_bytes, stream_), "memset(unit)")).ok()) return s;
+      unit = d_db_unit_.as<float>();
+    }
+    // flags layout: [0] database inexact, [1] query batch inexact, [2] max-norm bits
+    s = check_cuda(launch_tc_prep_db(d_db_.as<float>(), (int)n_, (int)n_pad, row_words_, mode, d_bias_.as<float>(),
+                                     mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, unit,
+                                     d_flags_.as<unsigned>() + 2, d_flags_.as<int>(), stream_),
+                   "tc_prep_db");
+    if (!s.ok()) return s;
+    ++stats_.kernel_launches;
+    unsigned bits = 0;
+    s = check_cuda(cudaMemcpyAsync(&bits, d_flags_.as<unsigned>() + 2, 4, cudaMemcpyDeviceToHost, stream_), "D2H(xmax)");
+    if (!s.ok()) return s;
+    s = check_cuda(cudaStreamSynchronize(stream_), "upload sync");
+    if (!s.ok()) return s;
+    memcpy(&x_max_, &bits, 4);
+  }
   s = check_cuda(cudaStreamSynchronize(stream_), "upload sync");
   if (!s.ok()) return s;
   n_dev_ = n_;
   data_dirty_ = false;
-  stats_.device_bytes = d_db_.cap + d_ids_.cap + d_aux_.cap;
+  stats_.device_bytes = d_db_.cap + d_ids_.cap + d_aux_.cap + d_bias_.cap + d_db_unit_.cap;
   return Status::OK();
 }
 
@@ -403,7 +436,7 @@ Status Engine::upload_graph() {
 // ------------------------------------------------------------------------------------ query
 Status Engine::stage_queries_device(const void* src, bool src_on_device, size_t nq, size_t elem_count,
                                     cudaStream_t stream) {
-  const size_t bq = scan_exact_block_queries();
+  const size_t bq = std::max(scan_exact_block_queries(), tc_block_queries());
   const size_t q_pad = round_up(nq, bq);
   const size_t row_bytes = (size_t)row_words_ * 4;
   const size_t old_cap = d_q_.cap;
@@ -457,6 +490,23 @@ Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d
   }
 
   // ---- sequential search ----
+  if (!(s = check_cuda(d_tc_keys_.ensure(nq * k * 8), "cudaMalloc(keys)")).ok()) return s;
+  uint64_t* keys = d_tc_keys_.as<uint64_t>();
+  const bool use_tc = !is_u8_ && !force_exact_ && k <= (size_t)tc_max_k();
+  s = use_tc ? run_seq_tc(dq, nq, k, keys, stream) : run_seq_exact(dq, nq, k, keys, stream);
+  if (!s.ok()) return s;
+  // sorted (distance, position) keys -> external ids + float distances (extract_knn_results, nmslib_c.cpp:293-328)
+  s = check_cuda(launch_merge_topk(keys, nullptr, 1, 0, k, (int)nq, (int)k, finalize_kind(), d_ids_.as<int32_t>(),
+                                   pos_base_, d_keys, d_ids, d_dists, d_counts, stream),
+                 "finalize");
+  ++stats_.kernel_launches;
+  return s;
+}
+
+// Exact scan on the CUDA cores (uint8 always; float spaces when the tensor-core answer of a query could
+// not be certified, or when NB200_FORCE_EXACT is set).  Writes the k best keys per query.
+Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream) {
+  Status s;
   const int bq = scan_exact_block_queries(), bn = scan_exact_block_points();
   const int n_tiles = (int)((n_dev_ + bn - 1) / bn);
   const int q_blocks = (int)((nq + bq - 1) / bq);
@@ -486,18 +536,112 @@ Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d
   }
   s = check_cuda(d_partial_.ensure(nq * (size_t)n_split * k * 8), "cudaMalloc(partial)");
   if (!s.ok()) return s;
-  scan_begin(stream);
+  const bool dominant = is_u8_ || force_exact_;
+  if (dominant) scan_begin(stream);
   s = check_cuda(launch_scan_exact(mode, d_db_.p, dq, d_aux_.p, q_aux, (int)n_dev_, (int)nq, row_words_, (int)k,
                                    pos_base_, d_partial_.as<uint64_t>(), n_split, tiles_per_split, stream),
                  "scan_exact");
-  scan_end(stream);
+  if (dominant) scan_end(stream);
   if (!s.ok()) return s;
   s = check_cuda(launch_merge_topk(d_partial_.as<uint64_t>(), nullptr, n_split, k, (size_t)n_split * k, (int)nq,
-                                   (int)k, finalize_kind(), d_ids_.as<int32_t>(), pos_base_, d_keys, d_ids, d_dists,
-                                   d_counts, stream),
+                                   (int)k, FIN_FLOAT, nullptr, pos_base_, out_keys, nullptr, nullptr, nullptr, stream),
                  "merge_topk");
   stats_.kernel_launches += 2;
   return s;
+}
+
+// Tensor-core candidates + exact fp32 re-rank + certificate; uncertified queries go to run_seq_exact.
+Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream) {
+  Status s;
+  const int mode = space_ == SPACE_COSINE ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
+  const int qb = tc_block_queries(), bn = tc_block_points();
+  const size_t q_pad = round_up(nq, qb);
+  const size_t n_pad = round_up(n_dev_, bn);
+  const int q_blocks = (int)(q_pad / qb);
+  const int n_tiles = (int)(n_pad / bn);
+  // one CTA per SM: pick the smallest split count whose last wave is >= 90 % full (else the fullest)
+  int best = 1;
+  double best_eff = 0;
+  const int max_split = std::min(n_tiles, 64);
+  for (int sp = 1; sp <= max_split; ++sp) {
+    const long ctas = (long)q_blocks * sp;
+    const long waves = (ctas + sm_count_ - 1) / sm_count_;
+    const double eff = (double)ctas / (double)(waves * sm_count_);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = sp;
+    }
+    if (eff >= 0.9) {
+      best = sp;
+      break;
+    }
+  }
+  const int tiles_per_split = (n_tiles + best - 1) / best;
+  const int n_split = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+  int kprime, cap;
+  tc_candidate_shape((int)k, &kprime, &cap);
+  const size_t units = (size_t)q_blocks * n_split;
+  if (!(s = check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)")).ok()) return s;
+  if (!(s = check_cuda(d_cand_.ensure(units * qb * (size_t)cap * 8), "cudaMalloc(cand)")).ok()) return s;
+  if (!(s = check_cuda(d_cand_cnt_.ensure(units * qb * 4), "cudaMalloc(cand_cnt)")).ok()) return s;
+  if (!(s = check_cuda(d_cand_thr_.ensure(units * qb * 4), "cudaMalloc(cand_thr)")).ok()) return s;
+  if (!(s = check_cuda(d_cert_.ensure(nq * 4), "cudaMalloc(cert)")).ok()) return s;
+  if (!(s = check_cuda(h_cert_.ensure(nq * 4), "cudaMallocHost(cert)")).ok()) return s;
+  if (!(s = check_cuda(cudaMemsetAsync(d_flags_.as<int>() + 1, 0, 4, stream), "memset(qflag)")).ok()) return s;
+  const float scale = mode == SCAN_L2 ? -2.f : -1.f;
+  s = check_cuda(launch_tc_prep_queries(static_cast<const float*>(dq), d_qa_.as<float>(), q_pad * (size_t)row_words_,
+                                        scale, d_flags_.as<int>() + 1, stream),
+                 "tc_prep_queries");
+  if (!s.ok()) return s;
+  const float* dbB = mode == SCAN_COSINE ? d_db_unit_.as<float>() : d_db_.as<float>();
+  scan_begin(stream);
+  s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad, d_bias_.as<float>(), (int)n_dev_, (int)nq,
+                                row_words_, (int)k, pos_base_, n_split, tiles_per_split, d_cand_.as<uint64_t>(),
+                                d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(), stream),
+                 "tc_scan");
+  scan_end(stream);
+  if (!s.ok()) return s;
+  s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
+                                  mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)nq, row_words_, (int)k,
+                                  n_split, mode, pos_base_, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                                  d_cand_thr_.as<float>(), x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(),
+                                  stream),
+                 "tc_rerank");
+  if (!s.ok()) return s;
+  stats_.kernel_launches += 3;
+  // certificates back to the host; re-run the (normally empty) set of uncertified queries exactly
+  s = check_cuda(cudaMemcpyAsync(h_cert_.p, d_cert_.p, nq * 4, cudaMemcpyDeviceToHost, stream), "D2H(cert)");
+  if (!s.ok()) return s;
+  s = check_cuda(cudaStreamSynchronize(stream), "tc scan");
+  if (!s.ok()) return s;
+  std::vector<int> fb;
+  const int* cert = h_cert_.as<int>();
+  for (size_t i = 0; i < nq; ++i)
+    if (!cert[i]) fb.push_back((int)i);
+  if (fb.empty()) return Status::OK();
+  stats_.fallback_queries += fb.size();
+  const size_t nfb = fb.size();
+  const size_t fb_pad = round_up(nfb, (size_t)scan_exact_block_queries());
+  if (!(s = check_cuda(d_fb_idx_.ensure(nfb * 4), "cudaMalloc(fb idx)")).ok()) return s;
+  if (!(s = check_cuda(d_fb_q_.ensure(fb_pad * (size_t)row_words_ * 4), "cudaMalloc(fb q)")).ok()) return s;
+  if (!(s = check_cuda(d_fb_keys_.ensure(nfb * k * 8), "cudaMalloc(fb keys)")).ok()) return s;
+  if (!(s = check_cuda(cudaMemsetAsync(d_fb_q_.p, 0, fb_pad * (size_t)row_words_ * 4, stream), "memset(fb q)")).ok())
+    return s;
+  s = check_cuda(cudaMemcpyAsync(d_fb_idx_.p, fb.data(), nfb * 4, cudaMemcpyHostToDevice, stream), "H2D(fb idx)");
+  if (!s.ok()) return s;
+  s = check_cuda(launch_gather_rows(static_cast<const uint32_t*>(dq), d_fb_idx_.as<int>(), (int)nfb, row_words_,
+                                    d_fb_q_.as<uint32_t>(), stream),
+                 "gather");
+  if (!s.ok()) return s;
+  s = run_seq_exact(d_fb_q_.p, nfb, k, d_fb_keys_.as<uint64_t>(), stream);
+  if (!s.ok()) return s;
+  s = check_cuda(launch_scatter_keys(d_fb_keys_.as<uint64_t>(), d_fb_idx_.as<int>(), (int)nfb, (int)k, out_keys,
+                                     stream),
+                 "scatter");
+  if (!s.ok()) return s;
+  stats_.kernel_launches += 2;
+  // fb (host vector) must outlive the async H2D above
+  return check_cuda(cudaStreamSynchronize(stream), "fallback scan");
 }
 
 Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, size_t k, int32_t* d_ids,

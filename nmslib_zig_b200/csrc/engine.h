@@ -124,6 +124,8 @@ class Engine {
   Status check_cuda(cudaError_t e, const char* what);
   Status upload_data();
   Status upload_graph();
+  Status run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream);
+  Status run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream);
   Status run(const void* d_queries_padded, size_t nq, size_t k, int32_t* d_ids, float* d_dists,
              uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream);
   Status stage_queries_device(const void* src, bool src_on_device, size_t nq, size_t elem_count,
@@ -159,6 +161,12 @@ class Engine {
   void scan_begin(cudaStream_t s);
   void scan_end(cudaStream_t s);
   DevBuf d_db_, d_aux_, d_ids_;
+  // tensor-core scan operands / scratch
+  DevBuf d_bias_, d_db_unit_, d_flags_, d_qa_, d_cand_, d_cand_cnt_, d_cand_thr_, d_tc_keys_, d_cert_, d_fb_idx_,
+      d_fb_q_, d_fb_keys_;
+  PinBuf h_cert_;
+  float x_max_ = 0.f;
+  bool force_exact_ = false;
   size_t n_dev_ = 0;
   DevBuf d_links0_, d_links0_cnt_, d_upper_, d_upper_off_, d_visited_, d_epoch_, d_counters_;
   int hnsw_slots_ = 0;

@@ -33,6 +33,34 @@ cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int l
                               int32_t* out_counts, cudaStream_t stream);
 int merge_topk_max_items();
 
+// gather rows idx[i] of a [*, row_words] array into dst[i] / scatter k-key rows back
+cudaError_t launch_gather_rows(const uint32_t* src, const int* idx, int count, int row_words, uint32_t* dst,
+                               cudaStream_t stream);
+cudaError_t launch_scatter_keys(const uint64_t* src, const int* idx, int count, int k, uint64_t* dst,
+                                cudaStream_t stream);
+
+// ---- scan_tc.cu (tcgen05 TF32 candidates + exact fp32 re-rank) -------------------------
+int tc_block_queries();   // queries per CTA (256): query buffers are padded to this
+int tc_block_points();    // database rows per tile (128)
+int tc_kblock_words();    // row padding granularity in 32-bit words (32 = 128 bytes)
+int tc_max_k();
+void tc_candidate_shape(int k, int* kprime, int* cap);
+// mode: SCAN_L2 / SCAN_COSINE / SCAN_NEGDOT.  bias[n_pad]; norm2[n] (may be NULL); db_unit: normalised
+// copy (cosine only); max_norm_bits: float bits of max |operand row|; inexact_flag: set if not TF32-exact
+cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, int mode, float* bias, float* norm2,
+                              float* db_unit, unsigned* max_norm_bits, int* inexact_flag, cudaStream_t stream);
+cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, float scale, int* inexact_flag,
+                                   cudaStream_t stream);
+// qa: prepared queries [q_pad][row_words]; dbB: B operand rows [n_pad][row_words];
+// cand: [units][256][cap] keys, cand_cnt / cand_thr: [units][256], units = q_blocks * n_split
+cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* bias, int n,
+                           int nq, int row_words, int k, uint32_t pos_base, int n_split, int tiles_per_split,
+                           uint64_t* cand, int* cand_cnt, float* cand_thr, cudaStream_t stream);
+cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int nq, int row_words,
+                             int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
+                             const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
+                             uint64_t* out_keys, int* out_cert, cudaStream_t stream);
+
 // ---- hnsw_search.cu ------------------------------------------------------------------
 struct HnswDeviceGraph {
   const float* vectors;      // [n][row_words] (cosine: unit-norm rows, as the reference stores them)

@@ -1,0 +1,752 @@
+// scan_tc.cu -- K1: brute-force kNN as a tcgen05 (5th-gen tensor core) TF32 contraction with a
+// fused in-register top-k candidate filter: the Q x N distance matrix lives only in TMEM.
+//
+// Replaces, for the float spaces, the same reference functions as scan_exact.cu
+// (SeqSearch::Search seqsearch.cc:144-150 + L2SqrSIMD / ScalarProductSIMD /
+// NormScalarProductSIMD + KNNQueue), but as "candidates on the tensor cores, exact re-rank
+// in fp32":
+//   pass 1 (tc_scan_kernel)  rank(q, x) = A'(q) . x + bias(x) on the tensor cores, where
+//          l2 / l2sqr : A' = -2 q,  bias = |x|^2     (rank = d^2 - |q|^2)
+//          cosinesimil: A' = -q,    x pre-normalised (rank = -|q| * nsp)
+//          negdotprod : A' = -q                      (rank = -q.x)
+//        Each query keeps the candidates whose rank beats a running threshold in a small
+//        per-query buffer (k' > k survivors after each compaction).
+//   pass 2 (tc_rerank_kernel) the reference's own fp32 formula on the candidates only, the k
+//        best by (distance, position), and a CERTIFICATE: every point that is not a candidate
+//        has approximate rank >= thr, hence exact rank >= thr - E, with E a rigorous bound on
+//        the TF32 error of pass 1.  If the exact k-th rank + E < thr the answer is provably the
+//        exact top-k; otherwise the query is re-run by the exact scan (scan_exact.cu).
+//
+// Kernel anatomy (one CTA per SM, 192 threads, no cluster):
+//   warp 0   TMA producer: cp.async.bulk.tensor (128B-swizzled 128-row x 32-float boxes) into a
+//            ring of shared-memory stages, mbarrier complete_tx
+//   warp 1   TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer.  A CTA owns 256
+//            queries = two M=128 operand tiles, so every 128-row database tile that reaches
+//            shared memory feeds two MMAs (halves L2->SM traffic per flop); four 128-column fp32
+//            accumulators = all 512 TMEM columns, double buffered against the epilogue
+//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time (thread == TMEM lane == one query row),
+//            + bias, 3-input min tree, one compare per 32 values; survivors are appended to the
+//            row's candidate buffer; a full buffer is compacted warp-cooperatively
+//            (ballot-based radix select of the k'-th smallest).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nb200 {
+namespace {
+
+constexpr int TC_BM = 128;          // queries per operand tile (two tiles per CTA)
+constexpr int TC_QB = 256;          // queries per CTA
+constexpr int TC_BN = 128;          // database rows per tile
+constexpr int TC_KB = 32;           // floats per k-block: one 128-byte swizzle row
+constexpr int CHUNK_BYTES = TC_BM * TC_KB * 4;  // 16 KB: 128 rows x 128 B
+constexpr int TC_THREADS = 192;
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (PTX "tcgen05 matrix descriptor"): K-major operand, rows of
+// 128 bytes, 128B swizzle (what the TMA box above produces).  start >> 4 in [0,14), LBO >> 4 in
+// [16,30) (unused for swizzled K-major: 1), SBO >> 4 in [32,46) = 8 rows * 128 B, version 1 in
+// [46,48), layout SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::tf32: D = F32 (1 @4), A = B = TF32 (2 @7, 2 @10), both K-major,
+// N >> 3 @17, M >> 4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// ---------------------------------------------------------------- candidate buffers
+// Warp-cooperative compaction of one query row's buffer: keep the kprime smallest keys
+// (ties at the cut kept in buffer order), return the kprime-th smallest rank (ordered bits).
+template <int KPL>
+__device__ __forceinline__ uint32_t compact_row(uint64_t* buf, int cnt, int kprime, int lane) {
+  uint64_t key[KPL];
+  bool valid[KPL];
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    const int i = s * 32 + lane;
+    valid[s] = i < cnt;
+    key[s] = valid[s] ? buf[i] : KEY_MAX;
+  }
+  // smallest v with #(rank <= v) >= kprime: binary search over the 32-bit ordered rank
+  uint32_t lo = 0, hi = 0xFFFFFFFFu;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) c += __popc(__ballot_sync(FULL, valid[s] && (uint32_t)(key[s] >> 32) <= mid));
+    if (c >= kprime) hi = mid; else lo = mid + 1;
+  }
+  const uint32_t t = lo;
+  __syncwarp();
+  int out = 0;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {  // strictly better than the cut
+    const bool keep = valid[s] && (uint32_t)(key[s] >> 32) < t;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) buf[out + __popc(m & ((1u << lane) - 1))] = key[s];
+    out += __popc(m);
+  }
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {  // ties at the cut, up to kprime in total
+    const bool eq = valid[s] && (uint32_t)(key[s] >> 32) == t;
+    const unsigned m = __ballot_sync(FULL, eq);
+    const int pos = out + __popc(m & ((1u << lane) - 1));
+    if (eq && pos < kprime) buf[pos] = key[s];
+    out = min(kprime, out + __popc(m));
+  }
+  __syncwarp();
+  return t;
+}
+
+struct TcParams {
+  const float* bias;       // [n_pad]: per database row bias, +inf on padding rows
+  int n, nq, n_kb, tiles_per_split, n_split;
+  uint32_t pos_base;
+  uint64_t* cand;          // [units][256][cap]
+  int* cand_cnt;           // [units][256]
+  float* cand_thr;         // [units][256]   final threshold (rank domain), +inf if nothing was ever dropped
+  int cap, kprime;
+  int n_stage;             // shared-memory ring depth
+  int a_resident;          // 1: both query tiles stay in shared memory for the CTA's life (D <= 128)
+};
+
+template <int KPL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: [A resident: 2*n_kb chunks] [stages: n_stage * stage_bytes] [bias: 2*128 f32] [barriers]
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;
+  const int stage_bytes = p.a_resident ? CHUNK_BYTES : 3 * CHUNK_BYTES;  // B [+ A0 + A1]
+  unsigned char* smem_a = smem;
+  unsigned char* smem_st = smem + a_bytes;
+  float* bias_s = reinterpret_cast<float*>(smem_st + (size_t)p.n_stage * stage_bytes);  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * TC_BN);
+  uint64_t* full_bar = bars;                   // [n_stage]
+  uint64_t* empty_bar = bars + p.n_stage;      // [n_stage]
+  uint64_t* tfull_bar = bars + 2 * p.n_stage;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2]
+  uint64_t* afull_bar = tempty_bar + 2;        // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(afull_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, qblock = blockIdx.y;
+  const int q0 = qblock * TC_QB;
+  const int n_tiles_total = (p.n + TC_BN - 1) / TC_BN;
+  const int t0 = split * p.tiles_per_split;
+  const int t1 = min(t0 + p.tiles_per_split, n_tiles_total);
+  const int n_tiles = max(t1 - t0, 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.n_stage; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
+    mbar_init(afull_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && n_tiles > 0) {
+      if (p.a_resident) {
+        mbar_expect_tx(afull_bar, (uint32_t)a_bytes);
+        for (int h = 0; h < 2; ++h)
+          for (int kb = 0; kb < p.n_kb; ++kb)
+            tma_load_2d(&tmA, afull_bar, smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES, kb * TC_KB, q0 + h * TC_BM);
+      }
+      int it = 0;
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+          const int s = it % p.n_stage;
+          mbar_wait(&empty_bar[s], ((it / p.n_stage) & 1) ^ 1);
+          unsigned char* st = smem_st + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          tma_load_2d(&tmB, &full_bar[s], st, kb * TC_KB, t * TC_BN);
+          if (!p.a_resident) {
+            tma_load_2d(&tmA, &full_bar[s], st + CHUNK_BYTES, kb * TC_KB, q0);
+            tma_load_2d(&tmA, &full_bar[s], st + 2 * CHUNK_BYTES, kb * TC_KB, q0 + TC_BM);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0 && n_tiles > 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+      if (p.a_resident) mbar_wait(afull_bar, 0);
+      int it = 0;
+      for (int ti = 0; ti < n_tiles; ++ti) {
+        const int b = ti & 1;
+        mbar_wait(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+          const int s = it % p.n_stage;
+          mbar_wait(&full_bar[s], (it / p.n_stage) & 1);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem_st + (size_t)s * stage_bytes);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sa = p.a_resident ? smem_u32(smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES)
+                                             : sb + (uint32_t)(1 + h) * CHUNK_BYTES;
+            const uint32_t tmem_d = tmem_base + (uint32_t)((b * 2 + h) * TC_BN);
+#pragma unroll
+            for (int k = 0; k < TC_KB / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
+              umma_tf32(tmem_d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
+                        (uint32_t)((kb | k) != 0));
+            }
+          }
+          tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        }
+        tc_commit(&tfull_bar[b]);    // accumulators of tile ti are complete
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, thread == TMEM lane == query row =====================
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;       // row inside each 128-query half
+    const size_t unit = (size_t)qblock * p.n_split + split;
+    uint64_t* buf[2];
+    float thr[2];
+    int cnt[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      buf[h] = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
+      cnt[h] = 0;
+      thr[h] = (q0 + h * TC_BM + row < p.nq) ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+    }
+    float bias_next = n_tiles > 0 ? p.bias[(size_t)t0 * TC_BN + row] : 0.f;
+    for (int ti = 0; ti < n_tiles; ++ti) {
+      const int b = ti & 1;
+      const int tile = t0 + ti;
+      bias_s[b * TC_BN + row] = bias_next;
+      if (ti + 1 < n_tiles) bias_next = p.bias[(size_t)(tile + 1) * TC_BN + row];
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue-only named barrier
+      mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+          // make room: a chunk may append up to 32 keys to a row
+          unsigned need = __ballot_sync(FULL, cnt[h] > p.cap - 32);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf[h], src);
+            const int c = __shfl_sync(FULL, cnt[h], src);
+            const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, p.kprime, lane);
+            if (lane == src) {
+              cnt[h] = p.kprime;
+              thr[h] = f32_from_ordered(t);
+            }
+          }
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + h) * TC_BN + ch * 32), v);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + b * TC_BN + ch * 32);
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            r[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+            r[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+            r[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+            r[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+          }
+          float m = min3(r[0], r[1], r[2]);
+#pragma unroll
+          for (int j = 3; j + 1 < 32; j += 2) m = min3(m, r[j], r[j + 1]);
+          m = fminf(m, r[31]);
+          if (m < thr[h]) {  // rare once the threshold is warm
+            const uint32_t pos0 = p.pos_base + (uint32_t)(tile * TC_BN + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (r[j] < thr[h]) {
+                buf[h][cnt[h]] = make_key(f32_ordered(r[j]), pos0 + j);
+                ++cnt[h];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[b]);
+    }
+    // publish this split's per-row candidate count and final threshold
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const size_t slot = unit * TC_QB + h * TC_BM + row;
+      p.cand_cnt[slot] = (q0 + h * TC_BM + row < p.nq) ? cnt[h] : 0;
+      p.cand_thr[slot] = thr[h];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- pass 2: exact re-rank
+struct RerankParams {
+  const float* db;         // [n_pad][row_words] ORIGINAL vectors
+  const float* queries;    // [q_pad][row_words] ORIGINAL queries
+  const float* db_norm2;   // [n_pad] |x|^2 (cosine) or NULL
+  int nq, row_words, k, n_split, cap, mode;  // mode: SCAN_L2 / SCAN_COSINE / SCAN_NEGDOT
+  uint32_t pos_base;
+  const uint64_t* cand;
+  const int* cand_cnt;
+  const float* cand_thr;
+  float eps_inexact, eps_exact;   // relative error bounds of pass 1
+  float x_max;                    // max |B-operand row|
+  const int* inexact_flags;       // [2]: nonzero if the database / this query batch is not TF32-exact
+  uint64_t* out_keys;             // [nq][k]
+  int* out_cert;                  // [nq] 1 = certified exact
+};
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, int items_pow2) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);          // [items_pow2] exact keys
+  float* srank = reinterpret_cast<float*>(sk + items_pow2);       // [items_pow2] exact rank (certificate domain)
+  __shared__ int s_off[65];
+  __shared__ float s_minthr, s_qn2;
+  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qb = q / TC_QB, row = q % TC_QB;
+  const float* qv = p.queries + (size_t)q * p.row_words;
+
+  if (tid == 0) {
+    int off = 0;
+    float mt = __int_as_float(0x7F800000);
+    for (int s = 0; s < p.n_split; ++s) {
+      const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
+      s_off[s] = off;
+      off += p.cand_cnt[slot];
+      mt = fminf(mt, p.cand_thr[slot]);
+    }
+    s_off[p.n_split] = off;
+    s_minthr = mt;
+  }
+  if (warp == 0) {
+    float s = 0.f;
+    for (int c = lane; c < p.row_words; c += 32) s = fmaf(qv[c], qv[c], s);
+    s = warp_sum_f(s);
+    if (lane == 0) s_qn2 = s;
+  }
+  for (int t = tid; t < items_pow2; t += blockDim.x) {
+    sk[t] = KEY_MAX;
+    srank[t] = __int_as_float(0x7F800000);
+  }
+  __syncthreads();
+  const int total = s_off[p.n_split];
+  const float qn2 = s_qn2;
+  const int rw4 = p.row_words >> 2;
+  const float4* q4 = reinterpret_cast<const float4*>(qv);
+
+  // exact fp32 distance of every candidate: one warp per candidate, 128-bit loads
+  for (int s = 0; s < p.n_split; ++s) {
+    const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
+    const uint64_t* cb = p.cand + slot * (size_t)p.cap;
+    const int c = s_off[s + 1] - s_off[s];
+    for (int i = warp; i < c; i += 4) {
+      const uint32_t pos = (uint32_t)cb[i];
+      const size_t local = (size_t)(pos - p.pos_base);
+      const float4* x4 = reinterpret_cast<const float4*>(p.db + local * p.row_words);
+      float acc = 0.f;
+      for (int e = lane; e < rw4; e += 32) {
+        const float4 x = __ldg(x4 + e), y = q4[e];
+        if (p.mode == SCAN_L2) {
+          const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+          acc = fmaf(d0, d0, acc);
+          acc = fmaf(d1, d1, acc);
+          acc = fmaf(d2, d2, acc);
+          acc = fmaf(d3, d3, acc);
+        } else {
+          acc = fmaf(x.x, y.x, acc);
+          acc = fmaf(x.y, y.y, acc);
+          acc = fmaf(x.z, y.z, acc);
+          acc = fmaf(x.w, y.w, acc);
+        }
+      }
+      acc = warp_sum_f(acc);
+      if (lane == 0) {
+        float dist, rank;
+        if (p.mode == SCAN_L2) {
+          dist = acc;                 // sum (x-y)^2, the reference's formula (distcomp_lp.cc:304-365)
+          rank = acc - qn2;           // pass 1 ranks by |x|^2 - 2 q.x
+        } else if (p.mode == SCAN_NEGDOT) {
+          dist = -acc;
+          rank = -acc;
+        } else {
+          const float nx = p.db_norm2[local];
+          const float eps = 2.0f * 1.17549435e-38f;
+          float nsp = 0.f;
+          if (!(nx < eps || qn2 < eps)) nsp = fmaxf(-1.f, fminf(1.f, acc / sqrtf(nx) / sqrtf(qn2)));
+          dist = fmaxf(0.f, 1.f - nsp);
+          rank = (nx < eps) ? 0.f : -acc * rsqrtf(nx);   // pass 1 ranks by -q.x / |x|
+        }
+        sk[s_off[s] + i] = make_key(f32_ordered(dist), pos);
+        srank[s_off[s] + i] = rank;
+      }
+    }
+  }
+  __syncthreads();
+
+  // sort (key, rank) ascending by key
+  for (int size = 2; size <= items_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < items_pow2 / 2; t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const uint64_t a = sk[lo], b = sk[hi];
+        if ((a > b) == up) {
+          sk[lo] = b;
+          sk[hi] = a;
+          const float ra = srank[lo];
+          srank[lo] = srank[hi];
+          srank[hi] = ra;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < p.k; e += blockDim.x) p.out_keys[(size_t)q * p.k + e] = e < items_pow2 ? sk[e] : KEY_MAX;
+
+  if (tid == 0) {
+    // certificate: every non-candidate has approximate rank >= s_minthr, exact rank >= s_minthr - E
+    int cert;
+    if (s_minthr == __int_as_float(0x7F800000)) {
+      cert = 1;  // nothing was ever dropped in any split: the candidates are the whole shard
+    } else if (total < p.k) {
+      cert = 0;
+    } else {
+      const bool inexact = p.inexact_flags[0] != 0 || p.inexact_flags[1] != 0;
+      const float a_norm = (p.mode == SCAN_L2 ? 2.f : 1.f) * sqrtf(qn2);
+      const float E = (inexact ? p.eps_inexact : p.eps_exact) * a_norm * p.x_max + 1e-30f;
+      // worst exact rank among the k answers (ranks are not exactly monotone in the key for cosine)
+      float worst = __int_as_float(0xFF800000);
+      for (int e = 0; e < p.k; ++e) worst = fmaxf(worst, srank[e]);
+      cert = (worst + E + fabsf(worst) * 1e-6f < s_minthr) ? 1 : 0;
+    }
+    p.out_cert[q] = cert;
+  }
+}
+
+// ---------------------------------------------------------------- operand preparation
+// A' = scale * q (scale = -2 for l2, -1 otherwise) into a buffer padded to 256-row blocks; also
+// flags a batch that is not TF32-exact (any of the 13 low mantissa bits set).
+__global__ void tc_prep_queries_kernel(const float* __restrict__ q, float* __restrict__ out, size_t words,
+                                       float scale, int* __restrict__ inexact_flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned bad = 0;
+  for (; i < words; i += stride) {
+    const float v = q[i];
+    bad |= __float_as_uint(v) & 0x1FFFu;
+    out[i] = v * scale;
+  }
+  bad = __reduce_or_sync(FULL, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicOr(inexact_flag, 1);
+}
+
+// database side: bias[row] (|x|^2 for l2, 0 otherwise; +inf on padding rows), optional normalised copy,
+// max operand-row norm, TF32-exactness flag.  One warp per row.
+__global__ void tc_prep_db_kernel(const float* __restrict__ db, int n, int n_pad, int row_words, int mode,
+                                  float* __restrict__ bias, float* __restrict__ norm2, float* __restrict__ db_unit,
+                                  unsigned* __restrict__ max_norm_bits, int* __restrict__ inexact_flag) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_pad) return;
+  if (warp >= n) {
+    if (lane == 0) bias[warp] = __int_as_float(0x7F800000);
+    return;
+  }
+  const float* r = db + (size_t)warp * row_words;
+  float s = 0.f;
+  unsigned bad = 0;
+  for (int c = lane; c < row_words; c += 32) {
+    const float v = r[c];
+    s = fmaf(v, v, s);
+    bad |= __float_as_uint(v) & 0x1FFFu;
+  }
+  s = warp_sum_f(s);
+  bad = __reduce_or_sync(FULL, bad);
+  float op_norm2 = s;
+  if (mode == SCAN_COSINE) {
+    const float eps = 2.0f * 1.17549435e-38f;
+    const float inv = s < eps ? 0.f : rsqrtf(s);
+    for (int c = lane; c < row_words; c += 32) db_unit[(size_t)warp * row_words + c] = r[c] * inv;
+    op_norm2 = s < eps ? 0.f : 1.0f;
+    bad = 1;  // the normalised copy is never TF32-exact
+  }
+  if (lane == 0) {
+    bias[warp] = (mode == SCAN_L2) ? s : 0.f;
+    if (norm2) norm2[warp] = s;
+    atomicMax(max_norm_bits, __float_as_uint(sqrtf(op_norm2) * 1.000001f));
+    if (bad) atomicOr(inexact_flag, 1);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// rows x row_words fp32, row-major; box = 128 rows x 32 floats, 128B swizzle
+bool make_tmap(CUtensorMap* map, const void* base, size_t rows, int row_words) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)row_words, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_words * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int tc_block_queries() { return TC_QB; }
+int tc_block_points() { return TC_BN; }
+int tc_kblock_words() { return TC_KB; }
+
+cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, int mode, float* bias, float* norm2,
+                              float* db_unit, unsigned* max_norm_bits, int* inexact_flag, cudaStream_t stream) {
+  const int threads = 256;
+  const int blocks = (int)(((size_t)n_pad * 32 + threads - 1) / threads);
+  tc_prep_db_kernel<<<blocks, threads, 0, stream>>>(db, n, n_pad, row_words, mode, bias, norm2, db_unit,
+                                                    max_norm_bits, inexact_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, float scale, int* inexact_flag,
+                                   cudaStream_t stream) {
+  int blocks = (int)std::min<size_t>((words + 255) / 256, 148 * 8);
+  if (blocks < 1) blocks = 1;
+  tc_prep_queries_kernel<<<blocks, 256, 0, stream>>>(q, out, words, scale, inexact_flag);
+  return cudaGetLastError();
+}
+
+// cand capacity per (unit,row) and survivors per compaction for a given k
+void tc_candidate_shape(int k, int* kprime, int* cap) {
+  int kp = k + 22 < 2 * k ? k + 22 + (k / 4) : 2 * k;  // headroom for the certificate
+  if (kp < k + 22) kp = k + 22;
+  kp = (kp + 31) / 32 * 32;
+  int c = kp <= 32 ? 128 : kp <= 96 ? 256 : 512;
+  if (kp > c - 64) kp = c - 64;
+  *kprime = kp;
+  *cap = c;
+}
+int tc_max_k() { return 256; }
+
+cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* bias, int n,
+                           int nq, int row_words, int k, uint32_t pos_base, int n_split, int tiles_per_split,
+                           uint64_t* cand, int* cand_cnt, float* cand_thr, cudaStream_t stream) {
+  if (n <= 0 || nq <= 0) return cudaSuccess;
+  if (row_words % TC_KB) return cudaErrorInvalidValue;
+  CUtensorMap tmA, tmB;
+  if (!make_tmap(&tmA, qa, q_pad, row_words) || !make_tmap(&tmB, dbB, n_pad, row_words)) return cudaErrorUnknown;
+  TcParams p;
+  p.bias = bias;
+  p.n = n;
+  p.nq = nq;
+  p.n_kb = row_words / TC_KB;
+  p.tiles_per_split = tiles_per_split;
+  p.n_split = n_split;
+  p.pos_base = pos_base;
+  p.cand = cand;
+  p.cand_cnt = cand_cnt;
+  p.cand_thr = cand_thr;
+  tc_candidate_shape(k, &p.kprime, &p.cap);
+  p.a_resident = (2 * p.n_kb * CHUNK_BYTES <= 128 * 1024) ? 1 : 0;
+  const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;
+  const int stage_bytes = p.a_resident ? CHUNK_BYTES : 3 * CHUNK_BYTES;
+  const int budget = 200 * 1024;
+  p.n_stage = (budget - a_bytes) / stage_bytes;
+  if (p.n_stage > 8) p.n_stage = 8;
+  if (p.n_stage < 2) return cudaErrorInvalidValue;
+  const size_t smem = 1024 + (size_t)a_bytes + (size_t)p.n_stage * stage_bytes + 2 * TC_BN * 4 + (2 * 8 + 5) * 8 + 16;
+  dim3 grid(n_split, (nq + TC_QB - 1) / TC_QB);
+  cudaError_t e;
+#define NB_TC(KPL)                                                                                        \
+  e = cudaFuncSetAttribute(tc_scan_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+  if (e != cudaSuccess) return e;                                                                         \
+  tc_scan_kernel<KPL><<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, p);
+  switch (p.cap) {
+    case 128: NB_TC(4); break;
+    case 256: NB_TC(8); break;
+    default: NB_TC(16); break;
+  }
+#undef NB_TC
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int nq, int row_words,
+                             int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
+                             const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
+                             uint64_t* out_keys, int* out_cert, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  RerankParams p;
+  p.db = db;
+  p.queries = queries;
+  p.db_norm2 = db_norm2;
+  p.nq = nq;
+  p.row_words = row_words;
+  p.k = k;
+  p.n_split = n_split;
+  int kprime;
+  tc_candidate_shape(k, &kprime, &p.cap);
+  p.mode = mode;
+  p.pos_base = pos_base;
+  p.cand = cand;
+  p.cand_cnt = cand_cnt;
+  p.cand_thr = cand_thr;
+  // Error model of pass 1 (DESIGN.md "certificate"): TF32 operands are fp32 with the low 13 mantissa
+  // bits dropped (relative 2^-10 each when truncated), products exact, fp32 accumulation over D terms.
+  const float dterms = (float)row_words;
+  p.eps_exact = dterms * 2.384185791015625e-07f;                    // D * 2^-22  (accumulation only)
+  p.eps_inexact = 2.0f * 0.0009765625f * 1.01f + p.eps_exact;       // 2 * 2^-10 + accumulation
+  p.x_max = x_max;
+  p.inexact_flags = inexact_flags;
+  p.out_keys = out_keys;
+  p.out_cert = out_cert;
+  if (n_split > 64) return cudaErrorInvalidValue;
+  int items = n_split * p.cap;
+  int p2 = 1;
+  while (p2 < items || p2 < k) p2 <<= 1;
+  const size_t smem = (size_t)p2 * 12 + 16;
+  cudaError_t e = cudaFuncSetAttribute(tc_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  tc_rerank_kernel<<<nq, 128, smem, stream>>>(p, p2);
+  return cudaGetLastError();
+}
+
+}  // namespace nb200

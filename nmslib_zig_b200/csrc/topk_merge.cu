@@ -97,6 +97,39 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ keys, const int32
 
 }  // namespace
 
+namespace {
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, int count,
+                                   int row_vec, uint4* __restrict__ dst) {
+  const int r = blockIdx.x;
+  if (r >= count) return;
+  const uint4* s = src + (size_t)idx[r] * row_vec;
+  uint4* d = dst + (size_t)r * row_vec;
+  for (int c = threadIdx.x; c < row_vec; c += blockDim.x) d[c] = s[c];
+}
+__global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, const int* __restrict__ idx, int count, int k,
+                                    uint64_t* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count * k) return;
+  const int r = i / k, e = i - r * k;
+  dst[(size_t)idx[r] * k + e] = src[i];
+}
+}  // namespace
+
+cudaError_t launch_gather_rows(const uint32_t* src, const int* idx, int count, int row_words, uint32_t* dst,
+                               cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  gather_rows_kernel<<<count, 64, 0, stream>>>(reinterpret_cast<const uint4*>(src), idx, count, row_words / 4,
+                                               reinterpret_cast<uint4*>(dst));
+  return cudaGetLastError();
+}
+cudaError_t launch_scatter_keys(const uint64_t* src, const int* idx, int count, int k, uint64_t* dst,
+                                cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  const int total = count * k;
+  scatter_keys_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, idx, count, k, dst);
+  return cudaGetLastError();
+}
+
 int merge_topk_max_items() { return MAX_ITEMS; }
 
 cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int lists, size_t list_stride,

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import nmslib_zig_b200 as nb
-from helpers import assert_knn_matches, recall
+from helpers import ATOL, ATOL_COSINE, assert_knn_matches, recall
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -35,7 +35,8 @@ def test_same_graph_matches_reference_golden(case):
         rec_gpu, rec_ref = recall(r.ids, g["exact_ids"]), recall(ref_ids, g["exact_ids"])
         assert rec_gpu >= rec_ref - 1e-9, f"{case} ef={ef}: recall {rec_gpu} < reference {rec_ref}"
         assert agreement(r.ids, ref_ids) >= 0.995, f"{case} ef={ef}: id agreement {agreement(r.ids, ref_ids)}"
-        assert_knn_matches(r.ids, r.distances, r.sizes, ref_ids, ref_d, g[f"counts_ef{ef}"], what=f"{case} ef={ef}")
+        assert_knn_matches(r.ids, r.distances, r.sizes, ref_ids, ref_d, g[f"counts_ef{ef}"], what=f"{case} ef={ef}",
+                           atol=ATOL_COSINE if str(g["space"]).startswith("cos") else ATOL)
     s = idx.stats()
     assert s["distance_evals"] > 0 and s["hnsw_expansions"] > 0
     idx.deinit()

@@ -10,7 +10,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from helpers import assert_knn_matches, recall
+from helpers import ATOL, ATOL_COSINE, assert_knn_matches, recall
 from oracle import oracle as O
 
 GOLDEN = Path(__file__).resolve().parent / "golden"

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import nmslib_zig_b200 as nb
-from helpers import assert_knn_matches
+from helpers import ATOL, ATOL_COSINE, assert_knn_matches
 from nmslib_zig_b200 import synth
 from oracle import oracle as O
 
@@ -34,7 +34,7 @@ def check_against_oracle(space, data, queries, k, ids=None, what=""):
     pos_of = {int(v): i for i, v in enumerate(ids_arr)}
     dist_of = lambda q, i: O.pair_distance(space, data[pos_of[i]], queries[q])
     assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, exact=(space == "l2sqr_sift"), dist_of=dist_of,
-                       what=what or space)
+                       what=what or space, atol=ATOL_COSINE if space.startswith("cos") else ATOL)
     idx.deinit()
     return r
 
@@ -51,7 +51,8 @@ def test_matches_reference_golden(case):
     pos_of = {int(v): i for i, v in enumerate(g["ids"])}
     dist_of = lambda q, i: O.pair_distance(space, g["data"][pos_of[i]], g["queries"][q])
     assert_knn_matches(r.ids, r.distances, r.sizes, g["ref_ids"], ref_d, g["ref_counts"],
-                       exact=(space == "l2sqr_sift"), dist_of=dist_of, what=case)
+                       exact=(space == "l2sqr_sift"), dist_of=dist_of, what=case,
+                       atol=ATOL_COSINE if space.startswith("cos") else ATOL)
     # the single-query entry (lib.zig knnQuery -> get_size + fill) is a batch of one
     one = idx.knnQuery(g["queries"][0], k)
     assert np.array_equal(one.ids, r.ids[0, : r.sizes[0]]) and np.array_equal(one.distances, r.distances[0, : r.sizes[0]])
@@ -116,7 +117,8 @@ def test_duplicates_zero_rows_and_tie_order():
         idx = make_index(space, d)
         r = idx.knnQueryBatch(q, 8)
         oi, od, oc = O.seq_knn(space, d, q, 8)
-        assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, what=f"ties/{space}")
+        assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, what=f"ties/{space}",
+                           atol=ATOL_COSINE if space.startswith("cos") else ATOL)
         if space in ("l2", "l2sqr"):
             assert np.array_equal(r.ids[:10, 0], np.arange(10, 20))          # the earlier duplicate wins
             assert np.array_equal(r.ids[:10, 1], np.arange(500, 510))
@@ -209,3 +211,19 @@ def test_config2_full_size_properties():
     r2 = idx.knnQueryBatch(q[:2048][perm], 10)
     assert np.array_equal(r2.ids, r.ids[:2048][perm]) and np.array_equal(r2.distances, r.distances[:2048][perm])
     idx.deinit()
+
+
+def test_tensor_core_path_is_the_one_that_runs_and_certifies():
+    """Float seq_search goes through the tcgen05 candidate pass + exact re-rank; the certificate
+    must hold for (nearly) every query on ordinary data, i.e. the exact-scan re-run stays idle."""
+    for space, data, q, k in [("l2sqr", synth.sift_like_f32(60_000, 3), synth.sift_like_f32(1_500, 4), 10),
+                              ("l2", synth.uniform(20_000, 128, 1), synth.uniform(700, 128, 2), 10),
+                              ("negdotprod", synth.embedding_like(30_000, 96, 9), synth.embedding_like(300, 96, 10), 100)]:
+        idx = make_index(space, data)
+        r = idx.knnQueryBatch(q, k)
+        st = idx.stats()
+        oi, od, oc = O.seq_knn(space, data, q, k)
+        assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, what=f"tc/{space}")
+        assert st["fallback_queries"] <= 0.02 * len(q), f"{space}: {st['fallback_queries']} uncertified queries"
+        assert st["scan_count"] >= 1 and st["last_scan_ms"] > 0
+        idx.deinit()
