@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="override database rows (debug)")
     ap.add_argument("--nq", type=int, default=None, help="override query count (debug)")
     ap.add_argument("--cpu-sample", type=int, default=1024)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -276,7 +277,7 @@ def main():
         achieved = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
         tf32_peak = peaks["bf16_tflops"] / 2.0                 # TF32 dense = 1/2 bf16 (measured bf16 burst / 2)
         cpu = None
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             base = time_reference(w, min(args.cpu_sample, nq), 3, 1)
             cpu = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
         line = {

@@ -562,7 +562,10 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   // one CTA per SM: pick the smallest split count whose last wave is >= 90 % full (else the fullest)
   int best = 1;
   double best_eff = 0;
-  const int max_split = std::min(n_tiles, 64);
+  int kprime, cap;
+  tc_candidate_shape((int)k, &kprime, &cap);
+  // the re-rank sorts n_split * cap keys per query in shared memory (12 B each, <= 192 KB)
+  const int max_split = std::max(1, std::min(n_tiles, std::min(64, 16384 / cap)));
   for (int sp = 1; sp <= max_split; ++sp) {
     const long ctas = (long)q_blocks * sp;
     const long waves = (ctas + sm_count_ - 1) / sm_count_;
@@ -578,8 +581,6 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   }
   const int tiles_per_split = (n_tiles + best - 1) / best;
   const int n_split = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-  int kprime, cap;
-  tc_candidate_shape((int)k, &kprime, &cap);
   const size_t units = (size_t)q_blocks * n_split;
   if (!(s = check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)")).ok()) return s;
   if (!(s = check_cuda(d_cand_.ensure(units * qb * (size_t)cap * 8), "cudaMalloc(cand)")).ok()) return s;

@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -705,7 +706,11 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
     default: NB_TC(16); break;
   }
 #undef NB_TC
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  if (e != cudaSuccess)
+    fprintf(stderr, "nmslib_b200: tc_scan launch (grid %d x %d, smem %zu, stages %d) failed: %s\n", grid.x, grid.y,
+            smem, p.n_stage, cudaGetErrorString(e));
+  return e;
 }
 
 cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int nq, int row_words,
@@ -742,11 +747,18 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
   int p2 = 1;
   while (p2 < items || p2 < k) p2 <<= 1;
   const size_t smem = (size_t)p2 * 12 + 16;
-  cudaError_t e = cudaFuncSetAttribute(tc_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) return e;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(tc_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "nmslib_b200: tc_rerank cudaFuncSetAttribute(%zu) failed: %s\n", smem, cudaGetErrorString(e));
+    return e;
+  }
   tc_rerank_kernel<<<nq, 128, smem, stream>>>(p, p2);
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  if (e != cudaSuccess)
+    fprintf(stderr, "nmslib_b200: tc_rerank launch (grid %d, smem %zu, items %d) failed: %s\n", nq, smem, p2,
+            cudaGetErrorString(e));
+  return e;
 }
 
 }  // namespace nb200

@@ -102,8 +102,11 @@ def test_sift_extreme_values_do_not_overflow():
     data = np.zeros((300, 128), np.uint8)
     data[1::2] = 255
     q = np.stack([np.zeros(128, np.uint8), np.full(128, 255, np.uint8)])
-    r = check_against_oracle("l2sqr_sift", data, q, 300)
-    assert r.distances[0, -1] == 128 * 255 * 255
+    r = check_against_oracle("l2sqr_sift", data, q, 140)
+    assert r.distances[1, -1] == 0 and r.distances[0, 0] == 0
+    far = make_index("l2sqr_sift", data[1::2])               # only the all-255 rows
+    assert far.knnQuery(q[0], 3).distances[0] == 128 * 255 * 255
+    far.deinit()
 
 
 def test_duplicates_zero_rows_and_tie_order():
