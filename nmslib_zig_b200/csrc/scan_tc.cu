@@ -17,17 +17,18 @@
 //        the TF32 error of pass 1.  If the exact k-th rank + E < thr the answer is provably the
 //        exact top-k; otherwise the query is re-run by the exact scan (scan_exact.cu).
 //
-// Kernel anatomy (one CTA per SM, 192 threads, no cluster):
+// Kernel anatomy (one CTA per SM, 320 threads, no cluster):
 //   warp 0   TMA producer: cp.async.bulk.tensor (128B-swizzled 128-row x 32-float boxes) into a
 //            ring of shared-memory stages, mbarrier complete_tx
 //   warp 1   TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer.  A CTA owns 256
 //            queries = two M=128 operand tiles, so every 128-row database tile that reaches
 //            shared memory feeds two MMAs (halves L2->SM traffic per flop); four 128-column fp32
 //            accumulators = all 512 TMEM columns, double buffered against the epilogue
-//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time (thread == TMEM lane == one query row),
-//            + bias, 3-input min tree, one compare per 32 values; survivors are appended to the
-//            row's candidate buffer; a full buffer is compacted warp-cooperatively
-//            (ballot-based radix select of the k'-th smallest).
+//   warps 2-9 epilogue (two per scheduler, one query row per thread): tcgen05.ld 32 columns at a
+//            time with the next load in flight, + bias, 3-input min tree, one compare per 32
+//            values; survivors (rare once the threshold is warm) are appended to the row's
+//            candidate buffer; a full buffer is compacted warp-cooperatively (ballot-based
+//            radix select of the k'-th smallest rank).
 #include <cuda.h>
 
 #include <algorithm>
@@ -44,7 +45,7 @@ constexpr int TC_QB = 256;          // queries per CTA
 constexpr int TC_BN = 128;          // database rows per tile
 constexpr int TC_KB = 32;           // floats per k-block: one 128-byte swizzle row
 constexpr int CHUNK_BYTES = TC_BM * TC_KB * 4;  // 16 KB: 128 rows x 128 B
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -152,13 +153,15 @@ __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(
 // (ties at the cut kept in buffer order), return the kprime-th smallest rank (ordered bits).
 template <int KPL>
 __device__ __forceinline__ uint32_t compact_row(uint64_t* buf, int cnt, int kprime, int lane) {
-  uint64_t key[KPL];
+  uint64_t key[KPL];   // (raw float rank bits << 32) | position
+  uint32_t ord[KPL];   // order-preserving image of the rank
   bool valid[KPL];
 #pragma unroll
   for (int s = 0; s < KPL; ++s) {
     const int i = s * 32 + lane;
     valid[s] = i < cnt;
     key[s] = valid[s] ? buf[i] : KEY_MAX;
+    ord[s] = f32_ordered(__uint_as_float((uint32_t)(key[s] >> 32)));
   }
   // smallest v with #(rank <= v) >= kprime: binary search over the 32-bit ordered rank
   uint32_t lo = 0, hi = 0xFFFFFFFFu;
@@ -166,7 +169,7 @@ __device__ __forceinline__ uint32_t compact_row(uint64_t* buf, int cnt, int kpri
     const uint32_t mid = lo + ((hi - lo) >> 1);
     int c = 0;
 #pragma unroll
-    for (int s = 0; s < KPL; ++s) c += __popc(__ballot_sync(FULL, valid[s] && (uint32_t)(key[s] >> 32) <= mid));
+    for (int s = 0; s < KPL; ++s) c += __popc(__ballot_sync(FULL, valid[s] && ord[s] <= mid));
     if (c >= kprime) hi = mid; else lo = mid + 1;
   }
   const uint32_t t = lo;
@@ -174,14 +177,14 @@ __device__ __forceinline__ uint32_t compact_row(uint64_t* buf, int cnt, int kpri
   int out = 0;
 #pragma unroll
   for (int s = 0; s < KPL; ++s) {  // strictly better than the cut
-    const bool keep = valid[s] && (uint32_t)(key[s] >> 32) < t;
+    const bool keep = valid[s] && ord[s] < t;
     const unsigned m = __ballot_sync(FULL, keep);
     if (keep) buf[out + __popc(m & ((1u << lane) - 1))] = key[s];
     out += __popc(m);
   }
 #pragma unroll
   for (int s = 0; s < KPL; ++s) {  // ties at the cut, up to kprime in total
-    const bool eq = valid[s] && (uint32_t)(key[s] >> 32) == t;
+    const bool eq = valid[s] && ord[s] == t;
     const unsigned m = __ballot_sync(FULL, eq);
     const int pos = out + __popc(m & ((1u << lane) - 1));
     if (eq && pos < kprime) buf[pos] = key[s];
@@ -207,14 +210,14 @@ template <int KPL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [A resident: 2*n_kb chunks] [stages: n_stage * stage_bytes] [bias: 2*128 f32] [barriers]
+  // carve: [A resident: 2*n_kb chunks] [stages: n_stage * stage_bytes] [bias: 8 warps x 128 f32] [barriers]
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;
   const int stage_bytes = p.a_resident ? CHUNK_BYTES : 3 * CHUNK_BYTES;  // B [+ A0 + A1]
   unsigned char* smem_a = smem;
   unsigned char* smem_st = smem + a_bytes;
   float* bias_s = reinterpret_cast<float*>(smem_st + (size_t)p.n_stage * stage_bytes);  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * TC_BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 8 * TC_BN);
   uint64_t* full_bar = bars;                   // [n_stage]
   uint64_t* empty_bar = bars + p.n_stage;      // [n_stage]
   uint64_t* tfull_bar = bars + 2 * p.n_stage;  // [2]
@@ -237,7 +240,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], 256);
     }
     mbar_init(afull_bar, 1);
     fence_barrier_init();
@@ -309,84 +312,100 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, thread == TMEM lane == query row =====================
-    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;       // row inside each 128-query half
+    // ===================== epilogue: 8 warps (2 per scheduler), thread == one query row ==========
+    // Warps 2-5 read operand half 0, warps 6-9 half 1; a warp may only touch the TMEM lane quarter
+    // (warp index % 4).  The warps never synchronise with each other: each stages the tile's 128
+    // bias values into its own slice of shared memory.
+    const int e = warp - 2;
+    const int h = e >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;       // row inside the 128-query half
     const size_t unit = (size_t)qblock * p.n_split + split;
-    uint64_t* buf[2];
-    float thr[2];
-    int cnt[2];
+    const bool row_valid = q0 + h * TC_BM + row < p.nq;
+    uint64_t* const buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
+    int cnt = 0;
+    float thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+    float* const my_bias = bias_s + e * TC_BN;
+    const float4* gbias = reinterpret_cast<const float4*>(p.bias);
+    float4 bias_next = n_tiles > 0 ? __ldg(gbias + (size_t)t0 * (TC_BN / 4) + lane) : make_float4(0, 0, 0, 0);
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    // one 32-column chunk: + bias, group minima, rare append of the values that beat the threshold
+    auto process = [&](const uint32_t (&v)[32], const float* bias32, uint32_t pos0) {
+      // make room first: a chunk may append up to 32 keys to a row
+      unsigned need = __ballot_sync(FULL, cnt > p.cap - 32);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf, src);
+        const int c = __shfl_sync(FULL, cnt, src);
+        const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, p.kprime, lane);
+        if (lane == src) {
+          cnt = p.kprime;
+          thr = f32_from_ordered(t);
+        }
+      }
+      const float4* b4 = reinterpret_cast<const float4*>(bias32);
+      float r[32];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      buf[h] = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
-      cnt[h] = 0;
-      thr[h] = (q0 + h * TC_BM + row < p.nq) ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
-    }
-    float bias_next = n_tiles > 0 ? p.bias[(size_t)t0 * TC_BN + row] : 0.f;
-    for (int ti = 0; ti < n_tiles; ++ti) {
-      const int b = ti & 1;
-      const int tile = t0 + ti;
-      bias_s[b * TC_BN + row] = bias_next;
-      if (ti + 1 < n_tiles) bias_next = p.bias[(size_t)(tile + 1) * TC_BN + row];
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue-only named barrier
-      mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
-      tc_fence_after();
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = b4[j];
+        r[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+        r[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+        r[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+        r[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+      }
+      float g[4];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll 1
-        for (int ch = 0; ch < TC_BN / 32; ++ch) {
-          // make room: a chunk may append up to 32 keys to a row
-          unsigned need = __ballot_sync(FULL, cnt[h] > p.cap - 32);
-          while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf[h], src);
-            const int c = __shfl_sync(FULL, cnt[h], src);
-            const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, p.kprime, lane);
-            if (lane == src) {
-              cnt[h] = p.kprime;
-              thr[h] = f32_from_ordered(t);
-            }
-          }
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + h) * TC_BN + ch * 32), v);
-          tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(bias_s + b * TC_BN + ch * 32);
-          float r[32];
+      for (int q = 0; q < 4; ++q)
+        g[q] = min3(min3(r[8 * q], r[8 * q + 1], r[8 * q + 2]), min3(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
+                    fminf(r[8 * q + 6], r[8 * q + 7]));
+      const float m = fminf(min3(g[0], g[1], g[2]), g[3]);
+      if (m < thr) {  // some value of this row beats its threshold: look only into the groups that do
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = b4[j];
-            r[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-            r[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-            r[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-            r[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
-          }
-          float m = min3(r[0], r[1], r[2]);
+        for (int q = 0; q < 4; ++q) {
+          if (g[q] < thr) {
 #pragma unroll
-          for (int j = 3; j + 1 < 32; j += 2) m = min3(m, r[j], r[j + 1]);
-          m = fminf(m, r[31]);
-          if (m < thr[h]) {  // rare once the threshold is warm
-            const uint32_t pos0 = p.pos_base + (uint32_t)(tile * TC_BN + ch * 32);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (r[j] < thr[h]) {
-                buf[h][cnt[h]] = make_key(f32_ordered(r[j]), pos0 + j);
-                ++cnt[h];
+            for (int j = 8 * q; j < 8 * q + 8; ++j) {
+              if (r[j] < thr) {
+                buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
+                ++cnt;
               }
             }
           }
         }
       }
+    };
+
+    for (int ti = 0; ti < n_tiles; ++ti) {
+      const int b = ti & 1;
+      const int tile = t0 + ti;
+      __syncwarp();
+      reinterpret_cast<float4*>(my_bias)[lane] = bias_next;
+      if (ti + 1 < n_tiles) bias_next = __ldg(gbias + (size_t)(tile + 1) * (TC_BN / 4) + lane);
+      __syncwarp();
+      mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tcol = trow + (uint32_t)((b * 2 + h) * TC_BN);
+      const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TC_BN);
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tcol, v0);
+#pragma unroll 1
+      for (int cp = 0; cp < TC_BN / 64; ++cp) {  // two chunks per iteration, next load in flight while computing
+        tmem_ld_wait();
+        tmem_ld32(tcol + (uint32_t)(cp * 64 + 32), v1);
+        process(v0, my_bias + cp * 64, pos_tile + cp * 64);
+        tmem_ld_wait();
+        if (cp + 1 < TC_BN / 64) tmem_ld32(tcol + (uint32_t)(cp * 64 + 64), v0);
+        process(v1, my_bias + cp * 64 + 32, pos_tile + cp * 64 + 32);
+      }
       tc_fence_before();
       mbar_arrive(&tempty_bar[b]);
     }
     // publish this split's per-row candidate count and final threshold
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const size_t slot = unit * TC_QB + h * TC_BM + row;
-      p.cand_cnt[slot] = (q0 + h * TC_BM + row < p.nq) ? cnt[h] : 0;
-      p.cand_thr[slot] = thr[h];
-    }
+    const size_t slot = unit * TC_QB + h * TC_BM + row;
+    p.cand_cnt[slot] = row_valid ? cnt : 0;
+    p.cand_thr[slot] = thr;
   }
 
   tc_fence_before();
@@ -448,13 +467,18 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
     s = warp_sum_f(s);
     if (lane == 0) s_qn2 = s;
   }
-  for (int t = tid; t < items_pow2; t += blockDim.x) {
+  __syncthreads();
+  const int total = s_off[p.n_split];
+  const float qn2 = s_qn2;
+  // sort only as many slots as this query actually has candidates (the buffers are mostly far from full)
+  int p2e = 32;
+  while (p2e < total || p2e < p.k) p2e <<= 1;
+  if (p2e > items_pow2) p2e = items_pow2;
+  for (int t = tid; t < p2e; t += blockDim.x) {
     sk[t] = KEY_MAX;
     srank[t] = __int_as_float(0x7F800000);
   }
   __syncthreads();
-  const int total = s_off[p.n_split];
-  const float qn2 = s_qn2;
   const int rw4 = p.row_words >> 2;
   const float4* q4 = reinterpret_cast<const float4*>(qv);
 
@@ -508,9 +532,9 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   __syncthreads();
 
   // sort (key, rank) ascending by key
-  for (int size = 2; size <= items_pow2; size <<= 1) {
+  for (int size = 2; size <= p2e; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < items_pow2 / 2; t += blockDim.x) {
+      for (int t = tid; t < p2e / 2; t += blockDim.x) {
         const int lo = 2 * t - (t & (stride - 1));
         const int hi = lo + stride;
         const bool up = (lo & size) == 0;
@@ -526,7 +550,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
       __syncthreads();
     }
   }
-  for (int e = tid; e < p.k; e += blockDim.x) p.out_keys[(size_t)q * p.k + e] = e < items_pow2 ? sk[e] : KEY_MAX;
+  for (int e = tid; e < p.k; e += blockDim.x) p.out_keys[(size_t)q * p.k + e] = e < p2e ? sk[e] : KEY_MAX;
 
   if (tid == 0) {
     // certificate: every non-candidate has approximate rank >= s_minthr, exact rank >= s_minthr - E
@@ -693,7 +717,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   p.n_stage = (budget - a_bytes) / stage_bytes;
   if (p.n_stage > 8) p.n_stage = 8;
   if (p.n_stage < 2) return cudaErrorInvalidValue;
-  const size_t smem = 1024 + (size_t)a_bytes + (size_t)p.n_stage * stage_bytes + 2 * TC_BN * 4 + (2 * 8 + 5) * 8 + 16;
+  const size_t smem = 1024 + (size_t)a_bytes + (size_t)p.n_stage * stage_bytes + 8 * TC_BN * 4 + (2 * 8 + 5) * 8 + 16;
   dim3 grid(n_split, (nq + TC_QB - 1) / TC_QB);
   cudaError_t e;
 #define NB_TC(KPL)                                                                                        \
