@@ -265,17 +265,21 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kb = 0; kb < p.n_kb; ++kb)
             tma_load_2d(&tmA, afull_bar, smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES, kb * TC_KB, q0 + h * TC_BM);
       }
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;  // ring position and its phase bit (no division in this loop: one thread issues it all)
       for (int t = t0; t < t1; ++t) {
-        for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-          const int s = it % p.n_stage;
-          mbar_wait(&empty_bar[s], ((it / p.n_stage) & 1) ^ 1);
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* st = smem_st + (size_t)s * stage_bytes;
           mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           tma_load_2d(&tmB, &full_bar[s], st, kb * TC_KB, t * TC_BN);
           if (!p.a_resident) {
             tma_load_2d(&tmA, &full_bar[s], st + CHUNK_BYTES, kb * TC_KB, q0);
             tma_load_2d(&tmA, &full_bar[s], st + 2 * CHUNK_BYTES, kb * TC_KB, q0 + TC_BM);
+          }
+          if (++s == p.n_stage) {
+            s = 0;
+            ph ^= 1;
           }
         }
       }
@@ -285,28 +289,40 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && n_tiles > 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
       if (p.a_resident) mbar_wait(afull_bar, 0);
-      int it = 0;
+      // This single thread must keep the tensor pipe fed (8 MMAs of 64 cycles per k-block), so the
+      // loop carries ring position / phase / descriptors incrementally: no division, no rebuild.
+      const uint32_t st_base = smem_u32(smem_st);
+      const uint32_t a_base = smem_u32(smem_a);
+      const uint64_t a_res = p.a_resident ? 1 : 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int ti = 0; ti < n_tiles; ++ti) {
         const int b = ti & 1;
         mbar_wait(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-          const int s = it % p.n_stage;
-          mbar_wait(&full_bar[s], (it / p.n_stage) & 1);
+        const uint32_t tmem_d0 = tmem_base + (uint32_t)(b * 2 * TC_BN);
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sb = smem_u32(smem_st + (size_t)s * stage_bytes);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t sa = p.a_resident ? smem_u32(smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES)
-                                             : sb + (uint32_t)(1 + h) * CHUNK_BYTES;
-            const uint32_t tmem_d = tmem_base + (uint32_t)((b * 2 + h) * TC_BN);
-#pragma unroll
-            for (int k = 0; k < TC_KB / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
-              umma_tf32(tmem_d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
-                        (uint32_t)((kb | k) != 0));
-            }
-          }
+          const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
+          const uint64_t db = make_smem_desc(sb);
+          const uint64_t da0 = make_smem_desc(a_res ? a_base + (uint32_t)kb * CHUNK_BYTES : sb + CHUNK_BYTES);
+          const uint64_t da1 = make_smem_desc(a_res ? a_base + (uint32_t)(p.n_kb + kb) * CHUNK_BYTES : sb + 2 * CHUNK_BYTES);
+          const uint32_t acc = kb != 0;
+          // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (address >> 4) field
+          umma_tf32(tmem_d0, da0, db, idesc, acc);
+          umma_tf32(tmem_d0, da0 + 2, db + 2, idesc, 1);
+          umma_tf32(tmem_d0, da0 + 4, db + 4, idesc, 1);
+          umma_tf32(tmem_d0, da0 + 6, db + 6, idesc, 1);
+          umma_tf32(tmem_d0 + TC_BN, da1, db, idesc, acc);
+          umma_tf32(tmem_d0 + TC_BN, da1 + 2, db + 2, idesc, 1);
+          umma_tf32(tmem_d0 + TC_BN, da1 + 4, db + 4, idesc, 1);
+          umma_tf32(tmem_d0 + TC_BN, da1 + 6, db + 6, idesc, 1);
           tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+          if (++s == p.n_stage) {
+            s = 0;
+            ph ^= 1;
+          }
         }
         tc_commit(&tfull_bar[b]);    // accumulators of tile ti are complete
       }
