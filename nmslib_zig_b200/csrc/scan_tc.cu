@@ -149,48 +149,67 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
 // ---------------------------------------------------------------- candidate buffers
-// Warp-cooperative compaction of one query row's buffer: keep the kprime smallest keys
-// (ties at the cut kept in buffer order), return the kprime-th smallest rank (ordered bits).
+// Warp-cooperative compaction of one query row's buffer.  Keeps the keys whose rank is <= a cut T
+// chosen so that between kprime and kprime + slack keys survive, and returns T (ordered bits): every
+// key that is dropped, now or later, has rank >= T, which is what the certificate of pass 2 needs.
+// The cut is found by bisecting the VALUE range [min, max] of the live ranks and stopping as soon as
+// the survivor count lands in the window -- typically 5-8 ballot rounds instead of a 32-step exact
+// select: a compaction stalls the TMEM pipeline of the whole CTA, so it has to be short.
 template <int KPL>
-__device__ __forceinline__ uint32_t compact_row(uint64_t* buf, int cnt, int kprime, int lane) {
+__device__ __forceinline__ uint32_t compact_row(uint64_t* buf, int cnt, int kprime, int slack, int lane,
+                                                int* new_cnt) {
   uint64_t key[KPL];   // (raw float rank bits << 32) | position
   uint32_t ord[KPL];   // order-preserving image of the rank
   bool valid[KPL];
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
 #pragma unroll
   for (int s = 0; s < KPL; ++s) {
     const int i = s * 32 + lane;
     valid[s] = i < cnt;
     key[s] = valid[s] ? buf[i] : KEY_MAX;
     ord[s] = f32_ordered(__uint_as_float((uint32_t)(key[s] >> 32)));
+    if (valid[s]) {
+      lo = min(lo, ord[s]);
+      hi = max(hi, ord[s]);
+    }
   }
-  // smallest v with #(rank <= v) >= kprime: binary search over the 32-bit ordered rank
-  uint32_t lo = 0, hi = 0xFFFFFFFFu;
+  lo = __reduce_min_sync(FULL, lo);
+  hi = __reduce_max_sync(FULL, hi);
+  const int limit = kprime + slack;
+  // invariant: #(rank <= hi) >= kprime
   while (lo < hi) {
     const uint32_t mid = lo + ((hi - lo) >> 1);
     int c = 0;
 #pragma unroll
     for (int s = 0; s < KPL; ++s) c += __popc(__ballot_sync(FULL, valid[s] && ord[s] <= mid));
-    if (c >= kprime) hi = mid; else lo = mid + 1;
+    if (c < kprime) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+      if (c <= limit) break;
+    }
   }
-  const uint32_t t = lo;
+  const uint32_t t = hi;
   __syncwarp();
   int out = 0;
 #pragma unroll
   for (int s = 0; s < KPL; ++s) {  // strictly better than the cut
     const bool keep = valid[s] && ord[s] < t;
     const unsigned m = __ballot_sync(FULL, keep);
-    if (keep) buf[out + __popc(m & ((1u << lane) - 1))] = key[s];
-    out += __popc(m);
+    const int pos = out + __popc(m & ((1u << lane) - 1));
+    if (keep && pos < limit) buf[pos] = key[s];
+    out = min(limit, out + __popc(m));
   }
 #pragma unroll
-  for (int s = 0; s < KPL; ++s) {  // ties at the cut, up to kprime in total
+  for (int s = 0; s < KPL; ++s) {  // ties at the cut, while there is room
     const bool eq = valid[s] && ord[s] == t;
     const unsigned m = __ballot_sync(FULL, eq);
     const int pos = out + __popc(m & ((1u << lane) - 1));
-    if (eq && pos < kprime) buf[pos] = key[s];
-    out = min(kprime, out + __popc(m));
+    if (eq && pos < limit) buf[pos] = key[s];
+    out = min(limit, out + __popc(m));
   }
   __syncwarp();
+  *new_cnt = out;
   return t;
 }
 
@@ -355,9 +374,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         need &= need - 1;
         const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf, src);
         const int c = __shfl_sync(FULL, cnt, src);
-        const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, p.kprime, lane);
+        int kept;
+        const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, p.kprime, 16, lane, &kept);
         if (lane == src) {
-          cnt = p.kprime;
+          cnt = kept;
           thr = f32_from_ordered(t);
         }
       }
