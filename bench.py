@@ -176,8 +176,8 @@ def main():
     w = workload(args.workload, args.n, args.nq)
     n, nq, dim, k = w["n"], w["nq"], w["dim"], w["k"]
     u8 = w["dtype"] == "DenseUInt8Vector"
-    lo = (n * rank) // world
-    hi = (n * (rank + 1)) // world
+    from nmslib_zig_b200.shard import shard_bounds
+    lo, hi = shard_bounds(n, rank, world)
     idx = nb.Index(w["space"], None, w["method"], w["dtype"], w["dist"])
     idx.setShard(lo)                                   # keys carry GLOBAL positions (tie order)
     shard_ids = np.arange(lo, hi, dtype=np.int32)
