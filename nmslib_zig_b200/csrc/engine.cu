@@ -87,7 +87,7 @@ Engine::~Engine() {
   for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
                     &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
                     &d_out_counts_, &d_bias_, &d_db_unit_, &d_flags_, &d_qa_, &d_cand_, &d_cand_cnt_, &d_cand_thr_,
-                    &d_tc_keys_, &d_cert_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_})
+                    &d_tc_keys_, &d_cert_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_})
     b->release();
   for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_}) b->release();
   for (auto& e : ev_)
@@ -372,9 +372,16 @@ Status Engine::upload_data() {
       unit = d_db_unit_.as<float>();
     }
     // flags layout: [0] database inexact, [1] query batch inexact, [2] max-norm bits
+    float* nblock = nullptr;
+    if (mode == SCAN_L2) {  // |x|^2 as an extra K=8 MMA step: [n_pad][32] TF32 pieces + a constant tile of ones
+      if (!(s = check_cuda(d_nblock_.ensure(n_pad * (size_t)tc_kblock_words() * 4), "cudaMalloc(nblock)")).ok()) return s;
+      if (!(s = check_cuda(d_ones_.ensure((size_t)128 * tc_kblock_words() * 4), "cudaMalloc(ones)")).ok()) return s;
+      nblock = d_nblock_.as<float>();
+    }
     s = check_cuda(launch_tc_prep_db(d_db_.as<float>(), (int)n_, (int)n_pad, row_words_, mode, d_bias_.as<float>(),
-                                     mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, unit,
-                                     d_flags_.as<unsigned>() + 2, d_flags_.as<int>(), stream_),
+                                     mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, unit, nblock,
+                                     nblock ? d_ones_.as<float>() : nullptr, d_flags_.as<unsigned>() + 2,
+                                     d_flags_.as<int>(), stream_),
                    "tc_prep_db");
     if (!s.ok()) return s;
     ++stats_.kernel_launches;
@@ -389,7 +396,7 @@ Status Engine::upload_data() {
   if (!s.ok()) return s;
   n_dev_ = n_;
   data_dirty_ = false;
-  stats_.device_bytes = d_db_.cap + d_ids_.cap + d_aux_.cap + d_bias_.cap + d_db_unit_.cap;
+  stats_.device_bytes = d_db_.cap + d_ids_.cap + d_aux_.cap + d_bias_.cap + d_db_unit_.cap + d_nblock_.cap;
   return Status::OK();
 }
 
@@ -558,34 +565,17 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   const size_t q_pad = round_up(nq, qb);
   const size_t n_pad = round_up(n_dev_, bn);
   const int q_blocks = (int)(q_pad / qb);
-  const int n_tiles = (int)(n_pad / bn);
-  // one CTA per SM: pick the smallest split count whose last wave is >= 80 % full (else the fullest)
-  int best = 1;
-  double best_eff = 0;
+  // equal linear ranges of the (query block x tile) grid, one CTA per SM (scan_tc.cu tc_plan)
+  int n_cta, work_per_cta, s_max;
+  tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &n_cta, &work_per_cta, &s_max);
   int kprime, cap;
   tc_candidate_shape((int)k, &kprime, &cap);
-  // the re-rank sorts n_split * cap keys per query in shared memory (12 B each, <= 192 KB)
-  const int max_split = std::max(1, std::min(n_tiles, std::min(64, 16384 / cap)));
-  for (int sp = 1; sp <= max_split; ++sp) {
-    const long ctas = (long)q_blocks * sp;
-    const long waves = (ctas + sm_count_ - 1) / sm_count_;
-    const double eff = (double)ctas / (double)(waves * sm_count_);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = sp;
-    }
-    if (eff >= 0.8) {  // fewer, longer splits keep the per-row thresholds tight (fewer candidate appends)
-      best = sp;
-      break;
-    }
-  }
-  const int tiles_per_split = (n_tiles + best - 1) / best;
-  const int n_split = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-  const size_t units = (size_t)q_blocks * n_split;
+  const size_t units = (size_t)q_blocks * s_max;
   if (!(s = check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)")).ok()) return s;
   if (!(s = check_cuda(d_cand_.ensure(units * qb * (size_t)cap * 8), "cudaMalloc(cand)")).ok()) return s;
   if (!(s = check_cuda(d_cand_cnt_.ensure(units * qb * 4), "cudaMalloc(cand_cnt)")).ok()) return s;
   if (!(s = check_cuda(d_cand_thr_.ensure(units * qb * 4), "cudaMalloc(cand_thr)")).ok()) return s;
+  if (!(s = check_cuda(cudaMemsetAsync(d_cand_cnt_.p, 0, units * qb * 4, stream), "memset(cand_cnt)")).ok()) return s;
   if (!(s = check_cuda(d_cert_.ensure(nq * 4), "cudaMalloc(cert)")).ok()) return s;
   if (!(s = check_cuda(h_cert_.ensure(nq * 4), "cudaMallocHost(cert)")).ok()) return s;
   if (!(s = check_cuda(cudaMemsetAsync(d_flags_.as<int>() + 1, 0, 4, stream), "memset(qflag)")).ok()) return s;
@@ -596,15 +586,16 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   if (!s.ok()) return s;
   const float* dbB = mode == SCAN_COSINE ? d_db_unit_.as<float>() : d_db_.as<float>();
   scan_begin(stream);
-  s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad, d_bias_.as<float>(), (int)n_dev_, (int)nq,
-                                row_words_, (int)k, pos_base_, n_split, tiles_per_split, d_cand_.as<uint64_t>(),
-                                d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(), stream),
+  s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad,
+                                mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(), (int)n_dev_,
+                                (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max,
+                                d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(), stream),
                  "tc_scan");
   scan_end(stream);
   if (!s.ok()) return s;
   s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
                                   mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)nq, row_words_, (int)k,
-                                  n_split, mode, pos_base_, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                                  s_max, mode, pos_base_, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
                                   d_cand_thr_.as<float>(), x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(),
                                   stream),
                  "tc_rerank");

@@ -163,7 +163,7 @@ class Engine {
   DevBuf d_db_, d_aux_, d_ids_;
   // tensor-core scan operands / scratch
   DevBuf d_bias_, d_db_unit_, d_flags_, d_qa_, d_cand_, d_cand_cnt_, d_cand_thr_, d_tc_keys_, d_cert_, d_fb_idx_,
-      d_fb_q_, d_fb_keys_;
+      d_fb_q_, d_fb_keys_, d_nblock_, d_ones_;
   PinBuf h_cert_;
   float x_max_ = 0.f;
   bool force_exact_ = false;

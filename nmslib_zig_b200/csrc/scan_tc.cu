@@ -214,43 +214,54 @@ __device__ __forceinline__ uint32_t compact_row(uint64_t* buf, int cnt, int kpri
 }
 
 struct TcParams {
-  const float* bias;       // [n_pad]: per database row bias, +inf on padding rows
-  int n, nq, n_kb, tiles_per_split, n_split;
+  int n, nq, n_kb;
+  int n_tiles;             // 128-row tiles per query block (whole shard)
+  int q_blocks;            // 256-query blocks
+  int work_per_cta;        // W: linear (query block, tile) items per CTA
+  int total_work;          // q_blocks * n_tiles
+  int s_max;               // candidate-buffer pieces per query block
   uint32_t pos_base;
-  uint64_t* cand;          // [units][256][cap]
-  int* cand_cnt;           // [units][256]
-  float* cand_thr;         // [units][256]   final threshold (rank domain), +inf if nothing was ever dropped
+  uint64_t* cand;          // [q_blocks][s_max][256][cap]
+  int* cand_cnt;           // [q_blocks][s_max][256]   (zeroed by the host before the launch)
+  float* cand_thr;         // [q_blocks][s_max][256]   final threshold (rank domain) of a piece that compacted
   int cap, kprime;
   int n_stage;             // shared-memory ring depth
-  int a_resident;          // 1: both query tiles stay in shared memory for the CTA's life (D <= 128)
+  int a_resident;          // 1: both query tiles stay in shared memory while a piece is scanned (D <= 128)
+  int use_nb;              // 1: an extra K=8 step adds |x|^2 (three TF32 pieces x 1.0) inside the MMA (l2)
 };
 
+// Work decomposition: the (query block, database tile) grid is cut into `gridDim.x` equal linear
+// ranges, so every SM gets the same number of tiles whatever the batch size; a CTA's range may
+// cross into the next query block, in which case it finishes one "piece" and starts another
+// (its own operand tiles, thresholds and candidate buffers).
 template <int KPL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmN, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [A resident: 2*n_kb chunks] [stages: n_stage * stage_bytes] [bias: 8 warps x 128 f32] [barriers]
+  // carve: [A resident: 2*n_kb chunks] [ones chunk] [stages: n_stage * stage_bytes] [barriers]
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;
+  const int ones_bytes = p.use_nb ? CHUNK_BYTES : 0;
   const int stage_bytes = p.a_resident ? CHUNK_BYTES : 3 * CHUNK_BYTES;  // B [+ A0 + A1]
   unsigned char* smem_a = smem;
-  unsigned char* smem_st = smem + a_bytes;
-  float* bias_s = reinterpret_cast<float*>(smem_st + (size_t)p.n_stage * stage_bytes);  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 8 * TC_BN);
+  unsigned char* smem_ones = smem + a_bytes;
+  unsigned char* smem_st = smem_ones + ones_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + (size_t)p.n_stage * stage_bytes);
   uint64_t* full_bar = bars;                   // [n_stage]
   uint64_t* empty_bar = bars + p.n_stage;      // [n_stage]
   uint64_t* tfull_bar = bars + 2 * p.n_stage;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
-  uint64_t* afull_bar = tempty_bar + 2;        // [1]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(afull_bar + 1);
+  uint64_t* afull_bar = tempty_bar + 2;        // [1] resident A tiles of the current piece have landed
+  uint64_t* aempty_bar = afull_bar + 1;        // [1] every MMA of the finished piece has read them
+  uint64_t* ones_bar = aempty_bar + 1;         // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ones_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int split = blockIdx.x, qblock = blockIdx.y;
-  const int q0 = qblock * TC_QB;
-  const int n_tiles_total = (p.n + TC_BN - 1) / TC_BN;
-  const int t0 = split * p.tiles_per_split;
-  const int t1 = min(t0 + p.tiles_per_split, n_tiles_total);
-  const int n_tiles = max(t1 - t0, 0);
+  const int cta = blockIdx.x;
+  const long w_begin = (long)cta * p.work_per_cta;
+  const long w_end = min(w_begin + (long)p.work_per_cta, (long)p.total_work);
+  const int n_kb_all = p.n_kb + p.use_nb;
 
   if (tid == 0) {
     for (int s = 0; s < p.n_stage; ++s) {
@@ -262,12 +273,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tempty_bar[b], 256);
     }
     mbar_init(afull_bar, 1);
+    mbar_init(aempty_bar, 1);
+    mbar_init(ones_bar, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.use_nb) prefetch_tmap(&tmN);
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
   tc_fence_before();
@@ -276,97 +290,134 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0 && n_tiles > 0) {
-      if (p.a_resident) {
-        mbar_expect_tx(afull_bar, (uint32_t)a_bytes);
-        for (int h = 0; h < 2; ++h)
-          for (int kb = 0; kb < p.n_kb; ++kb)
-            tma_load_2d(&tmA, afull_bar, smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES, kb * TC_KB, q0 + h * TC_BM);
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0 && w_begin < w_end) {
+      if (p.use_nb) {
+        mbar_expect_tx(ones_bar, CHUNK_BYTES);
+        tma_load_2d(&tmO, ones_bar, smem_ones, 0, 0);
       }
       int s = 0;
-      uint32_t ph = 0;  // ring position and its phase bit (no division in this loop: one thread issues it all)
-      for (int t = t0; t < t1; ++t) {
-        for (int kb = 0; kb < p.n_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          unsigned char* st = smem_st + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-          tma_load_2d(&tmB, &full_bar[s], st, kb * TC_KB, t * TC_BN);
-          if (!p.a_resident) {
-            tma_load_2d(&tmA, &full_bar[s], st + CHUNK_BYTES, kb * TC_KB, q0);
-            tma_load_2d(&tmA, &full_bar[s], st + 2 * CHUNK_BYTES, kb * TC_KB, q0 + TC_BM);
-          }
-          if (++s == p.n_stage) {
-            s = 0;
-            ph ^= 1;
+      uint32_t ph = 0;  // ring position and its phase bit (no division in the hot loop)
+      int piece = 0;
+      for (long w = w_begin; w < w_end; ++piece) {
+        const int qb = (int)(w / p.n_tiles);
+        const int t_begin = (int)(w - (long)qb * p.n_tiles);
+        const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
+        const int q0 = qb * TC_QB;
+        if (p.a_resident) {
+          if (piece > 0) mbar_wait(aempty_bar, (piece - 1) & 1);
+          mbar_expect_tx(afull_bar, (uint32_t)a_bytes);
+          for (int h = 0; h < 2; ++h)
+            for (int kb = 0; kb < p.n_kb; ++kb)
+              tma_load_2d(&tmA, afull_bar, smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES, kb * TC_KB,
+                          q0 + h * TC_BM);
+        }
+        for (int t = t_begin; t < t_end; ++t) {
+          for (int kb = 0; kb < n_kb_all; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            unsigned char* st = smem_st + (size_t)s * stage_bytes;
+            if (kb < p.n_kb) {
+              mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+              tma_load_2d(&tmB, &full_bar[s], st, kb * TC_KB, t * TC_BN);
+              if (!p.a_resident) {
+                tma_load_2d(&tmA, &full_bar[s], st + CHUNK_BYTES, kb * TC_KB, q0);
+                tma_load_2d(&tmA, &full_bar[s], st + 2 * CHUNK_BYTES, kb * TC_KB, q0 + TC_BM);
+              }
+            } else {  // the |x|^2 block of this tile
+              mbar_expect_tx(&full_bar[s], CHUNK_BYTES);
+              tma_load_2d(&tmN, &full_bar[s], st, 0, t * TC_BN);
+            }
+            if (++s == p.n_stage) {
+              s = 0;
+              ph ^= 1;
+            }
           }
         }
+        w += t_end - t_begin;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && n_tiles > 0) {
+    if (lane == 0 && w_begin < w_end) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
-      if (p.a_resident) mbar_wait(afull_bar, 0);
       // This single thread must keep the tensor pipe fed (8 MMAs of 64 cycles per k-block), so the
       // loop carries ring position / phase / descriptors incrementally: no division, no rebuild.
       const uint32_t st_base = smem_u32(smem_st);
       const uint32_t a_base = smem_u32(smem_a);
-      const uint64_t a_res = p.a_resident ? 1 : 0;
+      const uint64_t d_ones = make_smem_desc(smem_u32(smem_ones));
+      const bool a_res = p.a_resident != 0;
+      if (p.use_nb) mbar_wait(ones_bar, 0);
       int s = 0;
       uint32_t ph = 0;
-      for (int ti = 0; ti < n_tiles; ++ti) {
-        const int b = ti & 1;
-        mbar_wait(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d0 = tmem_base + (uint32_t)(b * 2 * TC_BN);
-        for (int kb = 0; kb < p.n_kb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
+      int ti = 0, piece = 0;
+      for (long w = w_begin; w < w_end; ++piece) {
+        const int qb = (int)(w / p.n_tiles);
+        const int t_begin = (int)(w - (long)qb * p.n_tiles);
+        const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
+        if (a_res) mbar_wait(afull_bar, piece & 1);
+        for (int t = t_begin; t < t_end; ++t, ++ti) {
+          const int b = ti & 1;
+          mbar_wait(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
-          const uint64_t db = make_smem_desc(sb);
-          const uint64_t da0 = make_smem_desc(a_res ? a_base + (uint32_t)kb * CHUNK_BYTES : sb + CHUNK_BYTES);
-          const uint64_t da1 = make_smem_desc(a_res ? a_base + (uint32_t)(p.n_kb + kb) * CHUNK_BYTES : sb + 2 * CHUNK_BYTES);
-          const uint32_t acc = kb != 0;
-          // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (address >> 4) field
-          umma_tf32(tmem_d0, da0, db, idesc, acc);
-          umma_tf32(tmem_d0, da0 + 2, db + 2, idesc, 1);
-          umma_tf32(tmem_d0, da0 + 4, db + 4, idesc, 1);
-          umma_tf32(tmem_d0, da0 + 6, db + 6, idesc, 1);
-          umma_tf32(tmem_d0 + TC_BN, da1, db, idesc, acc);
-          umma_tf32(tmem_d0 + TC_BN, da1 + 2, db + 2, idesc, 1);
-          umma_tf32(tmem_d0 + TC_BN, da1 + 4, db + 4, idesc, 1);
-          umma_tf32(tmem_d0 + TC_BN, da1 + 6, db + 6, idesc, 1);
-          tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
-          if (++s == p.n_stage) {
-            s = 0;
-            ph ^= 1;
+          const uint32_t tmem_d0 = tmem_base + (uint32_t)(b * 2 * TC_BN);
+          for (int kb = 0; kb < p.n_kb; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
+            const uint64_t db = make_smem_desc(sb);
+            const uint64_t da0 = make_smem_desc(a_res ? a_base + (uint32_t)kb * CHUNK_BYTES : sb + CHUNK_BYTES);
+            const uint64_t da1 =
+                make_smem_desc(a_res ? a_base + (uint32_t)(p.n_kb + kb) * CHUNK_BYTES : sb + 2 * CHUNK_BYTES);
+            const uint32_t acc = kb != 0;
+            // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (address >> 4) field
+            umma_tf32(tmem_d0, da0, db, idesc, acc);
+            umma_tf32(tmem_d0, da0 + 2, db + 2, idesc, 1);
+            umma_tf32(tmem_d0, da0 + 4, db + 4, idesc, 1);
+            umma_tf32(tmem_d0, da0 + 6, db + 6, idesc, 1);
+            umma_tf32(tmem_d0 + TC_BN, da1, db, idesc, acc);
+            umma_tf32(tmem_d0 + TC_BN, da1 + 2, db + 2, idesc, 1);
+            umma_tf32(tmem_d0 + TC_BN, da1 + 4, db + 4, idesc, 1);
+            umma_tf32(tmem_d0 + TC_BN, da1 + 6, db + 6, idesc, 1);
+            tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+            if (++s == p.n_stage) {
+              s = 0;
+              ph ^= 1;
+            }
           }
+          if (p.use_nb) {  // + 1.0 * (hi + mid + lo pieces of |x|^2): one K=8 step per operand half
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint64_t db = make_smem_desc(st_base + (uint32_t)s * (uint32_t)stage_bytes);
+            umma_tf32(tmem_d0, d_ones, db, idesc, 1);
+            umma_tf32(tmem_d0 + TC_BN, d_ones, db, idesc, 1);
+            tc_commit(&empty_bar[s]);
+            if (++s == p.n_stage) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+          tc_commit(&tfull_bar[b]);    // accumulators of this tile are complete
         }
-        tc_commit(&tfull_bar[b]);    // accumulators of tile ti are complete
+        if (a_res) tc_commit(aempty_bar);  // the resident operand tiles may be overwritten
+        w += t_end - t_begin;
       }
     }
   } else {
     // ===================== epilogue: 8 warps (2 per scheduler), thread == one query row ==========
     // Warps 2-5 read operand half 0, warps 6-9 half 1; a warp may only touch the TMEM lane quarter
-    // (warp index % 4).  The warps never synchronise with each other: each stages the tile's 128
-    // bias values into its own slice of shared memory.
+    // (warp index % 4).  The warps never synchronise with each other.  The accumulator already holds
+    // the rank (bias folded into the MMA), so the fast path is: tcgen05.ld, min tree, one compare.
     const int e = warp - 2;
     const int h = e >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;       // row inside the 128-query half
-    const size_t unit = (size_t)qblock * p.n_split + split;
-    const bool row_valid = q0 + h * TC_BM + row < p.nq;
-    uint64_t* const buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
-    int cnt = 0;
-    float thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
-    float* const my_bias = bias_s + e * TC_BN;
-    const float4* gbias = reinterpret_cast<const float4*>(p.bias);
-    float4 bias_next = n_tiles > 0 ? __ldg(gbias + (size_t)t0 * (TC_BN / 4) + lane) : make_float4(0, 0, 0, 0);
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint64_t* buf = nullptr;
+    int cnt = 0;
+    float thr = 0.f;
 
-    // one 32-column chunk: + bias, group minima, rare append of the values that beat the threshold
-    auto process = [&](const uint32_t (&v)[32], const float* bias32, uint32_t pos0) {
+    // one 32-column chunk; `vcols` = number of valid columns in it (< 32 only in the shard's last tile)
+    auto process = [&](const uint32_t (&v)[32], uint32_t pos0, int vcols) {
       // make room first: a chunk may append up to 32 keys to a row
       unsigned need = __ballot_sync(FULL, cnt > p.cap - 32);
       while (need) {
@@ -381,15 +432,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           thr = f32_from_ordered(t);
         }
       }
-      const float4* b4 = reinterpret_cast<const float4*>(bias32);
       float r[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 bb = b4[j];
-        r[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-        r[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-        r[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-        r[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+      for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+      if (vcols < 32) {  // padding rows of the database: never candidates
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j >= vcols) r[j] = __int_as_float(0x7F800000);
       }
       float g[4];
 #pragma unroll
@@ -413,35 +462,45 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
 
-    for (int ti = 0; ti < n_tiles; ++ti) {
-      const int b = ti & 1;
-      const int tile = t0 + ti;
-      __syncwarp();
-      reinterpret_cast<float4*>(my_bias)[lane] = bias_next;
-      if (ti + 1 < n_tiles) bias_next = __ldg(gbias + (size_t)(tile + 1) * (TC_BN / 4) + lane);
-      __syncwarp();
-      mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tcol = trow + (uint32_t)((b * 2 + h) * TC_BN);
-      const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TC_BN);
-      uint32_t v0[32], v1[32];
-      tmem_ld32(tcol, v0);
+    int ti = 0;
+    for (long w = w_begin; w < w_end;) {
+      const int qb = (int)(w / p.n_tiles);
+      const int t_begin = (int)(w - (long)qb * p.n_tiles);
+      const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
+      // piece slot of this CTA inside query block qb
+      const int first_cta = (int)(((long)qb * p.n_tiles) / p.work_per_cta);
+      const size_t unit = (size_t)qb * p.s_max + (cta - first_cta);
+      const bool row_valid = qb * TC_QB + h * TC_BM + row < p.nq;
+      buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
+      cnt = 0;
+      thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+      for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
+        const int b = ti & 1;
+        mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tcol = trow + (uint32_t)((b * 2 + h) * TC_BN);
+        const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TC_BN);
+        const int vtile = p.n - tile * TC_BN;  // >= 128 except in the last tile
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tcol, v0);
 #pragma unroll 1
-      for (int cp = 0; cp < TC_BN / 64; ++cp) {  // two chunks per iteration, next load in flight while computing
-        tmem_ld_wait();
-        tmem_ld32(tcol + (uint32_t)(cp * 64 + 32), v1);
-        process(v0, my_bias + cp * 64, pos_tile + cp * 64);
-        tmem_ld_wait();
-        if (cp + 1 < TC_BN / 64) tmem_ld32(tcol + (uint32_t)(cp * 64 + 64), v0);
-        process(v1, my_bias + cp * 64 + 32, pos_tile + cp * 64 + 32);
+        for (int cp = 0; cp < TC_BN / 64; ++cp) {  // two chunks per iteration, next load in flight while computing
+          tmem_ld_wait();
+          tmem_ld32(tcol + (uint32_t)(cp * 64 + 32), v1);
+          process(v0, pos_tile + cp * 64, vtile - cp * 64);
+          tmem_ld_wait();
+          if (cp + 1 < TC_BN / 64) tmem_ld32(tcol + (uint32_t)(cp * 64 + 64), v0);
+          process(v1, pos_tile + cp * 64 + 32, vtile - cp * 64 - 32);
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[b]);
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[b]);
+      // publish this piece's per-row candidate count and final threshold
+      const size_t slot = unit * TC_QB + h * TC_BM + row;
+      p.cand_cnt[slot] = row_valid ? cnt : 0;
+      p.cand_thr[slot] = thr;
+      w += t_end - t_begin;
     }
-    // publish this split's per-row candidate count and final threshold
-    const size_t slot = unit * TC_QB + h * TC_BM + row;
-    p.cand_cnt[slot] = row_valid ? cnt : 0;
-    p.cand_thr[slot] = thr;
   }
 
   tc_fence_before();
@@ -491,8 +550,9 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
     for (int s = 0; s < p.n_split; ++s) {
       const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
       s_off[s] = off;
-      off += p.cand_cnt[slot];
-      mt = fminf(mt, p.cand_thr[slot]);
+      const int c = p.cand_cnt[slot];
+      off += c;
+      if (c > 0) mt = fminf(mt, p.cand_thr[slot]);  // cnt == 0: piece unused, or it never dropped anything
     }
     s_off[p.n_split] = off;
     s_minthr = mt;
@@ -629,11 +689,13 @@ __global__ void tc_prep_queries_kernel(const float* __restrict__ q, float* __res
 // max operand-row norm, TF32-exactness flag.  One warp per row.
 __global__ void tc_prep_db_kernel(const float* __restrict__ db, int n, int n_pad, int row_words, int mode,
                                   float* __restrict__ bias, float* __restrict__ norm2, float* __restrict__ db_unit,
-                                  unsigned* __restrict__ max_norm_bits, int* __restrict__ inexact_flag) {
+                                  float* __restrict__ nblock, unsigned* __restrict__ max_norm_bits,
+                                  int* __restrict__ inexact_flag) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_pad) return;
   if (warp >= n) {
     if (lane == 0) bias[warp] = __int_as_float(0x7F800000);
+    if (nblock) nblock[(size_t)warp * TC_KB + lane] = 0.f;
     return;
   }
   const float* r = db + (size_t)warp * row_words;
@@ -653,6 +715,15 @@ __global__ void tc_prep_db_kernel(const float* __restrict__ db, int n, int n_pad
     for (int c = lane; c < row_words; c += 32) db_unit[(size_t)warp * row_words + c] = r[c] * inv;
     op_norm2 = s < eps ? 0.f : 1.0f;
     bad = 1;  // the normalised copy is never TF32-exact
+  }
+  if (nblock) {
+    // |x|^2 as three TF32-exact pieces (11 + 11 + 2 significant bits): hi + mid + lo == s exactly, so the
+    // tensor core adds the norm with fp32 accuracy in one K=8 step against a row of ones
+    const float hi = __uint_as_float(__float_as_uint(s) & 0xFFFFE000u);
+    const float r1 = s - hi;
+    const float mid = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
+    const float lo = r1 - mid;
+    nblock[(size_t)warp * TC_KB + lane] = lane == 0 ? hi : lane == 1 ? mid : lane == 2 ? lo : 0.f;
   }
   if (lane == 0) {
     bias[warp] = (mode == SCAN_L2) ? s : 0.f;
@@ -698,13 +769,48 @@ int tc_block_queries() { return TC_QB; }
 int tc_block_points() { return TC_BN; }
 int tc_kblock_words() { return TC_KB; }
 
+namespace {
+__global__ void tc_fill_ones_kernel(float* __restrict__ ones) {  // [128][32]: 1.0 in columns 0..2
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < TC_BM * TC_KB) ones[i] = (i % TC_KB) < 3 ? 1.0f : 0.0f;
+}
+}  // namespace
+
 cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, int mode, float* bias, float* norm2,
-                              float* db_unit, unsigned* max_norm_bits, int* inexact_flag, cudaStream_t stream) {
+                              float* db_unit, float* nblock, float* ones, unsigned* max_norm_bits,
+                              int* inexact_flag, cudaStream_t stream) {
   const int threads = 256;
   const int blocks = (int)(((size_t)n_pad * 32 + threads - 1) / threads);
-  tc_prep_db_kernel<<<blocks, threads, 0, stream>>>(db, n, n_pad, row_words, mode, bias, norm2, db_unit,
+  tc_prep_db_kernel<<<blocks, threads, 0, stream>>>(db, n, n_pad, row_words, mode, bias, norm2, db_unit, nblock,
                                                     max_norm_bits, inexact_flag);
+  if (ones) tc_fill_ones_kernel<<<(TC_BM * TC_KB + 255) / 256, 256, 0, stream>>>(ones);
   return cudaGetLastError();
+}
+
+// Balanced decomposition of the (query block x tile) grid over at most `sm_count` CTAs.
+void tc_plan(int nq, int n, int k, int sm_count, int* n_cta, int* work_per_cta, int* s_max) {
+  int kprime, cap;
+  tc_candidate_shape(k, &kprime, &cap);
+  const long q_blocks = (nq + TC_QB - 1) / TC_QB;
+  const long n_tiles = (n + TC_BN - 1) / TC_BN;
+  const long total = q_blocks * n_tiles;
+  long g = std::min<long>(sm_count, total);
+  // the re-rank sorts s_max * cap keys per query in shared memory: bound the pieces per query block
+  const long max_pieces = std::max<long>(2, 16384 / cap);
+  for (;; --g) {
+    const long w = (total + g - 1) / g;
+    long smax = 1;
+    for (long qb = 0; qb < q_blocks; ++qb) {
+      const long first = (qb * n_tiles) / w, last = ((qb + 1) * n_tiles - 1) / w;
+      smax = std::max(smax, last - first + 1);
+    }
+    if (smax <= max_pieces || g == 1) {
+      *n_cta = (int)((total + w - 1) / w);
+      *work_per_cta = (int)w;
+      *s_max = (int)smax;
+      return;
+    }
+  }
 }
 
 cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, float scale, int* inexact_flag,
@@ -727,39 +833,50 @@ void tc_candidate_shape(int k, int* kprime, int* cap) {
 }
 int tc_max_k() { return 256; }
 
-cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* bias, int n,
-                           int nq, int row_words, int k, uint32_t pos_base, int n_split, int tiles_per_split,
-                           uint64_t* cand, int* cand_cnt, float* cand_thr, cudaStream_t stream) {
+cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
+                           const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_cta,
+                           int work_per_cta, int s_max, uint64_t* cand, int* cand_cnt, float* cand_thr,
+                           cudaStream_t stream) {
   if (n <= 0 || nq <= 0) return cudaSuccess;
   if (row_words % TC_KB) return cudaErrorInvalidValue;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmN, tmO;
   if (!make_tmap(&tmA, qa, q_pad, row_words) || !make_tmap(&tmB, dbB, n_pad, row_words)) return cudaErrorUnknown;
+  const bool use_nb = nblock != nullptr;
+  if (use_nb) {
+    if (!make_tmap(&tmN, nblock, n_pad, TC_KB) || !make_tmap(&tmO, ones, TC_BM, TC_KB)) return cudaErrorUnknown;
+  } else {
+    tmN = tmB;
+    tmO = tmA;
+  }
   TcParams p;
-  p.bias = bias;
   p.n = n;
   p.nq = nq;
   p.n_kb = row_words / TC_KB;
-  p.tiles_per_split = tiles_per_split;
-  p.n_split = n_split;
+  p.n_tiles = (n + TC_BN - 1) / TC_BN;
+  p.q_blocks = (nq + TC_QB - 1) / TC_QB;
+  p.work_per_cta = work_per_cta;
+  p.total_work = p.q_blocks * p.n_tiles;
+  p.s_max = s_max;
   p.pos_base = pos_base;
   p.cand = cand;
   p.cand_cnt = cand_cnt;
   p.cand_thr = cand_thr;
   tc_candidate_shape(k, &p.kprime, &p.cap);
+  p.use_nb = use_nb ? 1 : 0;
   p.a_resident = (2 * p.n_kb * CHUNK_BYTES <= 128 * 1024) ? 1 : 0;
   const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;
+  const int ones_bytes = use_nb ? CHUNK_BYTES : 0;
   const int stage_bytes = p.a_resident ? CHUNK_BYTES : 3 * CHUNK_BYTES;
-  const int budget = 200 * 1024;
-  p.n_stage = (budget - a_bytes) / stage_bytes;
+  const int budget = 214 * 1024;
+  p.n_stage = (budget - a_bytes - ones_bytes) / stage_bytes;
   if (p.n_stage > 8) p.n_stage = 8;
   if (p.n_stage < 2) return cudaErrorInvalidValue;
-  const size_t smem = 1024 + (size_t)a_bytes + (size_t)p.n_stage * stage_bytes + 8 * TC_BN * 4 + (2 * 8 + 5) * 8 + 16;
-  dim3 grid(n_split, (nq + TC_QB - 1) / TC_QB);
+  const size_t smem = 1024 + (size_t)a_bytes + ones_bytes + (size_t)p.n_stage * stage_bytes + (2 * 8 + 8) * 8 + 16;
   cudaError_t e;
 #define NB_TC(KPL)                                                                                        \
   e = cudaFuncSetAttribute(tc_scan_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
   if (e != cudaSuccess) return e;                                                                         \
-  tc_scan_kernel<KPL><<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, p);
+  tc_scan_kernel<KPL><<<n_cta, TC_THREADS, smem, stream>>>(tmA, tmB, tmN, tmO, p);
   switch (p.cap) {
     case 128: NB_TC(4); break;
     case 256: NB_TC(8); break;
@@ -768,8 +885,8 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
 #undef NB_TC
   e = cudaGetLastError();
   if (e != cudaSuccess)
-    fprintf(stderr, "nmslib_b200: tc_scan launch (grid %d x %d, smem %zu, stages %d) failed: %s\n", grid.x, grid.y,
-            smem, p.n_stage, cudaGetErrorString(e));
+    fprintf(stderr, "nmslib_b200: tc_scan launch (grid %d, smem %zu, stages %d) failed: %s\n", n_cta, smem, p.n_stage,
+            cudaGetErrorString(e));
   return e;
 }
 
