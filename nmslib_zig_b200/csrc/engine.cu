@@ -566,8 +566,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   const size_t n_pad = round_up(n_dev_, bn);
   const int q_blocks = (int)(q_pad / qb);
   // equal linear ranges of the (query block x tile) grid, one CTA per SM (scan_tc.cu tc_plan)
-  int n_cta, work_per_cta, s_max;
-  tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &n_cta, &work_per_cta, &s_max);
+  int n_cta, work_per_cta, s_max, aligned;
+  tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &n_cta, &work_per_cta, &s_max, &aligned);
   int kprime, cap;
   tc_candidate_shape((int)k, &kprime, &cap);
   const size_t units = (size_t)q_blocks * s_max;
@@ -588,7 +588,7 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   scan_begin(stream);
   s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad,
                                 mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(), (int)n_dev_,
-                                (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max,
+                                (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
                                 d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(), stream),
                  "tc_scan");
   scan_end(stream);

@@ -228,6 +228,7 @@ struct TcParams {
   int n_stage;             // shared-memory ring depth
   int a_resident;          // 1: both query tiles stay in shared memory while a piece is scanned (D <= 128)
   int use_nb;              // 1: an extra K=8 step adds |x|^2 (three TF32 pieces x 1.0) inside the MMA (l2)
+  int aligned;             // 1: CTA = (segment, query block) with common tile boundaries; 0: equal linear ranges
 };
 
 // Work decomposition: the (query block, database tile) grid is cut into `gridDim.x` equal linear
@@ -259,8 +260,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
-  const long w_begin = (long)cta * p.work_per_cta;
-  const long w_end = min(w_begin + (long)p.work_per_cta, (long)p.total_work);
+  // aligned mode: CTA = (segment, query block), every query block is cut at the SAME tile boundaries and
+  // CTAs of one segment are neighbours in the grid, so co-resident CTAs sweep the same database tiles
+  // at the same time and the L2 serves all but one of them (the database is larger than the L2).
+  // linear mode (tiny batches): equal linear ranges of the (query block, tile) grid.
+  long w_begin, w_end;
+  if (p.aligned) {
+    const int qb_a = cta % p.q_blocks, seg = cta / p.q_blocks;
+    w_begin = (long)qb_a * p.n_tiles + min((long)seg * p.work_per_cta, (long)p.n_tiles);
+    w_end = (long)qb_a * p.n_tiles + min((long)(seg + 1) * p.work_per_cta, (long)p.n_tiles);
+  } else {
+    w_begin = (long)cta * p.work_per_cta;
+    w_end = min(w_begin + (long)p.work_per_cta, (long)p.total_work);
+  }
   const int n_kb_all = p.n_kb + p.use_nb;
 
   if (tid == 0) {
@@ -469,7 +481,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
       // piece slot of this CTA inside query block qb
       const int first_cta = (int)(((long)qb * p.n_tiles) / p.work_per_cta);
-      const size_t unit = (size_t)qb * p.s_max + (cta - first_cta);
+      const size_t unit = (size_t)qb * p.s_max + (p.aligned ? cta / p.q_blocks : cta - first_cta);
       const bool row_valid = qb * TC_QB + h * TC_BM + row < p.nq;
       buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
       cnt = 0;
@@ -787,16 +799,40 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
   return cudaGetLastError();
 }
 
-// Balanced decomposition of the (query block x tile) grid over at most `sm_count` CTAs.
-void tc_plan(int nq, int n, int k, int sm_count, int* n_cta, int* work_per_cta, int* s_max) {
+// Decomposition of the (query block x tile) grid over the SMs (one CTA per SM).
+//  * aligned: every query block is cut into the same `s` segments; q_blocks * s CTAs.  Chosen when some s
+//    fills >= 80 % of the last wave: co-scheduled CTAs then stream the same tiles and share them in L2.
+//  * linear (few query blocks): equal linear ranges, `sm_count` CTAs, a CTA may span two query blocks.
+void tc_plan(int nq, int n, int k, int sm_count, int* n_cta, int* work_per_cta, int* s_max, int* aligned) {
   int kprime, cap;
   tc_candidate_shape(k, &kprime, &cap);
   const long q_blocks = (nq + TC_QB - 1) / TC_QB;
   const long n_tiles = (n + TC_BN - 1) / TC_BN;
   const long total = q_blocks * n_tiles;
-  long g = std::min<long>(sm_count, total);
   // the re-rank sorts s_max * cap keys per query in shared memory: bound the pieces per query block
   const long max_pieces = std::max<long>(2, 16384 / cap);
+  if (q_blocks * 4 >= sm_count || q_blocks * n_tiles <= sm_count) {
+    long best = 1;
+    double best_eff = 0;
+    for (long sp = 1; sp <= std::min<long>(n_tiles, max_pieces); ++sp) {
+      const long ctas = q_blocks * sp;
+      const long waves = (ctas + sm_count - 1) / sm_count;
+      const double eff = (double)ctas / (double)(waves * sm_count);
+      if (eff > best_eff + 1e-9) {
+        best_eff = eff;
+        best = sp;
+      }
+      if (eff >= 0.8) break;
+    }
+    const long w = (n_tiles + best - 1) / best;
+    const long segs = (n_tiles + w - 1) / w;
+    *n_cta = (int)(q_blocks * segs);
+    *work_per_cta = (int)w;
+    *s_max = (int)segs;
+    *aligned = 1;
+    return;
+  }
+  long g = std::min<long>(sm_count, total);
   for (;; --g) {
     const long w = (total + g - 1) / g;
     long smax = 1;
@@ -808,17 +844,10 @@ void tc_plan(int nq, int n, int k, int sm_count, int* n_cta, int* work_per_cta, 
       *n_cta = (int)((total + w - 1) / w);
       *work_per_cta = (int)w;
       *s_max = (int)smax;
+      *aligned = 0;
       return;
     }
   }
-}
-
-cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, float scale, int* inexact_flag,
-                                   cudaStream_t stream) {
-  int blocks = (int)std::min<size_t>((words + 255) / 256, 148 * 8);
-  if (blocks < 1) blocks = 1;
-  tc_prep_queries_kernel<<<blocks, 256, 0, stream>>>(q, out, words, scale, inexact_flag);
-  return cudaGetLastError();
 }
 
 // cand capacity per (unit,row) and survivors per compaction for a given k
@@ -835,8 +864,8 @@ int tc_max_k() { return 256; }
 
 cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
                            const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_cta,
-                           int work_per_cta, int s_max, uint64_t* cand, int* cand_cnt, float* cand_thr,
-                           cudaStream_t stream) {
+                           int work_per_cta, int s_max, int aligned, uint64_t* cand, int* cand_cnt,
+                           float* cand_thr, cudaStream_t stream) {
   if (n <= 0 || nq <= 0) return cudaSuccess;
   if (row_words % TC_KB) return cudaErrorInvalidValue;
   CUtensorMap tmA, tmB, tmN, tmO;
@@ -857,6 +886,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   p.work_per_cta = work_per_cta;
   p.total_work = p.q_blocks * p.n_tiles;
   p.s_max = s_max;
+  p.aligned = aligned;
   p.pos_base = pos_base;
   p.cand = cand;
   p.cand_cnt = cand_cnt;
