@@ -850,6 +850,14 @@ void tc_plan(int nq, int n, int k, int sm_count, int* n_cta, int* work_per_cta, 
   }
 }
 
+cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, float scale, int* inexact_flag,
+                                   cudaStream_t stream) {
+  int blocks = (int)std::min<size_t>((words + 255) / 256, 148 * 8);
+  if (blocks < 1) blocks = 1;
+  tc_prep_queries_kernel<<<blocks, 256, 0, stream>>>(q, out, words, scale, inexact_flag);
+  return cudaGetLastError();
+}
+
 // cand capacity per (unit,row) and survivors per compaction for a given k
 void tc_candidate_shape(int k, int* kprime, int* cap) {
   int kp = k + 22 < 2 * k ? k + 22 + (k / 4) : 2 * k;  // headroom for the certificate
