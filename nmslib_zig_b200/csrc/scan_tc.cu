@@ -33,6 +33,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -82,6 +83,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// pull a box into L2 only (no shared-memory slot needed): issued a couple of tiles ahead of the real
+// load so that the ring of shared-memory stages only ever waits for L2-hit latency
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -229,6 +238,8 @@ struct TcParams {
   int a_resident;          // 1: both query tiles stay in shared memory while a piece is scanned (D <= 128)
   int use_nb;              // 1: an extra K=8 step adds |x|^2 (three TF32 pieces x 1.0) inside the MMA (l2)
   int aligned;             // 1: CTA = (segment, query block) with common tile boundaries; 0: equal linear ranges
+  int l2_ahead;            // tiles of L2 prefetch distance (0 = off)
+  int debug;               // NB200_TC_DEBUG bit 0: epilogue drains TMEM without selecting (timing experiments only)
 };
 
 // Work decomposition: the (query block, database tile) grid is cut into `gridDim.x` equal linear
@@ -325,6 +336,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                           q0 + h * TC_BM);
         }
         for (int t = t_begin; t < t_end; ++t) {
+          if (p.l2_ahead > 0 && t + p.l2_ahead < t_end) {
+            for (int kb = 0; kb < p.n_kb; ++kb) tma_prefetch_l2_2d(&tmB, kb * TC_KB, (t + p.l2_ahead) * TC_BN);
+            if (p.use_nb) tma_prefetch_l2_2d(&tmN, 0, (t + p.l2_ahead) * TC_BN);
+          }
           for (int kb = 0; kb < n_kb_all; ++kb) {
             mbar_wait(&empty_bar[s], ph ^ 1);
             unsigned char* st = smem_st + (size_t)s * stage_bytes;
@@ -494,6 +509,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TC_BN);
         const int vtile = p.n - tile * TC_BN;  // >= 128 except in the last tile
         uint32_t v0[32], v1[32];
+        if (p.debug & 1) {  // timing experiment: touch the accumulators, select nothing
+          tmem_ld32(tcol, v0);
+          tmem_ld_wait();
+          if (__uint_as_float(v0[0]) == 1.2345e-30f) thr = 0.f;
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[b]);
+          continue;
+        }
         tmem_ld32(tcol, v0);
 #pragma unroll 1
         for (int cp = 0; cp < TC_BN / 64; ++cp) {  // two chunks per iteration, next load in flight while computing
@@ -901,6 +924,12 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   p.cand_thr = cand_thr;
   tc_candidate_shape(k, &p.kprime, &p.cap);
   p.use_nb = use_nb ? 1 : 0;
+  {
+    const char* dbg = getenv("NB200_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    const char* la = getenv("NB200_TC_L2AHEAD");
+    p.l2_ahead = la ? atoi(la) : 2;
+  }
   p.a_resident = (2 * p.n_kb * CHUNK_BYTES <= 128 * 1024) ? 1 : 0;
   const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;
   const int ones_bytes = use_nb ? CHUNK_BYTES : 0;
