@@ -572,8 +572,11 @@ nmslib_error_t nmslib_save_index(nmslib_index_handle_t index, const char* path, 
           if (!ok) return NB_ERR(NMSLIB_ERROR_DATA_IO_FAILED, "Failed to save index: short write");
         }
         if (e->method() == nb200::METHOD_HNSW) {
-          if (e->graph().empty()) return NB_ERR(NMSLIB_ERROR_DATA_IO_FAILED, "Failed to save index: no HNSW graph");
-          Status s = nb200::write_hnsw_file(path, e->graph(), e->row_f32(0), e->graph().ext_ids.data());
+          if (e->graph().empty()) {  // not queried yet: build now (the reference builds at create_index time)
+            Status ps = e->ensure_graph_host();
+            if (!ps.ok()) return NB_STATUS(ps);
+          }
+          Status s = nb200::write_hnsw_file(path, e->graph(), e->hnsw_rows_for_save(), e->graph().ext_ids.data());
           if (!s.ok()) return NB_STATUS(s);
         } else {
           // SeqSearch has no SaveIndex in the reference (index.h:56-58 throws); we leave a marker

@@ -125,6 +125,8 @@ Status Engine::add_rows(const void* rows, size_t count, size_t elem_count, const
   for (size_t i = 0; i < count; ++i) h_ids_.push_back(ids ? ids[i] : (int32_t)i);  // nmslib_c.cpp:768
   n_ += count;
   data_dirty_ = true;
+  rows_normalized_ = false;
+  h_hnsw_rows_.clear();
   if (method_ == METHOD_HNSW && !graph_.empty()) {
     graph_ = HnswGraph();  // the graph no longer describes the data
     graph_dirty_ = true;
@@ -153,6 +155,8 @@ void Engine::reset() {
   graph_ = HnswGraph();
   data_dirty_ = graph_dirty_ = true;
   n_dev_ = 0;
+  rows_normalized_ = false;
+  h_hnsw_rows_.clear();
 }
 
 float Engine::host_distance(size_t a, size_t b) const {
@@ -247,6 +251,8 @@ Status Engine::adopt_graph(HnswGraph&& g) {
   h_ids_ = graph_.ext_ids;
   graph_.vectors.clear();
   graph_.vectors.shrink_to_fit();
+  rows_normalized_ = true;  // the file stores cosine rows already normalised
+  h_hnsw_rows_.clear();
   data_dirty_ = graph_dirty_ = true;
   built_ = true;
   return Status::OK();
@@ -289,7 +295,30 @@ Stats Engine::stats() {
   return stats_;
 }
 
+// Rows as the HNSW kernels want them: float32, unit-normalised for cosine (the reference normalises its
+// flat index once at build time, hnsw.cc:441-446), uint8 widened to float (distances stay exact integers).
+const float* Engine::hnsw_host_rows() {
+  if (!is_u8_ && (space_ != SPACE_COSINE || rows_normalized_)) return h_f32_.data();
+  if (h_hnsw_rows_.size() == n_ * (size_t)dim_) return h_hnsw_rows_.data();
+  h_hnsw_rows_.resize(n_ * (size_t)dim_);
+  for (size_t i = 0; i < n_; ++i) {
+    float* dst = &h_hnsw_rows_[i * (size_t)dim_];
+    if (is_u8_) {
+      const uint8_t* r = row_u8(i);
+      for (int j = 0; j < dim_; ++j) dst[j] = (float)r[j];
+    } else {
+      const float* r = row_f32(i);
+      float sum = 0.f;
+      for (int j = 0; j < dim_; ++j) sum += r[j] * r[j];
+      const float sc = sum != 0.f ? 1.f / std::sqrt(sum) : 1.f;  // NormalizeVect, hnsw.h:486-497
+      for (int j = 0; j < dim_; ++j) dst[j] = r[j] * sc;
+    }
+  }
+  return h_hnsw_rows_.data();
+}
+
 int Engine::finalize_kind() const {
+  if (method_ == METHOD_HNSW) return FIN_FLOAT;  // squared / cosine / negdot / (uint8: exact integers held in fp32)
   if (is_u8_) return FIN_INT;
   // l2 + seq_search reports the root; l2 + hnsw reports the squared distance
   if (space_ == SPACE_L2 && method_ == METHOD_SEQ) return FIN_SQRT;
@@ -333,16 +362,18 @@ Status Engine::upload_data() {
   // HBM layout: row-major [n_pad][row_words] 32-bit words, rows zero padded to a whole
   // pipeline stage (64 B) and the row count to a whole tile, so no kernel needs edge code.
   // float rows are padded to 128 bytes (one TMA / UMMA swizzle row of the tensor-core scan)
-  row_words_ = (int)round_up(is_u8_ ? (size_t)dim_ / 4 : (size_t)dim_, is_u8_ ? stage : tc_kblock_words());
-  if (is_u8_ && dim_ % 4) return Status::Err(kErrInvalid, "uint8 dimension must be a multiple of 4");
+  const bool dev_u8 = dev_u8_rows();
+  row_words_ = (int)round_up(dev_u8 ? (size_t)dim_ / 4 : (size_t)dim_, dev_u8 ? stage : tc_kblock_words());
+  if (dev_u8 && dim_ % 4) return Status::Err(kErrInvalid, "uint8 dimension must be a multiple of 4");
   const size_t n_pad = round_up(n_, bn);
   const size_t row_bytes = (size_t)row_words_ * 4;
   Status s = check_cuda(d_db_.ensure(n_pad * row_bytes), "cudaMalloc(data)");
   if (!s.ok()) return s;
   s = check_cuda(cudaMemsetAsync(d_db_.p, 0, n_pad * row_bytes, stream_), "memset(data)");
   if (!s.ok()) return s;
-  const size_t src_row = is_u8_ ? (size_t)dim_ : (size_t)dim_ * 4;
-  const void* src = is_u8_ ? (const void*)h_u8_.data() : (const void*)h_f32_.data();
+  const size_t src_row = dev_u8 ? (size_t)dim_ : (size_t)dim_ * 4;
+  const void* src = dev_u8 ? (const void*)h_u8_.data() : (const void*)h_f32_.data();
+  if (method_ == METHOD_HNSW) src = hnsw_host_rows();  // float rows; cosine: unit-normalised (hnsw.cc:441-446)
   s = check_cuda(cudaMemcpy2DAsync(d_db_.p, row_bytes, src, src_row, src_row, n_, cudaMemcpyHostToDevice, stream_),
                  "H2D(data)");
   if (!s.ok()) return s;
@@ -350,7 +381,7 @@ Status Engine::upload_data() {
   if (!s.ok()) return s;
   s = check_cuda(cudaMemcpyAsync(d_ids_.p, h_ids_.data(), n_ * 4, cudaMemcpyHostToDevice, stream_), "H2D(ids)");
   if (!s.ok()) return s;
-  if (space_ == SPACE_COSINE || is_u8_) {
+  if (method_ == METHOD_SEQ && (space_ == SPACE_COSINE || is_u8_)) {
     s = check_cuda(d_aux_.ensure(n_pad * 4), "cudaMalloc(aux)");
     if (!s.ok()) return s;
     s = check_cuda(launch_row_aux(is_u8_, d_db_.p, (int)n_, row_words_, d_aux_.p, stream_), "row_aux");
@@ -400,11 +431,25 @@ Status Engine::upload_data() {
   return Status::OK();
 }
 
+// No imported graph: build one on the host cores (hnsw_build.cpp) with the index-time parameters
+// recorded by nmslib_create_index (the reference drops them).  Needs no GPU.
+Status Engine::ensure_graph_host() {
+  if (method_ != METHOD_HNSW || !graph_.empty()) return Status::OK();
+  if (n_ == 0) return Status::Err(kErrBuild, "hnsw index holds no data");
+  const int dist_func = space_ == SPACE_COSINE ? 3 : space_ == SPACE_NEGDOT ? 4 : (dim_ % 16 == 0 ? 1 : 2);
+  HnswGraph g;
+  Status bs = build_hnsw_host(hnsw_host_rows(), n_, dim_, dist_func, h_ids_.data(), index_params_, &g);
+  if (!bs.ok()) return bs;
+  graph_ = std::move(g);
+  graph_dirty_ = true;
+  return Status::OK();
+}
+
 Status Engine::upload_graph() {
-  if (graph_.empty())
-    return Status::Err(kErrBuild,
-                       "hnsw index has no graph: import one built by the reference (nmslib_b200_import_hnsw / "
-                       "nmslib_load_index); graph construction stays on the reference CPU code");
+  {
+    Status bs = ensure_graph_host();
+    if (!bs.ok()) return bs;
+  }
   if (graph_.total != n_) return Status::Err(kErrBuild, "HNSW graph / data size mismatch");
   const HnswGraph& g = graph_;
   Status s = check_cuda(d_links0_.ensure(std::max<size_t>(g.links0.size(), 1) * 4), "cudaMalloc(links0)");
@@ -453,7 +498,7 @@ Status Engine::stage_queries_device(const void* src, bool src_on_device, size_t 
     s = check_cuda(cudaMemsetAsync(d_q_.p, 0, d_q_.cap, stream), "memset(queries)");
     if (!s.ok()) return s;
   }
-  const size_t src_row = is_u8_ ? elem_count : elem_count * 4;
+  const size_t src_row = dev_u8_rows() ? elem_count : elem_count * 4;
   return check_cuda(cudaMemcpy2DAsync(d_q_.p, row_bytes, src, src_row, src_row, nq,
                                       src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream),
                     "copy(queries)");
@@ -649,6 +694,8 @@ Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, s
   if (method_ == METHOD_SEQ && k > (size_t)scan_exact_max_k())
     return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported yet");
   if (method_ == METHOD_HNSW && k > (size_t)hnsw_max_ef()) return Status::Err(kErrTooLarge, "k too large for hnsw");
+  if (is_u8_ && method_ == METHOD_HNSW)
+    return Status::Err(kErrIncompat, "device-resident uint8 queries are not supported for hnsw (use the host entry)");
   cudaStream_t st = stream ? stream : stream_;
   s = stage_queries_device(d_queries, true, nq, elem_count, st);
   if (!s.ok()) return s;
@@ -681,6 +728,12 @@ Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_
   if (!(s = check_cuda(h_out_counts_.ensure(nq * 4), "cudaMallocHost(counts)")).ok()) return s;
 
   cudaEventRecord(ev_[0], stream_);
+  if (is_u8_ && method_ == METHOD_HNSW) {  // uint8 + hnsw runs on float rows: widen the queries
+    h_q_widen_.resize(nq * elem_count);
+    const uint8_t* qs = static_cast<const uint8_t*>(queries);
+    for (size_t i = 0; i < nq * elem_count; ++i) h_q_widen_[i] = (float)qs[i];
+    queries = h_q_widen_.data();
+  }
   s = stage_queries_device(queries, false, nq, elem_count, stream_);
   if (!s.ok()) return s;
   cudaEventRecord(ev_[1], stream_);

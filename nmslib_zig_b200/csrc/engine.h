@@ -67,6 +67,9 @@ struct HnswGraph {
 };
 Status read_hnsw_file(const std::string& path, HnswGraph* out);
 // vectors / ext_ids: [total][dim] and [total] (the Engine keeps them outside the graph)
+// host-side graph construction (hnsw_build.cpp): rows are float32 (cosine: unit-normalised)
+Status build_hnsw_host(const float* rows, size_t n, int dim, int dist_func, const int32_t* ext_ids,
+                       const std::vector<std::string>& params, HnswGraph* out);
 Status write_hnsw_file(const std::string& path, const HnswGraph& g, const float* vectors,
                        const int32_t* ext_ids);
 
@@ -103,8 +106,10 @@ class Engine {
   Status import_graph(const std::string& path);
   Status adopt_graph(HnswGraph&& g);
   const HnswGraph& graph() const { return graph_; }
+  const float* hnsw_rows_for_save() { return hnsw_host_rows(); }
   void set_pos_base(uint32_t b) { pos_base_ = b; }
   Status prepare();  // lazy upload; idempotent
+  Status ensure_graph_host();  // hnsw: build the graph on the host if none was imported (no GPU needed)
 
   // ---- queries ----
   // host in / host out: ids/dists are [nq][k] staging arrays owned by the engine
@@ -119,9 +124,11 @@ class Engine {
   std::mutex& mutex() { return mu_; }
   size_t ef() const { return ef_; }
   int finalize_kind() const;
+  bool dev_u8_rows() const { return is_u8_ && method_ == METHOD_SEQ; }
 
  private:
   Status check_cuda(cudaError_t e, const char* what);
+  const float* hnsw_host_rows();
   Status upload_data();
   Status upload_graph();
   Status run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream);
@@ -148,6 +155,8 @@ class Engine {
   std::vector<float> h_f32_;
   std::vector<uint8_t> h_u8_;
   std::vector<int32_t> h_ids_;
+  std::vector<float> h_hnsw_rows_, h_q_widen_;  // float / normalised rows for hnsw; widened uint8 queries
+  bool rows_normalized_ = false;
   HnswGraph graph_;
 
   cudaStream_t stream_ = nullptr;

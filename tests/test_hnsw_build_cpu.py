@@ -1,0 +1,83 @@
+"""The host-side HNSW builder (csrc/hnsw_build.cpp; index build is not the hot path, it only makes the
+library usable on its own): the graph it emits is in the reference's optimized-index format, is
+searchable by the oracle's restatement of Hnsw::SearchV1Merge and by the UNMODIFIED reference
+(nmslib_load_index), and its recall is in the reference builder's league.  CPU only."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import nmslib_zig_b200 as nb
+from helpers import recall
+from nmslib_zig_b200 import synth
+from oracle import oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _build(space, data, params, path, ids=None):
+    idx = nb.Index(space, None, "hnsw")
+    idx.addDenseBatch(data, ids)
+    idx.buildIndex(nb.Params(params))
+    idx.save(str(path), True)          # builds on the host cores; no GPU involved
+    idx.deinit()
+
+
+@pytest.mark.parametrize("space", ["l2", "cosinesimil", "negdotprod"])
+def test_built_graph_is_searchable_and_accurate(space, tmp_path):
+    data = synth.gist_like(6000, 24, 41, clusters=12)
+    q = synth.gist_like(100, 24, 42, clusters=12)
+    path = tmp_path / "g.hnsw"
+    _build(space, data, {"M": 12, "efConstruction": 100}, path)
+    h = O.PortHnsw(path)
+    assert (h.total, h.dim, h.maxM, h.maxM0) == (6000, 24, 12, 24)
+    assert h.dist_func == {"l2": 2, "cosinesimil": 3, "negdotprod": 4}[space]   # dim % 16 != 0 -> L2SqrExt
+    exact, _, _ = O.seq_knn(space, data, q, 10)
+    ids, d, c, _ = h.knn(q, 10, 100)
+    assert recall(ids, exact) >= 0.95
+    assert np.all(c == 10) and np.all(np.diff(d, axis=1) >= 0)
+    h.close()
+
+
+def test_three_point_index_like_lib_zig_tests(tmp_path):
+    """lib.zig:1273-1313 builds hnsw over 3 points; the builder must cope with tiny inputs."""
+    path = tmp_path / "tiny.hnsw"
+    _build("l2", np.eye(4, dtype=np.float32)[:3], {}, path, ids=[10, 20, 30])
+    h = O.PortHnsw(path)
+    ids, d, c, _ = h.knn(np.array([[1, 0, 0, 0]], np.float32), 2, 200)
+    assert ids[0, 0] == 10 and abs(d[0, 0]) < 1e-6 and c[0] == 2
+    assert abs(d[0, 1] - 2.0) < 1e-6            # hnsw + l2 reports the squared distance
+    h.close()
+    loaded = nb.Index.load(str(path))
+    assert loaded.dataQty() == 3 and np.array_equal(loaded.getDataPoint(1), np.eye(4, dtype=np.float32)[1])
+    loaded.deinit()
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+def test_reference_loads_and_searches_our_file(tmp_path):
+    """Interchange: a file written by nmslib_save_index here is loaded by the reference's
+    own nmslib_load_index and answers like the oracle does on the same graph."""
+    data = synth.gist_like(3000, 16, 43, clusters=8)
+    q = synth.gist_like(20, 16, 44, clusters=8)
+    path = tmp_path / "x.hnsw"
+    _build("l2", data, {"M": 8, "efConstruction": 60}, path, ids=np.arange(3000) + 7)
+    L = C.CDLL(str(ROOT / "oracle" / "_ref" / "libnmslib_ref.so"))
+    vp, sz = C.c_void_p, C.c_size_t
+    from nmslib_zig_b200.index import Allocator, Result, _ALLOC
+    L.nmslib_load_index.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(Allocator), C.c_int, C.POINTER(vp)]
+    L.nmslib_knn_query_fill.argtypes = [vp, vp, sz, sz, C.POINTER(Result), sz]
+    L.nmslib_index_destroy.argtypes = [vp]
+    L.nmslib_init()
+    h = vp()
+    assert L.nmslib_load_index(str(path).encode(), 0, 0, C.byref(_ALLOC), 1, C.byref(h)) == 0
+    port = O.PortHnsw(path)
+    pi, pd, pc, _ = port.knn(q, 5, 200)          # the reference's C ABI forces efSearch = 200
+    for i in range(len(q)):
+        ids = np.zeros(5, np.int32)
+        d = np.zeros(5, np.float32)
+        r = Result(ids.ctypes.data_as(C.POINTER(C.c_int32)), d.ctypes.data_as(C.POINTER(C.c_float)), 0, 5)
+        assert L.nmslib_knn_query_fill(h, q[i].ctypes.data, 16, 5, C.byref(r), 0) == 0
+        assert r.size == 5 and np.array_equal(ids, pi[i]) and np.allclose(d, pd[i], rtol=1e-5, atol=1e-6)
+    L.nmslib_index_destroy(h)
+    port.close()

@@ -66,15 +66,69 @@ def test_l2_hnsw_reports_squared_distances():
     idx.deinit()
 
 
-def test_hnsw_without_graph_fails_loudly():
-    idx = nb.Index("l2", None, "hnsw")
-    idx.addDenseBatch(np.eye(4, dtype=np.float32))
-    idx.buildIndex()
-    try:
-        r = idx.knnQuery(np.ones(4, np.float32), 2)   # once the device builder exists this returns results
-        assert len(r.ids) == 2
-    except nb.NmslibError as e:
-        assert e.name == "IndexBuildFailed"
+def test_lib_zig_dense_workflow_through_hnsw(tmp_path):
+    """The reference's own flagship test, call for call (lib.zig:1273-1313): hnsw over three unit
+    vectors with ids 10/20/30, k = 2 -> ids[0] == 10, distances[0] ~ 0, getDistance(0,1) ~ sqrt 2,
+    save -> reset -> load -> 3 points."""
+    idx = nb.Index.init("l2", nb.Params({"dim": 4}), "hnsw", "DenseVector", "Float")
+    data = np.eye(4, dtype=np.float32)[:3]
+    idx.addDenseBatch(data, [10, 20, 30])
+    idx.buildIndex(None, False)
+    assert idx.dataQty() == 3 and idx.getSpaceType() == "l2" and idx.getMethod() == "hnsw"
+    r = idx.knnQuery(np.array([1, 0, 0, 0], np.float32), 2)
+    assert len(r.ids) == 2 and r.ids[0] == 10 and abs(r.distances[0]) < 1e-4
+    assert abs(idx.getDistance(0, 1) - np.sqrt(2.0)) < 1e-4
+    assert np.array_equal(idx.getDataPoint(0), data[0])
+    idx.save(str(tmp_path / "test_index"), True)
+    idx.reset()
+    assert idx.dataQty() == 0
+    loaded = nb.Index.load(str(tmp_path / "test_index"), "DenseVector", "Float", True)
+    assert loaded.dataQty() == 3 and np.array_equal(loaded.getDataPoint(0), data[0])
+    r2 = loaded.knnQuery(np.array([0, 1, 0, 0], np.float32), 2)
+    assert r2.ids[0] == 20
+    loaded.deinit()
+    idx.deinit()
+
+
+def test_lib_zig_uint8_workflow_through_hnsw():
+    """lib.zig:1357-1380: l2sqr_sift + hnsw over uint8 vectors (the reference searches the pointer graph,
+    hnsw.cc:1174-1300; here the same beam runs on float-widened rows, distances stay exact integers)."""
+    from nmslib_zig_b200 import synth
+    from oracle import oracle as O
+    data = synth.sift_like_u8(5000, 7)
+    q = synth.sift_like_u8(64, 8)
+    idx = nb.Index("l2sqr_sift", None, "hnsw", "DenseUInt8Vector", "Int")
+    idx.addUInt8Batch(data)
+    idx.buildIndex(nb.Params({"M": 16, "efConstruction": 100}))
+    r = idx.knnQueryBatch(q, 10)
+    ei, ed, _ = O.seq_knn("l2sqr_sift", data, q, 10)
+    assert recall(r.ids, ei) >= 0.9
+    assert np.all(r.distances == np.round(r.distances))
+    for i in range(len(q)):                      # every reported distance is the exact integer distance of its id
+        for j in range(10):
+            assert r.distances[i, j] == O.pair_distance("l2sqr_sift", data[r.ids[i, j]], q[i])
+    two = idx.knnQuery(data[3], 2)
+    assert two.ids[0] == 3 and two.distances[0] == 0
+    idx.deinit()
+
+
+@pytest.mark.parametrize("space", ["l2", "cosinesimil", "negdotprod"])
+def test_self_built_graph_recall(space):
+    from nmslib_zig_b200 import synth
+    from oracle import oracle as O
+    data = synth.gist_like(20_000, 48, 41, clusters=16)
+    q = synth.gist_like(300, 48, 42, clusters=16)
+    idx = nb.Index(space, None, "hnsw")
+    idx.addDenseBatch(data)
+    idx.buildIndex(nb.Params({"M": 16, "efConstruction": 200}))
+    ei, _, _ = O.seq_knn(space, data, q, 10)
+    last = 0.0
+    for ef in (20, 100, 400):
+        idx.setQueryTimeParams(nb.Params({"efSearch": ef}))
+        rec = recall(idx.knnQueryBatch(q, 10).ids, ei)
+        assert rec >= last - 0.01
+        last = rec
+    assert last >= 0.95
     idx.deinit()
 
 

@@ -1,4 +1,5 @@
-"""Timing experiments on the tensor-core scan (config 2): environment switches -> scan time."""
+"""Timing experiments on the tensor-core scan: environment switches -> scan time.
+usage: tc_exp.py [dim] [n] [nq]   (SIFT-shaped l2sqr data, k = 10)"""
 import os
 import sys
 from pathlib import Path
@@ -9,14 +10,15 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import nmslib_zig_b200 as nb
 from nmslib_zig_b200 import synth
 
-cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
-data, q = synth.make(cfg, None if cfg == "c2" else 200_000, None if cfg == "c2" else 2_000)
-space, k = synth.CONFIGS[cfg][0], synth.CONFIGS[cfg][7]
-idx = nb.Index(space, None, "seq_search")
+dim = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+nq = int(sys.argv[3]) if len(sys.argv) > 3 else 10_000
+k = 10
+data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
+idx = nb.Index("l2sqr", None, "seq_search")
 idx.addDenseBatch(data)
 idx.buildIndex()
-settings = [{}, {"NB200_TC_L2AHEAD": "0"}, {"NB200_TC_L2AHEAD": "4"}, {"NB200_TC_DEBUG": "1"},
-            {"NB200_TC_DEBUG": "1", "NB200_TC_L2AHEAD": "0"}]
+settings = [{"NB200_TC_L2AHEAD": "0"}, {"NB200_TC_DEBUG": "1", "NB200_TC_L2AHEAD": "0"}]
 for s in settings:
     for kk in ("NB200_TC_DEBUG", "NB200_TC_L2AHEAD"):
         os.environ.pop(kk, None)
@@ -25,6 +27,7 @@ for s in settings:
     for _ in range(4):
         idx.knnQueryBatch(q, k)
         ms.append(idx.stats()["last_scan_ms"])
-    print(f"{cfg} {s}: scan_ms min={min(ms):.3f} all={[round(m, 3) for m in ms]} fallback={idx.stats()['fallback_queries']}",
+    tf = 2.0 * nq * n * dim / (min(ms) * 1e-3) / 1e12
+    print(f"dim={dim} n={n} nq={nq} {s}: scan_ms min={min(ms):.3f} -> {tf:.0f} TFLOP/s  fallback={idx.stats()['fallback_queries']}",
           flush=True)
 idx.deinit()
