@@ -442,21 +442,31 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* buf = nullptr;
     int cnt = 0;
     float thr = 0.f;
+    // KPL == 0 ("small k", k' = 16): the row's 16 best (rank, position) pairs live in registers as a
+    // sorted list, so the threshold is always the exact 16th best seen so far (fewest possible appends,
+    // no buffer, no compaction).  KPL > 0: append buffer in global memory + warp-cooperative compaction.
+    constexpr bool SMALLK = (KPL == 0);
+    constexpr int RK = 16;
+    float tk[RK];
+    uint32_t tp[RK];
 
     // one 32-column chunk; `vcols` = number of valid columns in it (< 32 only in the shard's last tile)
     auto process = [&](const uint32_t (&v)[32], uint32_t pos0, int vcols) {
-      // make room first: a chunk may append up to 32 keys to a row
-      unsigned need = __ballot_sync(FULL, cnt > p.cap - 32);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf, src);
-        const int c = __shfl_sync(FULL, cnt, src);
-        int kept;
-        const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, p.kprime, 16, lane, &kept);
-        if (lane == src) {
-          cnt = kept;
-          thr = f32_from_ordered(t);
+      if constexpr (!SMALLK) {
+        // make room first: a chunk may append up to 32 keys to a row
+        unsigned need = __ballot_sync(FULL, cnt > p.cap - 32);
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf, src);
+          const int c = __shfl_sync(FULL, cnt, src);
+          int kept;
+          const uint32_t t = compact_row<(KPL > 0 ? KPL : 1)>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, p.kprime,
+                                                              16, lane, &kept);
+          if (lane == src) {
+            cnt = kept;
+            thr = f32_from_ordered(t);
+          }
         }
       }
       float r[32];
@@ -480,8 +490,27 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 8 * q; j < 8 * q + 8; ++j) {
               if (r[j] < thr) {
-                buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
-                ++cnt;
+                if constexpr (SMALLK) {
+                  // branch-free sorted insertion: slot i takes its left neighbour if that one is worse than
+                  // the newcomer, the newcomer if it is the first slot worse than it, else stays
+                  const float x = r[j];
+                  const uint32_t xp = pos0 + j;
+#pragma unroll
+                  for (int i = RK - 1; i >= 1; --i) {
+                    const bool shift = tk[i - 1] > x;
+                    const bool here = tk[i] > x;
+                    tp[i] = shift ? tp[i - 1] : (here ? xp : tp[i]);
+                    tk[i] = shift ? tk[i - 1] : (here ? x : tk[i]);
+                  }
+                  if (tk[0] > x) {
+                    tk[0] = x;
+                    tp[0] = xp;
+                  }
+                  thr = tk[RK - 1];
+                } else {
+                  buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
+                  ++cnt;
+                }
               }
             }
           }
@@ -501,6 +530,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
       cnt = 0;
       thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+      if constexpr (SMALLK) {
+#pragma unroll
+        for (int i = 0; i < RK; ++i) {
+          tk[i] = __int_as_float(0x7F800000);
+          tp[i] = 0;
+        }
+      }
       for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
         const int b = ti & 1;
         mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
@@ -532,6 +568,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // publish this piece's per-row candidate count and final threshold
       const size_t slot = unit * TC_QB + h * TC_BM + row;
+      if constexpr (SMALLK) {
+        cnt = 0;
+#pragma unroll
+        for (int i = 0; i < RK; ++i) {
+          if (tk[i] < __int_as_float(0x7F800000)) {
+            buf[i] = ((uint64_t)__float_as_uint(tk[i]) << 32) | (uint64_t)tp[i];
+            cnt = i + 1;
+          }
+        }
+      }
       p.cand_cnt[slot] = row_valid ? cnt : 0;
       p.cand_thr[slot] = thr;
       w += t_end - t_begin;
@@ -833,7 +879,7 @@ void tc_plan(int nq, int n, int k, int sm_count, int* n_cta, int* work_per_cta, 
   const long n_tiles = (n + TC_BN - 1) / TC_BN;
   const long total = q_blocks * n_tiles;
   // the re-rank sorts s_max * cap keys per query in shared memory: bound the pieces per query block
-  const long max_pieces = std::max<long>(2, 16384 / cap);
+  const long max_pieces = std::min<long>(64, std::max<long>(2, 16384 / cap));
   if (q_blocks * 4 >= sm_count || q_blocks * n_tiles <= sm_count) {
     long best = 1;
     double best_eff = 0;
@@ -883,6 +929,11 @@ cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, flo
 
 // cand capacity per (unit,row) and survivors per compaction for a given k
 void tc_candidate_shape(int k, int* kprime, int* cap) {
+  if (k <= 12) {  // register-resident exact top-16 per row (tc_scan_kernel<0>)
+    *kprime = 16;
+    *cap = 16;
+    return;
+  }
   int kp = k + 22 < 2 * k ? k + 22 + (k / 4) : 2 * k;  // headroom for the certificate
   if (kp < k + 22) kp = k + 22;
   kp = (kp + 31) / 32 * 32;
@@ -945,6 +996,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   if (e != cudaSuccess) return e;                                                                         \
   tc_scan_kernel<KPL><<<n_cta, TC_THREADS, smem, stream>>>(tmA, tmB, tmN, tmO, p);
   switch (p.cap) {
+    case 16: NB_TC(0); break;
     case 128: NB_TC(4); break;
     case 256: NB_TC(8); break;
     default: NB_TC(16); break;
