@@ -487,14 +487,23 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (g[q] < thr) {
+            if constexpr (SMALLK) {
+              // which of the 8 values pass; then ONE copy of the insertion code per group, run per survivor
+              // (a predicated 32-fold unroll of the insertion would execute ~100 instructions per value)
+              unsigned mk = 0;
 #pragma unroll
-            for (int j = 8 * q; j < 8 * q + 8; ++j) {
-              if (r[j] < thr) {
-                if constexpr (SMALLK) {
+              for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] < thr ? 1u : 0u) << jj;
+#pragma unroll 1
+              while (mk) {
+                const int jj = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const float lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
+                const float hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
+                const float x = (jj & 4) ? hi4 : lo4;
+                if (x < thr) {
+                  const uint32_t xp = pos0 + 8 * q + jj;
                   // branch-free sorted insertion: slot i takes its left neighbour if that one is worse than
                   // the newcomer, the newcomer if it is the first slot worse than it, else stays
-                  const float x = r[j];
-                  const uint32_t xp = pos0 + j;
 #pragma unroll
                   for (int i = RK - 1; i >= 1; --i) {
                     const bool shift = tk[i - 1] > x;
@@ -507,7 +516,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tp[0] = xp;
                   }
                   thr = tk[RK - 1];
-                } else {
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 8 * q; j < 8 * q + 8; ++j) {
+                if (r[j] < thr) {
                   buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
                   ++cnt;
                 }
