@@ -567,21 +567,36 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive(&tempty_bar[b]);
           continue;
         }
-        // Drain first: pull the row's whole 128-column slice into registers and hand the TMEM buffer back
-        // to the MMA at once.  A warp that then runs into a slow path (append, compaction) no longer holds
-        // up the other seven warps and the tensor pipe through the 2-deep TMEM ring.
-        uint32_t v2[32], v3[32];
-        tmem_ld32(tcol, v0);
-        tmem_ld32(tcol + 32u, v1);
-        tmem_ld32(tcol + 64u, v2);
-        tmem_ld32(tcol + 96u, v3);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[b]);
-        process(v0, pos_tile, vtile);
-        process(v1, pos_tile + 32, vtile - 32);
-        process(v2, pos_tile + 64, vtile - 64);
-        process(v3, pos_tile + 96, vtile - 96);
+        if constexpr (SMALLK) {
+          // Drain first: pull the row's whole 128-column slice into registers and hand the TMEM buffer
+          // back to the MMA at once, so that a warp inside a long insertion does not hold up the other
+          // seven warps and the tensor pipe through the 2-deep TMEM ring.
+          uint32_t v2[32], v3[32];
+          tmem_ld32(tcol, v0);
+          tmem_ld32(tcol + 32u, v1);
+          tmem_ld32(tcol + 64u, v2);
+          tmem_ld32(tcol + 96u, v3);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[b]);
+          process(v0, pos_tile, vtile);
+          process(v1, pos_tile + 32, vtile - 32);
+          process(v2, pos_tile + 64, vtile - 64);
+          process(v3, pos_tile + 96, vtile - 96);
+        } else {
+          tmem_ld32(tcol, v0);
+#pragma unroll 1
+          for (int cp = 0; cp < TC_BN / 64; ++cp) {  // two chunks per iteration, next load in flight while computing
+            tmem_ld_wait();
+            tmem_ld32(tcol + (uint32_t)(cp * 64 + 32), v1);
+            process(v0, pos_tile + cp * 64, vtile - cp * 64);
+            tmem_ld_wait();
+            if (cp + 1 < TC_BN / 64) tmem_ld32(tcol + (uint32_t)(cp * 64 + 64), v0);
+            process(v1, pos_tile + cp * 64 + 32, vtile - cp * 64 - 32);
+          }
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[b]);
+        }
       }
       // publish this piece's per-row candidate count and final threshold
       const size_t slot = unit * TC_QB + h * TC_BM + row;
