@@ -74,6 +74,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// one lane of a converged warp (the compiler keeps everything outside the elected region uniform)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -122,6 +134,35 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with BF16 inputs (kind::f16): K = 16 per instruction, twice the MACs per operand byte
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A operand from tensor memory (lanes = rows, one 32-bit column per tf32 element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma(bool bf16, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if (bf16) umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  else umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -151,6 +192,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // Instruction descriptor for kind::tf32: D = F32 (1 @4), A = B = TF32 (2 @7, 2 @10), both K-major,
 // N >> 3 @17, M >> 4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {  // kind::f16: A = B = BF16 (1), D = F32
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
@@ -238,6 +282,8 @@ struct TcParams {
   int a_resident;          // 1: both query tiles stay in shared memory while a piece is scanned (D <= 128)
   int use_nb;              // 1: an extra K=8 step adds |x|^2 (three TF32 pieces x 1.0) inside the MMA (l2)
   int aligned;             // 1: CTA = (segment, query block) with common tile boundaries; 0: equal linear ranges
+  int bf16;                // 1: operands are BF16 (data proven BF16-exact), kind::f16; 0: TF32
+  int kb_elems;            // elements per 128-byte k-block: 32 (fp32/TF32) or 64 (BF16)
   int l2_ahead;            // tiles of L2 prefetch distance (0 = off)
   int debug;               // NB200_TC_DEBUG bit 0: epilogue drains TMEM without selecting (timing experiments only)
 };
@@ -269,7 +315,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* ones_bar = aempty_bar + 1;         // [1]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ones_bar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index is made provably warp-uniform (shfl), so that the single-thread TMA / MMA issue loops keep
+  // their descriptors in uniform registers instead of paying an ELECT + R2UR round trip per instruction
+  const int tid = threadIdx.x, warp = __shfl_sync(FULL, tid >> 5, 0), lane = tid & 31;
   const int cta = blockIdx.x;
   // aligned mode: CTA = (segment, query block), every query block is cut at the SAME tile boundaries and
   // CTAs of one segment are neighbours in the grid, so co-resident CTAs sweep the same database tiles
@@ -313,12 +361,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0 && w_begin < w_end) {
-      if (p.use_nb) {
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    if (w_begin < w_end) {
+      if (p.use_nb && elect_one()) {
         mbar_expect_tx(ones_bar, CHUNK_BYTES);
         tma_load_2d(&tmO, ones_bar, smem_ones, 0, 0);
       }
+      __syncwarp();
       int s = 0;
       uint32_t ph = 0;  // ring position and its phase bit (no division in the hot loop)
       int piece = 0;
@@ -329,31 +378,39 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q0 = qb * TC_QB;
         if (p.a_resident) {
           if (piece > 0) mbar_wait(aempty_bar, (piece - 1) & 1);
-          mbar_expect_tx(afull_bar, (uint32_t)a_bytes);
-          for (int h = 0; h < 2; ++h)
-            for (int kb = 0; kb < p.n_kb; ++kb)
-              tma_load_2d(&tmA, afull_bar, smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES, kb * TC_KB,
-                          q0 + h * TC_BM);
+          if (elect_one()) {
+            mbar_expect_tx(afull_bar, (uint32_t)a_bytes);
+            for (int h = 0; h < 2; ++h)
+              for (int kb = 0; kb < p.n_kb; ++kb)
+                tma_load_2d(&tmA, afull_bar, smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES, kb * p.kb_elems,
+                            q0 + h * TC_BM);
+          }
+          __syncwarp();
         }
         for (int t = t_begin; t < t_end; ++t) {
-          if (p.l2_ahead > 0 && t + p.l2_ahead < t_end) {
-            for (int kb = 0; kb < p.n_kb; ++kb) tma_prefetch_l2_2d(&tmB, kb * TC_KB, (t + p.l2_ahead) * TC_BN);
+          if (p.l2_ahead > 0 && t + p.l2_ahead < t_end && elect_one()) {
+            for (int kb = 0; kb < p.n_kb; ++kb) tma_prefetch_l2_2d(&tmB, kb * p.kb_elems, (t + p.l2_ahead) * TC_BN);
             if (p.use_nb) tma_prefetch_l2_2d(&tmN, 0, (t + p.l2_ahead) * TC_BN);
           }
           for (int kb = 0; kb < n_kb_all; ++kb) {
             mbar_wait(&empty_bar[s], ph ^ 1);
             unsigned char* st = smem_st + (size_t)s * stage_bytes;
-            if (kb < p.n_kb) {
-              mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-              tma_load_2d(&tmB, &full_bar[s], st, kb * TC_KB, t * TC_BN);
-              if (!p.a_resident) {
-                tma_load_2d(&tmA, &full_bar[s], st + CHUNK_BYTES, kb * TC_KB, q0);
-                tma_load_2d(&tmA, &full_bar[s], st + 2 * CHUNK_BYTES, kb * TC_KB, q0 + TC_BM);
+            if (elect_one()) {
+              if (p.debug & 2) {  // timing experiment: no database traffic, the MMAs read stale shared memory
+                mbar_arrive(&full_bar[s]);
+              } else if (kb < p.n_kb) {
+                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                tma_load_2d(&tmB, &full_bar[s], st, kb * p.kb_elems, t * TC_BN);
+                if (!p.a_resident) {
+                  tma_load_2d(&tmA, &full_bar[s], st + CHUNK_BYTES, kb * p.kb_elems, q0);
+                  tma_load_2d(&tmA, &full_bar[s], st + 2 * CHUNK_BYTES, kb * p.kb_elems, q0 + TC_BM);
+                }
+              } else {  // the |x|^2 block of this tile
+                mbar_expect_tx(&full_bar[s], CHUNK_BYTES);
+                tma_load_2d(&tmN, &full_bar[s], st, 0, t * TC_BN);
               }
-            } else {  // the |x|^2 block of this tile
-              mbar_expect_tx(&full_bar[s], CHUNK_BYTES);
-              tma_load_2d(&tmN, &full_bar[s], st, 0, t * TC_BN);
             }
+            __syncwarp();
             if (++s == p.n_stage) {
               s = 0;
               ph ^= 1;
@@ -364,11 +421,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && w_begin < w_end) {
-      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
-      // This single thread must keep the tensor pipe fed (8 MMAs of 64 cycles per k-block), so the
-      // loop carries ring position / phase / descriptors incrementally: no division, no rebuild.
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+    if (w_begin < w_end) {
+      const bool bf = p.bf16 != 0;
+      const uint32_t idesc = bf ? make_idesc_bf16(TC_BM, TC_BN) : make_idesc_tf32(TC_BM, TC_BN);
+      // The issuing lane must keep the tensor pipe fed (8 MMAs of 64 cycles per k-block): everything outside
+      // the elected region is warp-uniform, so descriptors live in uniform registers (no ELECT/R2UR loop per
+      // MMA), and the loop carries ring position / phase incrementally: no division, no rebuild.
       const uint32_t st_base = smem_u32(smem_st);
       const uint32_t a_base = smem_u32(smem_a);
       const uint64_t d_ones = make_smem_desc(smem_u32(smem_ones));
@@ -396,16 +455,25 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t da1 =
                 make_smem_desc(a_res ? a_base + (uint32_t)(p.n_kb + kb) * CHUNK_BYTES : sb + 2 * CHUNK_BYTES);
             const uint32_t acc = kb != 0;
-            // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (address >> 4) field
-            umma_tf32(tmem_d0, da0, db, idesc, acc);
-            umma_tf32(tmem_d0, da0 + 2, db + 2, idesc, 1);
-            umma_tf32(tmem_d0, da0 + 4, db + 4, idesc, 1);
-            umma_tf32(tmem_d0, da0 + 6, db + 6, idesc, 1);
-            umma_tf32(tmem_d0 + TC_BN, da1, db, idesc, acc);
-            umma_tf32(tmem_d0 + TC_BN, da1 + 2, db + 2, idesc, 1);
-            umma_tf32(tmem_d0 + TC_BN, da1 + 4, db + 4, idesc, 1);
-            umma_tf32(tmem_d0 + TC_BN, da1 + 6, db + 6, idesc, 1);
-            tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+            if (elect_one()) {
+              if (p.debug & 8) {  // timing experiment: A operand read from tensor memory (garbage values)
+                for (int j = 0; j < 4; ++j) umma_tf32_ts(tmem_d0, tmem_base + 8 * j, db + 2 * j, idesc, acc | j);
+                for (int j = 0; j < 4; ++j)
+                  umma_tf32_ts(tmem_d0 + TC_BN, tmem_base + 32 + 8 * j, db + 2 * j, idesc, acc | j);
+              } else if (!(p.debug & 4)) {  // (bit 2 set: timing experiment without the MMAs, TMA traffic only)
+                // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (address >> 4) field
+                umma(bf, tmem_d0, da0, db, idesc, acc);
+                umma(bf, tmem_d0, da0 + 2, db + 2, idesc, 1);
+                umma(bf, tmem_d0, da0 + 4, db + 4, idesc, 1);
+                umma(bf, tmem_d0, da0 + 6, db + 6, idesc, 1);
+                umma(bf, tmem_d0 + TC_BN, da1, db, idesc, acc);
+                umma(bf, tmem_d0 + TC_BN, da1 + 2, db + 2, idesc, 1);
+                umma(bf, tmem_d0 + TC_BN, da1 + 4, db + 4, idesc, 1);
+                umma(bf, tmem_d0 + TC_BN, da1 + 6, db + 6, idesc, 1);
+              }
+              tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+            }
+            __syncwarp();
             if (++s == p.n_stage) {
               s = 0;
               ph ^= 1;
@@ -415,17 +483,24 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             const uint64_t db = make_smem_desc(st_base + (uint32_t)s * (uint32_t)stage_bytes);
-            umma_tf32(tmem_d0, d_ones, db, idesc, 1);
-            umma_tf32(tmem_d0 + TC_BN, d_ones, db, idesc, 1);
-            tc_commit(&empty_bar[s]);
+            if (elect_one()) {
+              umma(bf, tmem_d0, d_ones, db, idesc, 1);
+              umma(bf, tmem_d0 + TC_BN, d_ones, db, idesc, 1);
+              tc_commit(&empty_bar[s]);
+            }
+            __syncwarp();
             if (++s == p.n_stage) {
               s = 0;
               ph ^= 1;
             }
           }
-          tc_commit(&tfull_bar[b]);    // accumulators of this tile are complete
+          if (elect_one()) tc_commit(&tfull_bar[b]);  // accumulators of this tile are complete
+          __syncwarp();
         }
-        if (a_res) tc_commit(aempty_bar);  // the resident operand tiles may be overwritten
+        if (a_res) {
+          if (elect_one()) tc_commit(aempty_bar);  // the resident operand tiles may be overwritten
+          __syncwarp();
+        }
         w += t_end - t_begin;
       }
     }
@@ -562,6 +637,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.debug & 1) {  // timing experiment: touch the accumulators, select nothing
           tmem_ld32(tcol, v0);
           tmem_ld_wait();
+          if (p.debug & 16) {  // ... all of them
+            tmem_ld32(tcol + 32u, v1);
+            tmem_ld32(tcol + 64u, v0);
+            tmem_ld_wait();
+            tmem_ld32(tcol + 96u, v1);
+            tmem_ld_wait();
+            if (__uint_as_float(v1[3]) == 1.2345e-30f) thr = 0.f;
+          }
           if (__uint_as_float(v0[0]) == 1.2345e-30f) thr = 0.f;
           tc_fence_before();
           mbar_arrive(&tempty_bar[b]);
@@ -846,6 +929,62 @@ __global__ void tc_prep_db_kernel(const float* __restrict__ db, int n, int n_pad
   }
 }
 
+// ---- BF16 operand copies (only made when every element is BF16-exact: low 16 bits zero) ----
+__device__ __forceinline__ uint16_t bf16_bits(float v) { return (uint16_t)(__float_as_uint(v) >> 16); }
+
+// database rows -> [n_pad][row_bf] bf16 (zero padded), |x|^2 -> three bf16 pieces in [n_pad][64]; flag if inexact
+__global__ void tc_prep_db_bf16_kernel(const float* __restrict__ db, int n, int n_pad, int row_words, int row_bf,
+                                       int with_norm, uint16_t* __restrict__ out, uint16_t* __restrict__ nblock,
+                                       int* __restrict__ inexact_flag) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_pad) return;
+  uint16_t* o = out + (size_t)warp * row_bf;
+  float s = 0.f;
+  unsigned bad = 0;
+  for (int c = lane; c < row_bf; c += 32) {
+    const float v = (warp < n && c < row_words) ? db[(size_t)warp * row_words + c] : 0.f;
+    bad |= __float_as_uint(v) & 0xFFFFu;
+    s = fmaf(v, v, s);
+    o[c] = bf16_bits(v);
+  }
+  s = warp_sum_f(s);
+  bad = __reduce_or_sync(FULL, bad);
+  if (nblock) {
+    float piece = 0.f;
+    if (with_norm && warp < n) {  // 8 + 8 + 8 significant bits: hi + mid + lo == s exactly
+      const float hi = __uint_as_float(__float_as_uint(s) & 0xFFFF0000u);
+      const float r1 = s - hi;
+      const float mid = __uint_as_float(__float_as_uint(r1) & 0xFFFF0000u);
+      const float lo = r1 - mid;
+      if (__float_as_uint(lo) & 0xFFFFu) bad = 1;  // cannot happen for 24-bit norms; keeps the flag honest
+      piece = lane == 0 ? hi : lane == 1 ? mid : lane == 2 ? lo : 0.f;
+    }
+    nblock[(size_t)warp * 64 + lane] = bf16_bits(piece);
+    nblock[(size_t)warp * 64 + 32 + lane] = 0;
+  }
+  if (lane == 0 && bad) atomicOr(inexact_flag, 1);
+}
+
+// A' = scale * q as bf16 into [q_pad][row_bf]; flags a batch that is not BF16-exact
+__global__ void tc_prep_queries_bf16_kernel(const float* __restrict__ q, int q_pad, int row_words, int row_bf,
+                                            float scale, uint16_t* __restrict__ out, int* __restrict__ inexact_flag) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= q_pad) return;
+  unsigned bad = 0;
+  for (int c = lane; c < row_bf; c += 32) {
+    const float v = c < row_words ? q[(size_t)warp * row_words + c] : 0.f;
+    bad |= __float_as_uint(v) & 0xFFFFu;
+    out[(size_t)warp * row_bf + c] = bf16_bits(v * scale);
+  }
+  bad = __reduce_or_sync(FULL, bad);
+  if (lane == 0 && bad) atomicOr(inexact_flag, 1);
+}
+
+__global__ void tc_fill_ones_bf16_kernel(uint16_t* __restrict__ ones) {  // [128][64]: 1.0 in columns 0..2
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < TC_BM * 64) ones[i] = (i % 64) < 3 ? (uint16_t)0x3F80 : (uint16_t)0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -863,14 +1002,15 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // rows x row_words fp32, row-major; box = 128 rows x 32 floats, 128B swizzle
-bool make_tmap(CUtensorMap* map, const void* base, size_t rows, int row_words) {
+bool make_tmap(CUtensorMap* map, const void* base, size_t rows, int row_elems, bool bf16 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)row_words, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)row_words * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BM};
+  const int esz = bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_elems * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)TC_BM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -897,6 +1037,25 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
   tc_prep_db_kernel<<<blocks, threads, 0, stream>>>(db, n, n_pad, row_words, mode, bias, norm2, db_unit, nblock,
                                                     max_norm_bits, inexact_flag);
   if (ones) tc_fill_ones_kernel<<<(TC_BM * TC_KB + 255) / 256, 256, 0, stream>>>(ones);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_prep_db_bf16(const float* db, int n, int n_pad, int row_words, int row_bf, int with_norm,
+                                   void* out, void* nblock, void* ones, int* inexact_flag, cudaStream_t stream) {
+  const int threads = 256;
+  const int blocks = (int)(((size_t)n_pad * 32 + threads - 1) / threads);
+  tc_prep_db_bf16_kernel<<<blocks, threads, 0, stream>>>(db, n, n_pad, row_words, row_bf, with_norm,
+                                                         static_cast<uint16_t*>(out), static_cast<uint16_t*>(nblock),
+                                                         inexact_flag);
+  if (ones) tc_fill_ones_bf16_kernel<<<(TC_BM * 64 + 255) / 256, 256, 0, stream>>>(static_cast<uint16_t*>(ones));
+  return cudaGetLastError();
+}
+cudaError_t launch_tc_prep_queries_bf16(const float* q, int q_pad, int row_words, int row_bf, float scale, void* out,
+                                        int* inexact_flag, cudaStream_t stream) {
+  const int threads = 256;
+  const int blocks = (int)(((size_t)q_pad * 32 + threads - 1) / threads);
+  tc_prep_queries_bf16_kernel<<<blocks, threads, 0, stream>>>(q, q_pad, row_words, row_bf, scale,
+                                                              static_cast<uint16_t*>(out), inexact_flag);
   return cudaGetLastError();
 }
 
@@ -983,15 +1142,19 @@ int tc_max_k() { return 256; }
 
 cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
                            const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_cta,
-                           int work_per_cta, int s_max, int aligned, uint64_t* cand, int* cand_cnt,
+                           int work_per_cta, int s_max, int aligned, int bf16, uint64_t* cand, int* cand_cnt,
                            float* cand_thr, cudaStream_t stream) {
   if (n <= 0 || nq <= 0) return cudaSuccess;
-  if (row_words % TC_KB) return cudaErrorInvalidValue;
+  // row_words counts ELEMENTS per operand row here: fp32 words, or bf16 halves when bf16 != 0
+  const int kb_elems = bf16 ? 64 : TC_KB;
+  if (row_words % kb_elems) return cudaErrorInvalidValue;
   CUtensorMap tmA, tmB, tmN, tmO;
-  if (!make_tmap(&tmA, qa, q_pad, row_words) || !make_tmap(&tmB, dbB, n_pad, row_words)) return cudaErrorUnknown;
+  if (!make_tmap(&tmA, qa, q_pad, row_words, bf16) || !make_tmap(&tmB, dbB, n_pad, row_words, bf16))
+    return cudaErrorUnknown;
   const bool use_nb = nblock != nullptr;
   if (use_nb) {
-    if (!make_tmap(&tmN, nblock, n_pad, TC_KB) || !make_tmap(&tmO, ones, TC_BM, TC_KB)) return cudaErrorUnknown;
+    if (!make_tmap(&tmN, nblock, n_pad, kb_elems, bf16) || !make_tmap(&tmO, ones, TC_BM, kb_elems, bf16))
+      return cudaErrorUnknown;
   } else {
     tmN = tmB;
     tmO = tmA;
@@ -999,7 +1162,9 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   TcParams p;
   p.n = n;
   p.nq = nq;
-  p.n_kb = row_words / TC_KB;
+  p.n_kb = row_words / kb_elems;
+  p.bf16 = bf16 ? 1 : 0;
+  p.kb_elems = kb_elems;
   p.n_tiles = (n + TC_BN - 1) / TC_BN;
   p.q_blocks = (nq + TC_QB - 1) / TC_QB;
   p.work_per_cta = work_per_cta;
@@ -1016,7 +1181,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
     const char* dbg = getenv("NB200_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
     const char* la = getenv("NB200_TC_L2AHEAD");
-    p.l2_ahead = la ? atoi(la) : 2;
+    p.l2_ahead = la ? atoi(la) : 0;  // measured: prefetching ahead into L2 does not help (profiles/README.md)
   }
   p.a_resident = (2 * p.n_kb * CHUNK_BYTES <= 128 * 1024) ? 1 : 0;
   const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;

@@ -18,7 +18,11 @@ data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
 idx = nb.Index("l2sqr", None, "seq_search")
 idx.addDenseBatch(data)
 idx.buildIndex()
-settings = [{"NB200_TC_L2AHEAD": "0"}, {"NB200_TC_DEBUG": "1", "NB200_TC_L2AHEAD": "0"}]
+settings = [{}, {"NB200_TC_DEBUG": "1"}, {"NB200_TC_DEBUG": "3"}, {"NB200_TC_DEBUG": "5"}, {"NB200_TC_DEBUG": "7"},
+            {"NB200_TC_DEBUG": "1", "NB200_TC_L2AHEAD": "4"}]
+if os.environ.get("TC_EXP_SETTINGS"):
+    import json
+    settings = json.loads(os.environ["TC_EXP_SETTINGS"])
 for s in settings:
     for kk in ("NB200_TC_DEBUG", "NB200_TC_L2AHEAD"):
         os.environ.pop(kk, None)
