@@ -274,6 +274,14 @@ typedef struct {
 } nmslib_b200_stats_t;
 nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_stats_t* out);
 
+/* Diagnostic (needs no device): the work decomposition the tensor-core scan would use for a batch of
+ * `query_count` queries against `n` rows of at most 128 floats on a GPU with `sm_count` SMs.
+ * Writes up to `capacity` pieces as 5 ints {cta, query block (256 queries), first tile, end tile, slot}
+ * (tiles are 64 rows) and returns the number of pieces; *n_cta / *s_max receive the grid size and the
+ * number of candidate lists per query block. */
+size_t nmslib_b200_scan_plan(size_t query_count, size_t n, size_t k, int sm_count, int32_t* pieces,
+                             size_t capacity, int* n_cta, int* s_max);
+
 /* Library build / arch string, e.g. "nmslib_b200 0.1 sm_100a". Static storage. */
 const char* nmslib_b200_version(void);
 

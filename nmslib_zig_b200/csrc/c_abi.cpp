@@ -742,6 +742,27 @@ nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_st
   return NMSLIB_SUCCESS;
 }
 
+size_t nmslib_b200_scan_plan(size_t query_count, size_t n, size_t k, int sm_count, int32_t* pieces, size_t capacity,
+                             int* n_cta, int* s_max) {
+  std::vector<int> table;
+  int nc = 0, sm = 0;
+  nb200::tc_ts_plan((int)query_count, (int)n, (int)k, sm_count, &table, &nc, &sm);
+  if (n_cta) *n_cta = nc;
+  if (s_max) *s_max = sm;
+  size_t out = 0;
+  for (int c = 0; c < nc; ++c)
+    for (int i = 0; i < 8; ++i) {
+      const int* e = table.data() + ((size_t)c * 8 + i) * 4;
+      if (e[0] < 0) break;
+      if (pieces && out < capacity) {
+        pieces[out * 5] = c;
+        for (int j = 0; j < 4; ++j) pieces[out * 5 + 1 + j] = e[j];
+      }
+      ++out;
+    }
+  return out;
+}
+
 const char* nmslib_b200_version(void) { return "nmslib_b200 0.1 sm_100a"; }
 
 }  // extern "C"

@@ -87,7 +87,7 @@ Engine::~Engine() {
   for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
                     &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
                     &d_out_counts_, &d_bias_, &d_db_unit_, &d_flags_, &d_qa_, &d_cand_, &d_cand_cnt_, &d_cand_thr_,
-                    &d_tc_keys_, &d_cert_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_})
+                    &d_tc_keys_, &d_cert_, &d_plan_, &d_gthr_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_})
     b->release();
   for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_}) b->release();
   for (auto& e : ev_)
@@ -611,33 +611,67 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   const size_t n_pad = round_up(n_dev_, bn);
   const int q_blocks = (int)(q_pad / qb);
   // equal linear ranges of the (query block x tile) grid, one CTA per SM (scan_tc.cu tc_plan)
-  int n_cta, work_per_cta, s_max, aligned;
-  tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &n_cta, &work_per_cta, &s_max, &aligned);
+  const bool ts = tc_ts_supported(row_words_);  // rows <= 128 floats: queries live in tensor memory
+  int n_cta, work_per_cta = 0, s_max, aligned = 0;
+  if (ts) {
+    if (plan_key_[0] != nq || plan_key_[1] != n_dev_ || plan_key_[2] != k) {
+      tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &h_plan_, &plan_n_cta_, &plan_s_max_);
+      if (!(s = check_cuda(d_plan_.ensure(h_plan_.size() * 4), "cudaMalloc(plan)")).ok()) return s;
+      s = check_cuda(cudaMemcpyAsync(d_plan_.p, h_plan_.data(), h_plan_.size() * 4, cudaMemcpyHostToDevice, stream),
+                     "H2D(plan)");
+      if (!s.ok()) return s;
+      plan_key_[0] = nq;
+      plan_key_[1] = n_dev_;
+      plan_key_[2] = k;
+    }
+    n_cta = plan_n_cta_;
+    s_max = plan_s_max_;
+  } else {
+    tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_, bn, &n_cta, &work_per_cta, &s_max, &aligned);
+  }
   int kprime, cap;
   tc_candidate_shape((int)k, &kprime, &cap);
   const size_t units = (size_t)q_blocks * s_max;
-  if (!(s = check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)")).ok()) return s;
   if (!(s = check_cuda(d_cand_.ensure(units * qb * (size_t)cap * 8), "cudaMalloc(cand)")).ok()) return s;
   if (!(s = check_cuda(d_cand_cnt_.ensure(units * qb * 4), "cudaMalloc(cand_cnt)")).ok()) return s;
   if (!(s = check_cuda(d_cand_thr_.ensure(units * qb * 4), "cudaMalloc(cand_thr)")).ok()) return s;
-  if (!(s = check_cuda(cudaMemsetAsync(d_cand_cnt_.p, 0, units * qb * 4, stream), "memset(cand_cnt)")).ok()) return s;
+  if (!(s = check_cuda(cudaMemsetAsync(d_cand_cnt_.p, 0xFF, units * qb * 4, stream), "memset(cand_cnt)")).ok()) return s;
   if (!(s = check_cuda(d_cert_.ensure(nq * 4), "cudaMalloc(cert)")).ok()) return s;
   if (!(s = check_cuda(h_cert_.ensure(nq * 4), "cudaMallocHost(cert)")).ok()) return s;
   if (!(s = check_cuda(cudaMemsetAsync(d_flags_.as<int>() + 1, 0, 4, stream), "memset(qflag)")).ok()) return s;
   const float scale = mode == SCAN_L2 ? -2.f : -1.f;
-  s = check_cuda(launch_tc_prep_queries(static_cast<const float*>(dq), d_qa_.as<float>(), q_pad * (size_t)row_words_,
-                                        scale, d_flags_.as<int>() + 1, stream),
-                 "tc_prep_queries");
-  if (!s.ok()) return s;
   const float* dbB = mode == SCAN_COSINE ? d_db_unit_.as<float>() : d_db_.as<float>();
-  scan_begin(stream);
-  s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad,
-                                mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(), (int)n_dev_,
-                                (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
-                                /*bf16=*/0, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(), stream),
-                 "tc_scan");
-  scan_end(stream);
-  if (!s.ok()) return s;
+  if (ts) {
+    scan_begin(stream);
+    if (!(s = check_cuda(d_gthr_.ensure(q_pad * 4), "cudaMalloc(gthr)")).ok()) return s;
+    if (!(s = check_cuda(cudaMemsetAsync(d_gthr_.p, 0xFF, q_pad * 4, stream), "memset(gthr)")).ok()) return s;
+    s = check_cuda(launch_tc_scan_ts(static_cast<const float*>(dq), dbB, n_pad,
+                                     mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(),
+                                     (int)n_dev_, (int)nq, row_words_, (int)k, (int)k + tc_margin_, scale, pos_base_,
+                                     n_cta, s_max, d_plan_.as<int>(), d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                                     d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), d_flags_.as<int>() + 1,
+                                     stream),
+                   "tc_scan_ts");
+    scan_end(stream);
+    if (!s.ok()) return s;
+    stats_.kernel_launches += 2;
+  } else {
+    if (!(s = check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)")).ok()) return s;
+    s = check_cuda(launch_tc_prep_queries(static_cast<const float*>(dq), d_qa_.as<float>(), q_pad * (size_t)row_words_,
+                                          scale, d_flags_.as<int>() + 1, stream),
+                   "tc_prep_queries");
+    if (!s.ok()) return s;
+    scan_begin(stream);
+    s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad,
+                                  mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(), (int)n_dev_,
+                                  (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
+                                  /*bf16=*/0, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(),
+                                  stream),
+                   "tc_scan");
+    scan_end(stream);
+    if (!s.ok()) return s;
+    stats_.kernel_launches += 3;
+  }
   s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
                                   mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)nq, row_words_, (int)k,
                                   s_max, mode, pos_base_, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
@@ -645,7 +679,6 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
                                   stream),
                  "tc_rerank");
   if (!s.ok()) return s;
-  stats_.kernel_launches += 3;
   // certificates back to the host; re-run the (normally empty) set of uncertified queries exactly
   s = check_cuda(cudaMemcpyAsync(h_cert_.p, d_cert_.p, nq * 4, cudaMemcpyDeviceToHost, stream), "D2H(cert)");
   if (!s.ok()) return s;
@@ -657,6 +690,9 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     if (!cert[i]) fb.push_back((int)i);
   if (fb.empty()) return Status::OK();
   stats_.fallback_queries += fb.size();
+  // the thresholds sat too close to the k-th answer for this data's pass-1 error bound: keep more survivors per
+  // compaction from the next batch on (costs candidates, buys certificate margin)
+  if (fb.size() * 64 > nq && tc_margin_ < 128) tc_margin_ *= 2;
   const size_t nfb = fb.size();
   const size_t fb_pad = round_up(nfb, (size_t)scan_exact_block_queries());
   if (!(s = check_cuda(d_fb_idx_.ensure(nfb * 4), "cudaMalloc(fb idx)")).ok()) return s;

@@ -1,5 +1,6 @@
 // kernels.h -- host-callable launchers of the nmslib_b200 CUDA kernels.
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,7 +53,20 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
                               float* db_unit, float* nblock, float* ones, unsigned* max_norm_bits,
                               int* inexact_flag, cudaStream_t stream);
 // balanced (query block x tile) decomposition: CTAs, work items per CTA, candidate pieces per query block
-void tc_plan(int nq, int n, int k, int sm_count, int* n_cta, int* work_per_cta, int* s_max, int* aligned);
+// bn = database rows per tile of the kernel that will run (tc_block_points() or tc_ts_block_points())
+void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned);
+// rows of at most 128 floats: the prepared queries live in tensor memory (tc_scan_ts_kernel); q = the ORIGINAL
+// queries [q_pad][row_words], scaled on the fly; sets *inexact_flag when a valid query row is not TF32-exact
+bool tc_ts_supported(int row_words);
+int tc_ts_block_points();
+// table: n_cta * 8 pieces of {query block, first tile, end tile, candidate slot} (query block -1 ends a CTA's list)
+void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int* n_cta, int* s_max);
+// kprime: survivors of a compaction (k + margin; the certificate needs the margin); gthr: [q_pad] uint32, filled
+// with 0xFF by the caller before every launch (best threshold published per query, shared by all CTAs)
+cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, const float* nblock, const float* ones,
+                              int n, int nq, int row_words, int k, int kprime, float scale, uint32_t pos_base,
+                              int n_cta, int s_max, const int* d_pieces, uint64_t* cand, int* cand_cnt,
+                              float* cand_thr, uint32_t* gthr, int* inexact_flag, cudaStream_t stream);
 cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, float scale, int* inexact_flag,
                                    cudaStream_t stream);
 // qa: prepared queries [q_pad][row_words]; dbB: B operand rows [n_pad][row_words] (row_words = elements per

@@ -34,6 +34,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -176,6 +177,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 registers per thread -> 32 lanes x 32 consecutive columns (thread = lane = operand row)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (PTX "tcgen05 matrix descriptor"): K-major operand, rows of
 // 128 bytes, 128B swizzle (what the TMA box above produces).  start >> 4 in [0,14), LBO >> 4 in
@@ -457,9 +470,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t acc = kb != 0;
             if (elect_one()) {
               if (p.debug & 8) {  // timing experiment: A operand read from tensor memory (garbage values)
-                for (int j = 0; j < 4; ++j) umma_tf32_ts(tmem_d0, tmem_base + 8 * j, db + 2 * j, idesc, acc | j);
+                const uint32_t idx = (p.debug & 32) ? make_idesc_tf32(TC_BM, 64)
+                                     : (p.debug & 64) ? make_idesc_tf32(TC_BM, 48) : idesc;
+                for (int j = 0; j < 4; ++j) umma_tf32_ts(tmem_d0, tmem_base + 8 * j, db + 2 * j, idx, acc | j);
                 for (int j = 0; j < 4; ++j)
-                  umma_tf32_ts(tmem_d0 + TC_BN, tmem_base + 32 + 8 * j, db + 2 * j, idesc, acc | j);
+                  umma_tf32_ts(tmem_d0 + TC_BN, tmem_base + 32 + 8 * j, db + 2 * j, idx, acc | j);
               } else if (!(p.debug & 4)) {  // (bit 2 set: timing experiment without the MMAs, TMA traffic only)
                 // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (address >> 4) field
                 umma(bf, tmem_d0, da0, db, idesc, acc);
@@ -707,6 +722,378 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------- K1 for D <= 128: A operand in tensor memory
+// Same contract as tc_scan_kernel, different data path.  Measured on config 2 (profiles/README.md): with both
+// operands in shared memory an M=128 x N=128 x K=8 TF32 MMA takes ~96 cycles instead of the 64-cycle floor
+// (operand reads saturate the shared-memory port); with A in tensor memory it takes ~76.  So for rows of at
+// most 128 floats the CTA's 256 prepared queries live in TMEM for the whole piece:
+//   TMEM columns [0,128) A of half 0, [128,256) A of half 1 (thread = lane = query row, one column per
+//   float; written by the epilogue threads with tcgen05.st straight from the query rows in HBM, scaled),
+//   [256,512) two accumulator buffers x two halves x 64 columns.
+// Shared memory then holds nothing but database tiles: one stage = one whole 64-row tile (all k-blocks + the
+// |x|^2 block), so there is ONE full/empty handshake per tile and ~200 KB of loads in flight per SM.
+// The |x|^2 step keeps its A operand (the constant tile of ones) in shared memory: 2 of 34 MMAs per tile.
+constexpr int TS_BN = 64;                 // database rows per tile
+constexpr int TS_CHUNK = TS_BN * 128;     // 8 KB: 64 rows x one 128-byte k-block
+constexpr int TS_ACC0 = 256;              // first accumulator column
+
+constexpr int TS_MAXP = 8;                // pieces per CTA in the plan table
+
+struct TsParams {
+  int n, nq, n_kb;
+  int s_max;
+  const int4* pieces;      // [n_cta][TS_MAXP] {query block, first tile, end tile, slot}; query block < 0 ends the list
+  uint32_t pos_base;
+  uint64_t* cand;
+  int* cand_cnt;
+  float* cand_thr;
+  int cap, kprime, slack, hwm, n_stage, use_nb, debug;
+  uint32_t* gthr;          // [q_pad] ordered bits of the best threshold any piece has published (0xFFFFFFFF = none)
+  const float* q;          // [q_pad][row_words] original queries (zero padded rows)
+  int row_words;
+  float scale;             // A' = scale * q
+  int* inexact_flag;       // set when a valid query row is not TF32-exact
+  unsigned long long* counters;  // NB200_TC_COUNT diagnostics: [0] appended keys, [1] hit rounds, [2] compactions,
+                                 // [3] deferred compactions, [4] chunks; NULL = off
+};
+
+// Warm start of a piece: its first ts_warm_tiles() tiles are scanned twice.  The first time nothing is selected:
+// each row only keeps the minimum of every column class (column mod 32) in 32 registers; the largest of these 32
+// minima bounds the row's 32nd best rank from above (32 distinct points are at least as good), so it is a valid
+// starting threshold -- at about the 3 % quantile after 4096 columns -- bought with min/max instructions only.
+// Starting from +inf instead costs ~6 warp-cooperative compactions per row within the first 10 K columns, all
+// rows of a warp at the same time, and each of them stalls the two-deep accumulator ring.
+__device__ __forceinline__ int ts_warm_tiles(int kprime, int len) {
+  return (kprime <= 32 && len >= 64) ? min(64, len >> 3) : 0;
+}
+
+// one 32-column chunk of one row: fast path = min tree + one compare; survivors are appended to the row's
+// buffer, a full buffer is compacted warp-cooperatively first (see compact_row)
+// A row's threshold after a compaction, shared with the other CTAs that scan other tile ranges for the same
+// query: any published cut has kprime points at or below it, so it bounds the query's kprime-th best rank over
+// the whole shard and every piece may prune with the smallest one seen so far.
+__device__ __forceinline__ float publish_thr(uint32_t* gthr, uint32_t t_ord) {
+  const uint32_t old = atomicMin(gthr, t_ord);
+  return f32_from_ordered(min(old, t_ord));
+}
+
+template <int KPL>
+__device__ __forceinline__ void compact_lane(int src, uint64_t* buf, int& cnt, float& thr, int kprime, int slack,
+                                             uint32_t* gthr, int lane) {
+  const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf, src);
+  const int c = __shfl_sync(FULL, cnt, src);
+  int kept;
+  const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, kprime, slack, lane, &kept);
+  if (lane == src) {
+    cnt = kept;
+    thr = publish_thr(gthr, t);
+  }
+}
+
+template <int KPL>
+__device__ __forceinline__ void epi_process(const uint32_t (&v)[32], uint32_t pos0, int vcols, uint64_t* buf, int& cnt,
+                                            float& thr, int cap, int kprime, int slack, uint32_t* gthr, int lane,
+                                            unsigned (&ctr)[4]) {
+  unsigned need = __ballot_sync(FULL, cnt > cap - 32);
+  while (need) {  // about to overflow: compact at once (normally the deferred path below keeps rows far from here)
+    ++ctr[2];
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    compact_lane<KPL>(src, buf, cnt, thr, kprime, slack, gthr, lane);
+  }
+  float r[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+  if (vcols < 32) {  // rows past the end of the shard: never candidates
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j >= vcols) r[j] = __int_as_float(0x7F800000);
+  }
+  float g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    g[q] = min3(min3(r[8 * q], r[8 * q + 1], r[8 * q + 2]), min3(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
+                fminf(r[8 * q + 6], r[8 * q + 7]));
+  const float m = fminf(min3(g[0], g[1], g[2]), g[3]);
+  if (m < thr) {
+    ++ctr[1];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (g[q] < thr) {
+#pragma unroll
+        for (int j = 8 * q; j < 8 * q + 8; ++j) {
+          const bool hit = r[j] < thr;
+          if (hit) buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
+          cnt += hit ? 1 : 0;
+        }
+      }
+    }
+  }
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmN,
+                  const __grid_constant__ CUtensorMap tmO, const TsParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int ones_bytes = p.use_nb ? CHUNK_BYTES : 0;
+  const int stage_bytes = (p.n_kb + p.use_nb) * TS_CHUNK;
+  unsigned char* smem_ones = smem;
+  unsigned char* smem_st = smem + ones_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + (size_t)p.n_stage * stage_bytes);
+  uint64_t* full_bar = bars;                   // [n_stage] a whole tile has landed
+  uint64_t* empty_bar = bars + p.n_stage;      // [n_stage] every MMA of the tile has read it
+  uint64_t* tfull_bar = bars + 2 * p.n_stage;  // [2] accumulators complete
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulators drained (8 warps)
+  uint64_t* afull_bar = tempty_bar + 2;        // [1] the piece's query rows are in tensor memory (256 threads)
+  uint64_t* ones_bar = afull_bar + 1;          // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ones_bar + 1);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(FULL, tid >> 5, 0), lane = tid & 31;
+  // this CTA's work: a short list of pieces = (query block, tile range) made by the host (tc_ts_plan)
+  const int4* my_pieces = p.pieces + (size_t)blockIdx.x * TS_MAXP;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.n_stage; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 8);
+    }
+    mbar_init(afull_bar, 256);
+    mbar_init(ones_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmB);
+    if (p.use_nb) prefetch_tmap(&tmN);
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer: one whole tile per stage =====================
+    {
+      if (p.use_nb && elect_one()) {
+        mbar_expect_tx(ones_bar, CHUNK_BYTES);
+        tma_load_2d(&tmO, ones_bar, smem_ones, 0, 0);
+      }
+      __syncwarp();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int pi = 0; pi < TS_MAXP; ++pi) {
+        const int4 pc = __ldg(my_pieces + pi);
+        if (pc.x < 0) break;
+        const int t_begin = pc.y, len = pc.z - pc.y;
+        const int wa = ts_warm_tiles(p.kprime, len);
+        for (int idx = -wa; idx < len; ++idx) {
+          const int t = t_begin + (idx < 0 ? idx + wa : idx);
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          unsigned char* st = smem_st + (size_t)s * stage_bytes;
+          if (elect_one()) {
+            if (p.debug & 2) {  // timing experiment: no database traffic
+              mbar_arrive(&full_bar[s]);
+            } else {
+              mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+              for (int kb = 0; kb < p.n_kb; ++kb)
+                tma_load_2d(&tmB, &full_bar[s], st + kb * TS_CHUNK, kb * TC_KB, t * TS_BN);
+              if (p.use_nb) tma_load_2d(&tmN, &full_bar[s], st + p.n_kb * TS_CHUNK, 0, t * TS_BN);
+            }
+          }
+          __syncwarp();
+          if (++s == p.n_stage) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TS_BN);
+      const uint32_t st_base = smem_u32(smem_st);
+      const uint64_t d_ones = make_smem_desc(smem_u32(smem_ones));
+      if (p.use_nb) mbar_wait(ones_bar, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int ti = 0;
+      for (int pi = 0; pi < TS_MAXP; ++pi) {
+        const int4 pc = __ldg(my_pieces + pi);
+        if (pc.x < 0) break;
+        const int n_iter = (pc.z - pc.y) + ts_warm_tiles(p.kprime, pc.z - pc.y);
+        mbar_wait(afull_bar, pi & 1);
+        tc_fence_after();
+        for (int it = 0; it < n_iter; ++it, ++ti) {
+          const int b = ti & 1;
+          mbar_wait(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + (uint32_t)(TS_ACC0 + b * 2 * TS_BN);
+          const uint32_t d1 = d0 + TS_BN;
+          const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
+          if (elect_one()) {
+            if (!(p.debug & 4)) {
+              for (int kb = 0; kb < p.n_kb; ++kb) {
+                const uint64_t db = make_smem_desc(sb + (uint32_t)kb * TS_CHUNK);
+                const uint32_t a0 = tmem_base + (uint32_t)(kb * TC_KB);
+                const uint32_t a1 = a0 + 128u;
+                const uint32_t acc = kb != 0;
+                // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes (+2 in the descriptor) of B
+                umma_tf32_ts(d0, a0, db, idesc, acc);
+                umma_tf32_ts(d1, a1, db, idesc, acc);
+                umma_tf32_ts(d0, a0 + 8, db + 2, idesc, 1);
+                umma_tf32_ts(d1, a1 + 8, db + 2, idesc, 1);
+                umma_tf32_ts(d0, a0 + 16, db + 4, idesc, 1);
+                umma_tf32_ts(d1, a1 + 16, db + 4, idesc, 1);
+                umma_tf32_ts(d0, a0 + 24, db + 6, idesc, 1);
+                umma_tf32_ts(d1, a1 + 24, db + 6, idesc, 1);
+              }
+              if (p.use_nb) {  // + 1.0 * (hi + mid + lo pieces of |x|^2)
+                const uint64_t dbn = make_smem_desc(sb + (uint32_t)p.n_kb * TS_CHUNK);
+                umma_tf32(d0, d_ones, dbn, idesc, 1);
+                umma_tf32(d1, d_ones, dbn, idesc, 1);
+              }
+            }
+            tc_commit(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
+            tc_commit(&tfull_bar[b]);   // accumulators of this tile are complete
+          }
+          __syncwarp();
+          if (++s == p.n_stage) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps, thread == one query row =====================
+    const int e = warp - 2;
+    const int h = e >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    unsigned ctr[4] = {0, 0, 0, 0};
+    int ti = 0;
+    for (int pi = 0; pi < TS_MAXP; ++pi) {
+      const int4 pc = __ldg(my_pieces + pi);
+      if (pc.x < 0) break;
+      const int qb = pc.x, t_begin = pc.y, t_end = pc.z;
+      const size_t unit = (size_t)qb * p.s_max + pc.w;
+      const int qrow = qb * TC_QB + h * TC_BM + row;
+      const bool row_valid = qrow < p.nq;
+      uint64_t* buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
+      uint32_t* gthr = p.gthr + qrow;
+      int cnt = 0;
+      float thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+      {
+        // This piece's operand rows: HBM -> registers -> tensor memory.  Every MMA of the previous piece has
+        // completed (this thread has seen the tfull of its last tile), so the columns may be overwritten.
+        const float4* src = reinterpret_cast<const float4*>(p.q + (size_t)qrow * p.row_words);
+        unsigned bad = 0;
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 f = __ldg(src + kb * 8 + i);
+            bad |= (__float_as_uint(f.x) | __float_as_uint(f.y) | __float_as_uint(f.z) | __float_as_uint(f.w)) & 0x1FFFu;
+            v[4 * i] = __float_as_uint(f.x * p.scale);
+            v[4 * i + 1] = __float_as_uint(f.y * p.scale);
+            v[4 * i + 2] = __float_as_uint(f.z * p.scale);
+            v[4 * i + 3] = __float_as_uint(f.w * p.scale);
+          }
+          tmem_st32(trow + (uint32_t)(h * 128 + kb * TC_KB), v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(afull_bar);
+        if (!row_valid) bad = 0;
+        if (__any_sync(FULL, bad != 0) && lane == 0) atomicOr(p.inexact_flag, 1);
+      }
+      const int len = t_end - t_begin;
+      const int wa = ts_warm_tiles(p.kprime, len);
+      // wait for a tile's accumulators, pull this row's 64 columns into registers and hand the buffer back to
+      // the tensor core at once (a warp inside a compaction must not hold up the other seven and the MMA)
+      auto drain = [&](uint32_t (&v0)[32], uint32_t (&v1)[32]) {
+        const int b = ti & 1;
+        mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tcol = trow + (uint32_t)(TS_ACC0 + (b * 2 + h) * TS_BN);
+        tmem_ld32(tcol, v0);
+        tmem_ld32(tcol + 32u, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[b]);
+        ++ti;
+      };
+      if (wa > 0) {  // warm start (see ts_warm_tiles)
+        float gm[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gm[j] = __int_as_float(0x7F800000);
+        for (int i = 0; i < wa; ++i) {
+          uint32_t v0[32], v1[32];
+          drain(v0, v1);
+          const int vtile = p.n - (t_begin + i) * TS_BN;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = j < vtile ? __uint_as_float(v0[j]) : __int_as_float(0x7F800000);
+            const float c = j + 32 < vtile ? __uint_as_float(v1[j]) : __int_as_float(0x7F800000);
+            gm[j] = min3(gm[j], a, c);
+          }
+        }
+        float t = gm[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) t = fmaxf(t, gm[j]);
+        if (row_valid && !(p.debug & 1)) thr = publish_thr(gthr, f32_ordered(t));
+      }
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        uint32_t v0[32], v1[32];
+        drain(v0, v1);
+        if (p.debug & 1) {  // timing experiment: select nothing
+          if (__uint_as_float(v0[0]) == 1.2345e-30f || __uint_as_float(v1[0]) == 1.2345e-30f) thr = 0.f;
+          continue;
+        }
+        // what the other pieces of this query have found in the meantime (fminf ignores the NaN of "nothing yet")
+        if (((tile - t_begin) & 15) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
+        const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TS_BN);
+        const int vtile = p.n - tile * TS_BN;
+        epi_process<KPL>(v0, pos_tile, vtile, buf, cnt, thr, p.cap, p.kprime, p.slack, gthr, lane, ctr);
+        epi_process<KPL>(v1, pos_tile + 32, vtile - 32, buf, cnt, thr, p.cap, p.kprime, p.slack, gthr, lane, ctr);
+        // deferred compaction: a row past the high-water mark is compacted here, at most one row per warp and
+        // tile, so the bursts (all rows of a warp fill at the same rate) are spread over the slack that every
+        // tile leaves; only a row that is about to overflow is compacted at once (epi_process)
+        const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);
+        if (pend) {
+          ++ctr[3];
+          compact_lane<KPL>(__ffs(pend) - 1, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
+        }
+      }
+      const size_t slot = unit * TC_QB + h * TC_BM + row;
+      p.cand_cnt[slot] = row_valid ? cnt : 0;
+      p.cand_thr[slot] = thr;
+    }
+    if (p.counters && lane == 0) {
+      for (int i = 0; i < 4; ++i) atomicAdd(p.counters + i, (unsigned long long)ctr[i]);
+      atomicAdd(p.counters + 4, (unsigned long long)ti * 2);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------- pass 2: exact re-rank
 struct RerankParams {
   const float* db;         // [n_pad][row_words] ORIGINAL vectors
@@ -746,9 +1133,9 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
     for (int s = 0; s < p.n_split; ++s) {
       const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
       s_off[s] = off;
-      const int c = p.cand_cnt[slot];
-      off += c;
-      if (c > 0) mt = fminf(mt, p.cand_thr[slot]);  // cnt == 0: piece unused, or it never dropped anything
+      const int c = p.cand_cnt[slot];   // -1: slot unused (the host fills the array with 0xFF)
+      off += max(c, 0);
+      if (c >= 0) mt = fminf(mt, p.cand_thr[slot]);  // +inf when the piece never dropped anything
     }
     s_off[p.n_split] = off;
     s_minthr = mt;
@@ -1002,13 +1389,14 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // rows x row_words fp32, row-major; box = 128 rows x 32 floats, 128B swizzle
-bool make_tmap(CUtensorMap* map, const void* base, size_t rows, int row_elems, bool bf16 = false) {
+bool make_tmap(CUtensorMap* map, const void* base, size_t rows, int row_elems, bool bf16 = false,
+               int box_rows = TC_BM) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   const int esz = bf16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)row_elems * esz};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)TC_BM};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1063,11 +1451,11 @@ cudaError_t launch_tc_prep_queries_bf16(const float* q, int q_pad, int row_words
 //  * aligned: every query block is cut into the same `s` segments; q_blocks * s CTAs.  Chosen when some s
 //    fills >= 80 % of the last wave: co-scheduled CTAs then stream the same tiles and share them in L2.
 //  * linear (few query blocks): equal linear ranges, `sm_count` CTAs, a CTA may span two query blocks.
-void tc_plan(int nq, int n, int k, int sm_count, int* n_cta, int* work_per_cta, int* s_max, int* aligned) {
+void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned) {
   int kprime, cap;
   tc_candidate_shape(k, &kprime, &cap);
   const long q_blocks = (nq + TC_QB - 1) / TC_QB;
-  const long n_tiles = (n + TC_BN - 1) / TC_BN;
+  const long n_tiles = (n + bn - 1) / bn;
   const long total = q_blocks * n_tiles;
   // the re-rank sorts s_max * cap keys per query in shared memory: bound the pieces per query block
   const long max_pieces = std::min<long>(64, std::max<long>(2, 16384 / cap));
@@ -1133,7 +1521,7 @@ void tc_candidate_shape(int k, int* kprime, int* cap) {
   int kp = k + 22 < 2 * k ? k + 22 + (k / 4) : 2 * k;  // headroom for the certificate
   if (kp < k + 22) kp = k + 22;
   kp = (kp + 31) / 32 * 32;
-  int c = kp <= 32 ? 128 : kp <= 96 ? 256 : 512;
+  int c = kp <= 96 ? 256 : 512;  // (256 even for k' = 32: half as many compactions as 128, see profiles/README.md)
   if (kp > c - 64) kp = c - 64;
   *kprime = kp;
   *cap = c;
@@ -1208,6 +1596,173 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   if (e != cudaSuccess)
     fprintf(stderr, "nmslib_b200: tc_scan launch (grid %d, smem %zu, stages %d) failed: %s\n", n_cta, smem, p.n_stage,
             cudaGetErrorString(e));
+  return e;
+}
+
+bool tc_ts_supported(int row_words) {
+  static const bool off = [] {
+    const char* e = getenv("NB200_TC_NO_TS");
+    return e && e[0] == '1';
+  }();
+  return !off && row_words <= 128 && row_words % TC_KB == 0;
+}
+int tc_ts_block_points() { return TS_BN; }
+
+// Work decomposition of the TS kernel: a table of pieces (query block, tile range, candidate slot) per CTA.
+//  * whole waves of query blocks (>= sm_count of them): one CTA = one block over the whole shard; CTAs of a wave
+//    sweep the same tiles together, so the L2 serves all but one of them;
+//  * the remaining B' < sm_count blocks: g = floor(S / B') aligned segments per block (CTAs of a segment are
+//    neighbours and share tiles in L2) covering the first g*B'/S of the tiles, and the R = S - g*B' CTAs left
+//    over split what remains of every block in equal linear ranges -- every SM gets the same number of tiles.
+void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int* n_cta, int* s_max) {
+  int kprime, cap;
+  tc_candidate_shape(k, &kprime, &cap);
+  const int B = (nq + TC_QB - 1) / TC_QB;
+  const int T = (n + TS_BN - 1) / TS_BN;
+  const int S = std::max(1, sm_count);
+  const int max_pieces = std::min(64, std::max(4, 16384 / cap));
+  std::vector<std::vector<int4>> ctas;
+  std::vector<int> slots(B, 0);
+  auto add_piece = [&](std::vector<int4>& c, int qb, int t0, int t1) {
+    if (t1 <= t0) return;
+    c.push_back(make_int4(qb, t0, t1, slots[qb]++));
+  };
+  const int full = (B / S) * S;
+  for (int qb = 0; qb < full; ++qb) {
+    ctas.emplace_back();
+    add_piece(ctas.back(), qb, 0, T);
+  }
+  const int Bp = B - full;
+  if (Bp > 0) {
+    // (behind whole waves keep the lists per block few: every block's candidate buffers are sized by s_max)
+    int g = std::max(1, std::min(std::min(S / Bp, full > 0 ? 4 : max_pieces - 3), T));
+    int R = (g == S / Bp) ? S - g * Bp : 0;
+    if (R > 0 && (Bp + R - 1) / R + 1 > TS_MAXP - 2) R = 0;   // too many blocks per left-over CTA
+    long Wa = R > 0 ? ((long)T * Bp) / S : (T + g - 1) / g;
+    if (Wa < 1) { Wa = 1; R = 0; }
+    if (R == 0) g = (int)((T + Wa - 1) / Wa);
+    const long Ta = std::min<long>((long)g * Wa, T);
+    // aligned part: CTA index = seg * Bp + block, so the CTAs of a segment are launched together
+    for (int seg = 0; seg < g; ++seg)
+      for (int b = 0; b < Bp; ++b) {
+        const long t0 = (long)seg * Wa, t1 = std::min<long>(t0 + Wa, R > 0 ? Ta : T);
+        if (t1 <= t0) continue;
+        ctas.emplace_back();
+        add_piece(ctas.back(), full + b, (int)t0, (int)t1);
+      }
+    if (R > 0) {
+      const long r = T - Ta, total = (long)Bp * r, Wr = (total + R - 1) / R;
+      for (int j = 0; j < R; ++j) {
+        const long u0 = (long)j * Wr, u1 = std::min(u0 + Wr, total);
+        if (u1 <= u0) break;
+        ctas.emplace_back();
+        for (long u = u0; u < u1;) {
+          const long b = u / r, off = u - b * r, len = std::min(r - off, u1 - u);
+          add_piece(ctas.back(), full + (int)b, (int)(Ta + off), (int)(Ta + off + len));
+          u += len;
+        }
+      }
+    }
+  }
+  int smax = 1;
+  for (int v : slots) smax = std::max(smax, v);
+  table->assign(ctas.size() * TS_MAXP * 4, -1);
+  for (size_t c = 0; c < ctas.size(); ++c)
+    for (size_t i = 0; i < ctas[c].size() && i < (size_t)TS_MAXP; ++i) {
+      int* e = table->data() + (c * TS_MAXP + i) * 4;
+      e[0] = ctas[c][i].x;
+      e[1] = ctas[c][i].y;
+      e[2] = ctas[c][i].z;
+      e[3] = ctas[c][i].w;
+    }
+  *n_cta = (int)ctas.size();
+  *s_max = smax;
+}
+
+cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, const float* nblock, const float* ones,
+                              int n, int nq, int row_words, int k, int kprime, float scale, uint32_t pos_base,
+                              int n_cta, int s_max, const int* d_pieces, uint64_t* cand, int* cand_cnt,
+                              float* cand_thr, uint32_t* gthr, int* inexact_flag, cudaStream_t stream) {
+  if (n <= 0 || nq <= 0) return cudaSuccess;
+  if (!tc_ts_supported(row_words)) return cudaErrorInvalidValue;
+  CUtensorMap tmB, tmN, tmO;
+  if (!make_tmap(&tmB, dbB, n_pad, row_words, false, TS_BN)) return cudaErrorUnknown;
+  const bool use_nb = nblock != nullptr;
+  if (use_nb) {
+    if (!make_tmap(&tmN, nblock, n_pad, TC_KB, false, TS_BN) || !make_tmap(&tmO, ones, TC_BM, TC_KB)) return cudaErrorUnknown;
+  } else {
+    tmN = tmB;
+    tmO = tmB;
+  }
+  TsParams p;
+  p.n = n;
+  p.nq = nq;
+  p.n_kb = row_words / TC_KB;
+  p.s_max = s_max;
+  p.pieces = reinterpret_cast<const int4*>(d_pieces);
+  p.pos_base = pos_base;
+  p.cand = cand;
+  p.cand_cnt = cand_cnt;
+  p.cand_thr = cand_thr;
+  int kp_default;
+  tc_candidate_shape(k, &kp_default, &p.cap);
+  if (p.cap < 128) return cudaErrorInvalidValue;  // (the register mode of tc_scan_kernel<0> is not built here)
+  // survivors of a compaction: kprime .. kprime + slack; rows are compacted (deferred, one per warp and tile)
+  // once they hold more than hwm keys -- early, because the threshold only tightens at a compaction
+  p.kprime = std::max(k + 1, std::min(kprime, kp_default));
+  p.slack = std::max(8, p.kprime / 2);
+  p.hwm = std::min(p.cap / 2, std::max(64, 3 * p.kprime));
+  p.gthr = gthr;
+  p.use_nb = use_nb ? 1 : 0;
+  {
+    const char* dbg = getenv("NB200_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  p.q = q;
+  p.row_words = row_words;
+  p.scale = scale;
+  p.inexact_flag = inexact_flag;
+  p.counters = nullptr;
+  static const bool count = [] {
+    const char* e = getenv("NB200_TC_COUNT");
+    return e && e[0] == '1';
+  }();
+  if (count) {  // diagnostics only: synchronous, prints the epilogue's event counts of the previous launch
+    static unsigned long long* d_ctr = nullptr;
+    if (!d_ctr) {
+      cudaMalloc(&d_ctr, 64);
+    } else {
+      unsigned long long h[5];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, d_ctr, 40, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "tc_scan_ts counters: (unused) %llu, slow-path entries %llu, forced compactions %llu, deferred %llu, warp-chunks %llu\n",
+              h[0], h[1], h[2], h[3], h[4]);
+    }
+    cudaMemsetAsync(d_ctr, 0, 64, stream);
+    p.counters = d_ctr;
+  }
+  const int ones_bytes = use_nb ? CHUNK_BYTES : 0;
+  const int stage_bytes = (p.n_kb + p.use_nb) * TS_CHUNK;
+  const int budget = 225 * 1024;
+  p.n_stage = (budget - ones_bytes) / stage_bytes;
+  if (p.n_stage > 8) p.n_stage = 8;
+  if (p.n_stage < 2) return cudaErrorInvalidValue;
+  const size_t smem = 1024 + (size_t)ones_bytes + (size_t)p.n_stage * stage_bytes + (2 * 8 + 8) * 8 + 16;
+  cudaError_t e;
+#define NB_TS(KPL)                                                                                           \
+  e = cudaFuncSetAttribute(tc_scan_ts_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+  if (e != cudaSuccess) return e;                                                                            \
+  tc_scan_ts_kernel<KPL><<<n_cta, TC_THREADS, smem, stream>>>(tmB, tmN, tmO, p);
+  switch (p.cap) {
+    case 128: NB_TS(4); break;
+    case 256: NB_TS(8); break;
+    default: NB_TS(16); break;
+  }
+#undef NB_TS
+  e = cudaGetLastError();
+  if (e != cudaSuccess)
+    fprintf(stderr, "nmslib_b200: tc_scan_ts launch (grid %d, smem %zu, stages %d) failed: %s\n", n_cta, smem,
+            p.n_stage, cudaGetErrorString(e));
   return e;
 }
 

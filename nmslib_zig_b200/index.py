@@ -82,7 +82,7 @@ ABI_SYMBOLS = [
 EXT_SYMBOLS = [
     "nmslib_b200_set_device", "nmslib_b200_device_available", "nmslib_b200_set_shard", "nmslib_b200_import_hnsw",
     "nmslib_b200_prepare", "nmslib_b200_knn_device", "nmslib_b200_merge_topk", "nmslib_b200_get_stats",
-    "nmslib_b200_version",
+    "nmslib_b200_version", "nmslib_b200_scan_plan",
 ]
 
 _lib = None
@@ -172,6 +172,7 @@ def lib() -> C.CDLL:
         "nmslib_b200_merge_topk": (C.c_int, [vp, vp, vp, sz, sz, sz, vp, vp, vp]),
         "nmslib_b200_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "nmslib_b200_version": (C.c_char_p, []),
+        "nmslib_b200_scan_plan": (sz, [sz, sz, sz, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here == a symbol the header promises is not exported
@@ -485,6 +486,17 @@ def device_available() -> bool:
 
 def set_device(device: int):
     lib().nmslib_b200_set_device(device)
+
+
+def scan_plan(nq: int, n: int, k: int, sm_count: int = 148):
+    """Work decomposition of the tensor-core scan (host logic only): (pieces[m,5], n_cta, s_max) with
+    pieces = {cta, query block, first tile, end tile, slot}."""
+    L = lib()
+    nc, sm = C.c_int(0), C.c_int(0)
+    m = L.nmslib_b200_scan_plan(nq, n, k, sm_count, None, 0, C.byref(nc), C.byref(sm))
+    out = np.zeros((m, 5), np.int32)
+    L.nmslib_b200_scan_plan(nq, n, k, sm_count, out.ctypes.data, m, C.byref(nc), C.byref(sm))
+    return out, nc.value, sm.value
 
 
 def version() -> str:

@@ -1,0 +1,21 @@
+"""Three config-2 query batches (the ncu target: `-k regex:tc_scan -s 1 -c 1` captures a warm launch).
+usage: tc_prof.py [dim] [n] [nq] [k]"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import nmslib_zig_b200 as nb
+from nmslib_zig_b200 import synth
+
+dim = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+nq = int(sys.argv[3]) if len(sys.argv) > 3 else 10_000
+k = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
+idx = nb.Index("l2sqr", None, "seq_search")
+idx.addDenseBatch(data)
+idx.buildIndex()
+for _ in range(3):
+    idx.knnQueryBatch(q, k)
+    print("scan_ms", idx.stats()["last_scan_ms"], "fallback", idx.stats()["fallback_queries"], flush=True)
+idx.deinit()
