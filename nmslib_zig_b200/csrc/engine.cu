@@ -80,6 +80,7 @@ Engine::Engine(Space space, Method method, bool is_u8, int device)
     : space_(space), method_(method), is_u8_(is_u8), device_(device) {
   const char* fe = getenv("NB200_FORCE_EXACT");  // debugging / A-B switch: CUDA-core exact scan only
   force_exact_ = fe && fe[0] == '1';
+  if (const char* e = getenv("NB200_TC_MARGIN")) tc_margin_ = std::max(1, atoi(e));
 }
 
 Engine::~Engine() {

@@ -748,6 +748,8 @@ struct TsParams {
   int* cand_cnt;
   float* cand_thr;
   int cap, kprime, slack, hwm, n_stage, use_nb, debug;
+  int warm_max;            // tiles of the warm start (0 when kprime > 32: the 32 column classes bound only the 32nd best)
+  int refresh_mask;        // the shared threshold is re-read every (mask + 1) tiles
   uint32_t* gthr;          // [q_pad] ordered bits of the best threshold any piece has published (0xFFFFFFFF = none)
   const float* q;          // [q_pad][row_words] original queries (zero padded rows)
   int row_words;
@@ -763,8 +765,8 @@ struct TsParams {
 // starting threshold -- at about the 3 % quantile after 4096 columns -- bought with min/max instructions only.
 // Starting from +inf instead costs ~6 warp-cooperative compactions per row within the first 10 K columns, all
 // rows of a warp at the same time, and each of them stalls the two-deep accumulator ring.
-__device__ __forceinline__ int ts_warm_tiles(int kprime, int len) {
-  return (kprime <= 32 && len >= 64) ? min(64, len >> 3) : 0;
+__device__ __forceinline__ int ts_warm_tiles(int warm_max, int len) {
+  return len >= 64 ? min(warm_max, len >> 3) : 0;
 }
 
 // one 32-column chunk of one row: fast path = min tree + one compare; survivors are appended to the row's
@@ -790,16 +792,24 @@ __device__ __forceinline__ void compact_lane(int src, uint64_t* buf, int& cnt, f
   }
 }
 
-template <int KPL>
+constexpr int TS_RK = 16;  // register mode: ranks of a row's 16 best candidates, sorted, in registers
+
+// REG (kprime <= 16, i.e. k <= 10 with the default margin): the row's threshold is the exact 16th best rank seen,
+// kept as a sorted register list of RANKS only (insertion = a 16-step min/max chain); the (rank, position) keys
+// themselves are appended to the row's buffer, which then only ever receives the ~k ln(N) true improvements
+// and needs no compaction.  !REG: the threshold tightens when the buffer is compacted (compact_row).
+template <int KPL, bool REG>
 __device__ __forceinline__ void epi_process(const uint32_t (&v)[32], uint32_t pos0, int vcols, uint64_t* buf, int& cnt,
-                                            float& thr, int cap, int kprime, int slack, uint32_t* gthr, int lane,
-                                            unsigned (&ctr)[4]) {
+                                            float& thr, float (&tk)[TS_RK], int cap, int kprime, int slack,
+                                            uint32_t* gthr, int lane, unsigned (&ctr)[4]) {
   unsigned need = __ballot_sync(FULL, cnt > cap - 32);
-  while (need) {  // about to overflow: compact at once (normally the deferred path below keeps rows far from here)
+  while (need) {  // about to overflow: compact at once (!REG: normally the deferred path keeps rows far from here)
     ++ctr[2];
     const int src = __ffs(need) - 1;
     need &= need - 1;
+    const float keep = thr;
     compact_lane<KPL>(src, buf, cnt, thr, kprime, slack, gthr, lane);
+    if (REG) thr = fminf(thr, keep);  // (the cut is never below the 16th best, the list stays authoritative)
   }
   float r[32];
 #pragma unroll
@@ -820,18 +830,48 @@ __device__ __forceinline__ void epi_process(const uint32_t (&v)[32], uint32_t po
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (g[q] < thr) {
+        if constexpr (REG) {
+          // which of the group's 8 values pass, then ONE copy of the insertion code per group, run per survivor
+          unsigned mk = 0;
 #pragma unroll
-        for (int j = 8 * q; j < 8 * q + 8; ++j) {
-          const bool hit = r[j] < thr;
-          if (hit) buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
-          cnt += hit ? 1 : 0;
+          for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] < thr ? 1u : 0u) << jj;
+#pragma unroll 1
+          while (mk) {
+            const int jj = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const float lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
+            const float hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
+            const float x = (jj & 4) ? hi4 : lo4;
+            if (x < thr) {
+              buf[cnt] = ((uint64_t)__float_as_uint(x) << 32) | (uint64_t)(pos0 + 8 * q + jj);
+              ++cnt;
+              float t = x;  // sorted insertion: every slot keeps the smaller of (itself, what is carried)
+#pragma unroll
+              for (int i = 0; i < TS_RK; ++i) {
+                const float lo = fminf(tk[i], t);
+                t = fmaxf(tk[i], t);
+                tk[i] = lo;
+              }
+              if (tk[TS_RK - 1] < thr) {
+                thr = tk[TS_RK - 1];
+                atomicMin(gthr, f32_ordered(thr));  // (result unused: a fire-and-forget reduction)
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 8 * q; j < 8 * q + 8; ++j) {
+            const bool hit = r[j] < thr;
+            if (hit) buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
+            cnt += hit ? 1 : 0;
+          }
         }
       }
     }
   }
 }
 
-template <int KPL>
+template <int KPL, bool REG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmN,
                   const __grid_constant__ CUtensorMap tmO, const TsParams p) {
@@ -892,7 +932,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         const int4 pc = __ldg(my_pieces + pi);
         if (pc.x < 0) break;
         const int t_begin = pc.y, len = pc.z - pc.y;
-        const int wa = ts_warm_tiles(p.kprime, len);
+        const int wa = ts_warm_tiles(p.warm_max, len);
         for (int idx = -wa; idx < len; ++idx) {
           const int t = t_begin + (idx < 0 ? idx + wa : idx);
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -928,7 +968,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       for (int pi = 0; pi < TS_MAXP; ++pi) {
         const int4 pc = __ldg(my_pieces + pi);
         if (pc.x < 0) break;
-        const int n_iter = (pc.z - pc.y) + ts_warm_tiles(p.kprime, pc.z - pc.y);
+        const int n_iter = (pc.z - pc.y) + ts_warm_tiles(p.warm_max, pc.z - pc.y);
         mbar_wait(afull_bar, pi & 1);
         tc_fence_after();
         for (int it = 0; it < n_iter; ++it, ++ti) {
@@ -993,6 +1033,9 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       uint32_t* gthr = p.gthr + qrow;
       int cnt = 0;
       float thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+      float tk[TS_RK];
+#pragma unroll
+      for (int i = 0; i < TS_RK; ++i) tk[i] = __int_as_float(0x7F800000);
       {
         // This piece's operand rows: HBM -> registers -> tensor memory.  Every MMA of the previous piece has
         // completed (this thread has seen the tfull of its last tile), so the columns may be overwritten.
@@ -1018,7 +1061,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         if (__any_sync(FULL, bad != 0) && lane == 0) atomicOr(p.inexact_flag, 1);
       }
       const int len = t_end - t_begin;
-      const int wa = ts_warm_tiles(p.kprime, len);
+      const int wa = ts_warm_tiles(p.warm_max, len);
       // wait for a tile's accumulators, pull this row's 64 columns into registers and hand the buffer back to
       // the tensor core at once (a warp inside a compaction must not hold up the other seven and the MMA)
       auto drain = [&](uint32_t (&v0)[32], uint32_t (&v1)[32]) {
@@ -1062,11 +1105,14 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
           continue;
         }
         // what the other pieces of this query have found in the meantime (fminf ignores the NaN of "nothing yet")
-        if (((tile - t_begin) & 15) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
+        if (((tile - t_begin) & p.refresh_mask) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
+        if (p.debug & 64) thr = __int_as_float(0xFF800000);  // timing experiment: fast path only, nothing passes
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TS_BN);
         const int vtile = p.n - tile * TS_BN;
-        epi_process<KPL>(v0, pos_tile, vtile, buf, cnt, thr, p.cap, p.kprime, p.slack, gthr, lane, ctr);
-        epi_process<KPL>(v1, pos_tile + 32, vtile - 32, buf, cnt, thr, p.cap, p.kprime, p.slack, gthr, lane, ctr);
+        epi_process<KPL, REG>(v0, pos_tile, vtile, buf, cnt, thr, tk, p.cap, p.kprime, p.slack, gthr, lane, ctr);
+        epi_process<KPL, REG>(v1, pos_tile + 32, vtile - 32, buf, cnt, thr, tk, p.cap, p.kprime, p.slack, gthr, lane,
+                              ctr);
+        if constexpr (REG) continue;
         // deferred compaction: a row past the high-water mark is compacted here, at most one row per warp and
         // tile, so the bursts (all rows of a warp fill at the same rate) are spread over the slack that every
         // tile leaves; only a row that is about to overflow is compacted at once (epi_process)
@@ -1712,6 +1758,11 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   p.kprime = std::max(k + 1, std::min(kprime, kp_default));
   p.slack = std::max(8, p.kprime / 2);
   p.hwm = std::min(p.cap / 2, std::max(64, 3 * p.kprime));
+  p.warm_max = p.kprime <= 32 ? 64 : 0;
+  p.refresh_mask = 15;
+  if (const char* e = getenv("NB200_TC_HWM")) p.hwm = std::max(p.kprime + p.slack + 8, std::min(p.cap - 40, atoi(e)));
+  if (const char* e = getenv("NB200_TC_WARM")) p.warm_max = p.kprime <= 32 ? std::max(0, atoi(e)) : 0;
+  if (const char* e = getenv("NB200_TC_REFRESH")) p.refresh_mask = std::max(0, atoi(e));
   p.gthr = gthr;
   p.use_nb = use_nb ? 1 : 0;
   {
@@ -1749,14 +1800,22 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   if (p.n_stage < 2) return cudaErrorInvalidValue;
   const size_t smem = 1024 + (size_t)ones_bytes + (size_t)p.n_stage * stage_bytes + (2 * 8 + 8) * 8 + 16;
   cudaError_t e;
-#define NB_TS(KPL)                                                                                           \
-  e = cudaFuncSetAttribute(tc_scan_ts_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-  if (e != cudaSuccess) return e;                                                                            \
-  tc_scan_ts_kernel<KPL><<<n_cta, TC_THREADS, smem, stream>>>(tmB, tmN, tmO, p);
-  switch (p.cap) {
-    case 128: NB_TS(4); break;
-    case 256: NB_TS(8); break;
-    default: NB_TS(16); break;
+#define NB_TS(KPL, REG)                                                                                           \
+  e = cudaFuncSetAttribute(tc_scan_ts_kernel<KPL, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+  if (e != cudaSuccess) return e;                                                                                 \
+  tc_scan_ts_kernel<KPL, REG><<<n_cta, TC_THREADS, smem, stream>>>(tmB, tmN, tmO, p);
+  static const bool no_reg = [] {
+    const char* e2 = getenv("NB200_TC_NO_REG");
+    return e2 && e2[0] == '1';
+  }();
+  if (p.kprime <= TS_RK && p.cap == 256 && !no_reg) {
+    p.kprime = TS_RK;  // the register list always holds 16
+    p.slack = 8;
+    NB_TS(8, true);
+  } else if (p.cap == 256) {
+    NB_TS(8, false);
+  } else {
+    NB_TS(16, false);
   }
 #undef NB_TS
   e = cudaGetLastError();
