@@ -996,7 +996,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
                 umma_tf32_ts(d0, a0 + 24, db + 6, idesc, 1);
                 umma_tf32_ts(d1, a1 + 24, db + 6, idesc, 1);
               }
-              if (p.use_nb) {  // + 1.0 * (hi + mid + lo pieces of |x|^2)
+              if (p.use_nb && !(p.debug & 128)) {  // + 1.0 * (hi + mid + lo pieces of |x|^2)
                 const uint64_t dbn = make_smem_desc(sb + (uint32_t)p.n_kb * TS_CHUNK);
                 umma_tf32(d0, d_ones, dbn, idesc, 1);
                 umma_tf32(d1, d_ones, dbn, idesc, 1);
@@ -1167,93 +1167,101 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);          // [items_pow2] exact keys
   float* srank = reinterpret_cast<float*>(sk + items_pow2);       // [items_pow2] exact rank (certificate domain)
-  __shared__ int s_off[65];
+  uint32_t* spos = reinterpret_cast<uint32_t*>(srank);            // (the same words first hold the live positions)
+  __shared__ int s_cnt[65];
+  __shared__ int s_live;
   __shared__ float s_minthr, s_qn2;
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qb = q / TC_QB, row = q % TC_QB;
   const float* qv = p.queries + (size_t)q * p.row_words;
 
   if (tid == 0) {
-    int off = 0;
     float mt = __int_as_float(0x7F800000);
     for (int s = 0; s < p.n_split; ++s) {
       const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
-      s_off[s] = off;
       const int c = p.cand_cnt[slot];   // -1: slot unused (the host fills the array with 0xFF)
-      off += max(c, 0);
+      s_cnt[s] = max(c, 0);
       if (c >= 0) mt = fminf(mt, p.cand_thr[slot]);  // +inf when the piece never dropped anything
     }
-    s_off[p.n_split] = off;
     s_minthr = mt;
+    s_live = 0;
   }
-  if (warp == 0) {
+  if (warp == 1) {
     float s = 0.f;
     for (int c = lane; c < p.row_words; c += 32) s = fmaf(qv[c], qv[c], s);
     s = warp_sum_f(s);
     if (lane == 0) s_qn2 = s;
   }
   __syncthreads();
-  const int total = s_off[p.n_split];
   const float qn2 = s_qn2;
-  // sort only as many slots as this query actually has candidates (the buffers are mostly far from full)
+  const float minthr = s_minthr;
+  // Only candidates whose pass-1 rank lies below the smallest threshold any piece ended with can matter: if
+  // the certificate below holds, every true neighbour has pass-1 rank < minthr, and if it does not
+  // hold the query is re-run anyway.  With shared thresholds this is ~k' keys out of the few hundred appended.
+  for (int s = 0; s < p.n_split; ++s) {
+    const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
+    const uint64_t* cb = p.cand + slot * (size_t)p.cap;
+    const int c = s_cnt[s];
+    for (int i = tid; i < c; i += blockDim.x) {
+      const uint64_t key = cb[i];
+      if (__uint_as_float((uint32_t)(key >> 32)) < minthr) spos[atomicAdd(&s_live, 1)] = (uint32_t)key;
+    }
+  }
+  __syncthreads();
+  const int total = s_live;
   int p2e = 32;
   while (p2e < total || p2e < p.k) p2e <<= 1;
   if (p2e > items_pow2) p2e = items_pow2;
-  for (int t = tid; t < p2e; t += blockDim.x) {
-    sk[t] = KEY_MAX;
-    srank[t] = __int_as_float(0x7F800000);
-  }
+  for (int t = tid; t < p2e; t += blockDim.x) sk[t] = KEY_MAX;
   __syncthreads();
   const int rw4 = p.row_words >> 2;
   const float4* q4 = reinterpret_cast<const float4*>(qv);
 
-  // exact fp32 distance of every candidate: one warp per candidate, 128-bit loads
-  for (int s = 0; s < p.n_split; ++s) {
-    const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
-    const uint64_t* cb = p.cand + slot * (size_t)p.cap;
-    const int c = s_off[s + 1] - s_off[s];
-    for (int i = warp; i < c; i += 4) {
-      const uint32_t pos = (uint32_t)cb[i];
-      const size_t local = (size_t)(pos - p.pos_base);
-      const float4* x4 = reinterpret_cast<const float4*>(p.db + local * p.row_words);
-      float acc = 0.f;
-      for (int e = lane; e < rw4; e += 32) {
-        const float4 x = __ldg(x4 + e), y = q4[e];
-        if (p.mode == SCAN_L2) {
-          const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
-          acc = fmaf(d0, d0, acc);
-          acc = fmaf(d1, d1, acc);
-          acc = fmaf(d2, d2, acc);
-          acc = fmaf(d3, d3, acc);
-        } else {
-          acc = fmaf(x.x, y.x, acc);
-          acc = fmaf(x.y, y.y, acc);
-          acc = fmaf(x.z, y.z, acc);
-          acc = fmaf(x.w, y.w, acc);
-        }
-      }
-      acc = warp_sum_f(acc);
-      if (lane == 0) {
-        float dist, rank;
-        if (p.mode == SCAN_L2) {
-          dist = acc;                 // sum (x-y)^2, the reference's formula (distcomp_lp.cc:304-365)
-          rank = acc - qn2;           // pass 1 ranks by |x|^2 - 2 q.x
-        } else if (p.mode == SCAN_NEGDOT) {
-          dist = -acc;
-          rank = -acc;
-        } else {
-          const float nx = p.db_norm2[local];
-          const float eps = 2.0f * 1.17549435e-38f;
-          float nsp = 0.f;
-          if (!(nx < eps || qn2 < eps)) nsp = fmaxf(-1.f, fminf(1.f, acc / sqrtf(nx) / sqrtf(qn2)));
-          dist = fmaxf(0.f, 1.f - nsp);
-          rank = (nx < eps) ? 0.f : -acc * rsqrtf(nx);   // pass 1 ranks by -q.x / |x|
-        }
-        sk[s_off[s] + i] = make_key(f32_ordered(dist), pos);
-        srank[s_off[s] + i] = rank;
+  // exact fp32 distance of every live candidate: one warp per candidate, 128-bit loads
+  for (int i0 = warp; i0 < total; i0 += 4) {
+    const uint32_t pos = spos[i0];
+    const size_t local = (size_t)(pos - p.pos_base);
+    const float4* x4 = reinterpret_cast<const float4*>(p.db + local * p.row_words);
+    float acc = 0.f;
+    for (int e = lane; e < rw4; e += 32) {
+      const float4 x = __ldg(x4 + e), y = q4[e];
+      if (p.mode == SCAN_L2) {
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        acc = fmaf(d0, d0, acc);
+        acc = fmaf(d1, d1, acc);
+        acc = fmaf(d2, d2, acc);
+        acc = fmaf(d3, d3, acc);
+      } else {
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+        acc = fmaf(x.z, y.z, acc);
+        acc = fmaf(x.w, y.w, acc);
       }
     }
+    acc = warp_sum_f(acc);
+    float dist, rank;
+    if (p.mode == SCAN_L2) {
+      dist = acc;                 // sum (x-y)^2, the reference's formula (distcomp_lp.cc:304-365)
+      rank = acc - qn2;           // pass 1 ranks by |x|^2 - 2 q.x
+    } else if (p.mode == SCAN_NEGDOT) {
+      dist = -acc;
+      rank = -acc;
+    } else {
+      const float nx = p.db_norm2[local];
+      const float eps = 2.0f * 1.17549435e-38f;
+      float nsp = 0.f;
+      if (!(nx < eps || qn2 < eps)) nsp = fmaxf(-1.f, fminf(1.f, acc / sqrtf(nx) / sqrtf(qn2)));
+      dist = fmaxf(0.f, 1.f - nsp);
+      rank = (nx < eps) ? 0.f : -acc * rsqrtf(nx);   // pass 1 ranks by -q.x / |x|
+    }
+    __syncwarp();  // every lane has read spos[i0] before the slot is reused for the rank
+    if (lane == 0) {
+      sk[i0] = make_key(f32_ordered(dist), pos);
+      srank[i0] = rank;
+    }
   }
+  __syncthreads();
+  for (int t = total + tid; t < p2e; t += blockDim.x) srank[t] = __int_as_float(0x7F800000);
   __syncthreads();
 
   // sort (key, rank) ascending by key
@@ -1280,7 +1288,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   if (tid == 0) {
     // certificate: every non-candidate has approximate rank >= s_minthr, exact rank >= s_minthr - E
     int cert;
-    if (s_minthr == __int_as_float(0x7F800000)) {
+    if (minthr == __int_as_float(0x7F800000)) {
       cert = 1;  // nothing was ever dropped in any split: the candidates are the whole shard
     } else if (total < p.k) {
       cert = 0;
@@ -1291,7 +1299,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
       // worst exact rank among the k answers (ranks are not exactly monotone in the key for cosine)
       float worst = __int_as_float(0xFF800000);
       for (int e = 0; e < p.k; ++e) worst = fmaxf(worst, srank[e]);
-      cert = (worst + E + fabsf(worst) * 1e-6f < s_minthr) ? 1 : 0;
+      cert = (worst + E + fabsf(worst) * 1e-6f < minthr) ? 1 : 0;
     }
     p.out_cert[q] = cert;
   }
