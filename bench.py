@@ -283,7 +283,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u8" if u8 else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u8 (widened to tf32 operands, exact integer sums in f32)" if u8 else "f32",
+            "data": "synthetic",
             "config": {"workload": f"{w['name']}: {w['method']} {w['space']} {n}x{dim}, {nq} queries, k={k}",
                        "space": w["space"], "k": k, "rows_per_gpu": hi - lo,
                        "parallelism": f"row-sharded x{world}" + (" + NCCL all-gather + device k-way merge" if dist_on else ""),

@@ -88,7 +88,7 @@ Engine::~Engine() {
   for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
                     &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
                     &d_out_counts_, &d_bias_, &d_db_unit_, &d_flags_, &d_qa_, &d_cand_, &d_cand_cnt_, &d_cand_thr_,
-                    &d_tc_keys_, &d_cert_, &d_plan_, &d_gthr_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_})
+                    &d_tc_keys_, &d_cert_, &d_plan_, &d_gthr_, &d_u8tmp_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_})
     b->release();
   for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_}) b->release();
   for (auto& e : ev_)
@@ -320,7 +320,7 @@ const float* Engine::hnsw_host_rows() {
 
 int Engine::finalize_kind() const {
   if (method_ == METHOD_HNSW) return FIN_FLOAT;  // squared / cosine / negdot / (uint8: exact integers held in fp32)
-  if (is_u8_) return FIN_INT;
+  if (dev_u8_rows()) return FIN_INT;  // (widened uint8 rows carry fp32 keys: exact integers as floats)
   // l2 + seq_search reports the root; l2 + hnsw reports the squared distance
   if (space_ == SPACE_L2 && method_ == METHOD_SEQ) return FIN_SQRT;
   return FIN_FLOAT;
@@ -375,22 +375,38 @@ Status Engine::upload_data() {
   const size_t src_row = dev_u8 ? (size_t)dim_ : (size_t)dim_ * 4;
   const void* src = dev_u8 ? (const void*)h_u8_.data() : (const void*)h_f32_.data();
   if (method_ == METHOD_HNSW) src = hnsw_host_rows();  // float rows; cosine: unit-normalised (hnsw.cc:441-446)
-  s = check_cuda(cudaMemcpy2DAsync(d_db_.p, row_bytes, src, src_row, src_row, n_, cudaMemcpyHostToDevice, stream_),
-                 "H2D(data)");
-  if (!s.ok()) return s;
+  if (u8_widened()) {  // bytes up in 1 M-row chunks, widened to fp32 rows on the device
+    const size_t chunk = 1u << 20;
+    if (!(s = check_cuda(d_u8tmp_.ensure(std::min(n_, chunk) * (size_t)dim_), "cudaMalloc(u8 staging)")).ok()) return s;
+    for (size_t r0 = 0; r0 < n_; r0 += chunk) {
+      const size_t cnt = std::min(chunk, n_ - r0);
+      s = check_cuda(cudaMemcpyAsync(d_u8tmp_.p, h_u8_.data() + r0 * dim_, cnt * dim_, cudaMemcpyHostToDevice, stream_),
+                     "H2D(u8 data)");
+      if (!s.ok()) return s;
+      s = check_cuda(launch_widen_u8(d_u8tmp_.as<uint8_t>(), cnt, dim_, row_words_,
+                                     d_db_.as<float>() + r0 * (size_t)row_words_, stream_),
+                     "widen_u8");
+      if (!s.ok()) return s;
+      ++stats_.kernel_launches;
+    }
+  } else {
+    s = check_cuda(cudaMemcpy2DAsync(d_db_.p, row_bytes, src, src_row, src_row, n_, cudaMemcpyHostToDevice, stream_),
+                   "H2D(data)");
+    if (!s.ok()) return s;
+  }
   s = check_cuda(d_ids_.ensure(n_ * 4), "cudaMalloc(ids)");
   if (!s.ok()) return s;
   s = check_cuda(cudaMemcpyAsync(d_ids_.p, h_ids_.data(), n_ * 4, cudaMemcpyHostToDevice, stream_), "H2D(ids)");
   if (!s.ok()) return s;
-  if (method_ == METHOD_SEQ && (space_ == SPACE_COSINE || is_u8_)) {
+  if (method_ == METHOD_SEQ && (space_ == SPACE_COSINE || dev_u8)) {
     s = check_cuda(d_aux_.ensure(n_pad * 4), "cudaMalloc(aux)");
     if (!s.ok()) return s;
-    s = check_cuda(launch_row_aux(is_u8_, d_db_.p, (int)n_, row_words_, d_aux_.p, stream_), "row_aux");
+    s = check_cuda(launch_row_aux(dev_u8, d_db_.p, (int)n_, row_words_, d_aux_.p, stream_), "row_aux");
     if (!s.ok()) return s;
     ++stats_.kernel_launches;
   }
   x_max_ = 0.f;
-  if (!is_u8_ && method_ == METHOD_SEQ) {
+  if (!dev_u8 && method_ == METHOD_SEQ) {
     // operands of the tensor-core scan: bias (|x|^2 or 0, +inf on padding rows), the unit-norm copy
     // for cosine, max operand-row norm and the "is TF32-exact" flag (both feed the certificate)
     const int mode = space_ == SPACE_COSINE ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
@@ -499,6 +515,17 @@ Status Engine::stage_queries_device(const void* src, bool src_on_device, size_t 
     s = check_cuda(cudaMemsetAsync(d_q_.p, 0, d_q_.cap, stream), "memset(queries)");
     if (!s.ok()) return s;
   }
+  if (u8_widened()) {  // uint8 queries: bytes to a staging buffer, widened into the padded fp32 rows
+    s = check_cuda(d_u8tmp_.ensure(std::max<size_t>(nq * elem_count, d_u8tmp_.cap)), "cudaMalloc(u8 staging)");
+    if (!s.ok()) return s;
+    s = check_cuda(cudaMemcpyAsync(d_u8tmp_.p, src, nq * elem_count,
+                                   src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream),
+                   "copy(u8 queries)");
+    if (!s.ok()) return s;
+    ++stats_.kernel_launches;
+    return check_cuda(launch_widen_u8(d_u8tmp_.as<uint8_t>(), nq, (int)elem_count, row_words_, d_q_.as<float>(), stream),
+                      "widen_u8(queries)");
+  }
   const size_t src_row = dev_u8_rows() ? elem_count : elem_count * 4;
   return check_cuda(cudaMemcpy2DAsync(d_q_.p, row_bytes, src, src_row, src_row, nq,
                                       src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream),
@@ -545,7 +572,7 @@ Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d
   // ---- sequential search ----
   if (!(s = check_cuda(d_tc_keys_.ensure(nq * k * 8), "cudaMalloc(keys)")).ok()) return s;
   uint64_t* keys = d_tc_keys_.as<uint64_t>();
-  const bool use_tc = !is_u8_ && !force_exact_ && k <= (size_t)tc_max_k();
+  const bool use_tc = !dev_u8_rows() && !force_exact_ && k <= (size_t)tc_max_k();
   s = use_tc ? run_seq_tc(dq, nq, k, keys, stream) : run_seq_exact(dq, nq, k, keys, stream);
   if (!s.ok()) return s;
   // sorted (distance, position) keys -> external ids + float distances (extract_knn_results, nmslib_c.cpp:293-328)
@@ -576,20 +603,20 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
     case SPACE_L2SQR: mode = SCAN_L2; break;
     case SPACE_COSINE: mode = SCAN_COSINE; break;
     case SPACE_NEGDOT: mode = SCAN_NEGDOT; break;
-    default: mode = SCAN_SIFT; break;
+    default: mode = dev_u8_rows() ? SCAN_SIFT : SCAN_L2; break;  // widened uint8 rows: exact integers in fp32
   }
   const void* q_aux = nullptr;
   if (mode == SCAN_COSINE || mode == SCAN_SIFT) {
     s = check_cuda(d_qaux_.ensure(round_up(nq, bq) * 4), "cudaMalloc(qaux)");
     if (!s.ok()) return s;
-    s = check_cuda(launch_row_aux(is_u8_, dq, (int)nq, row_words_, d_qaux_.p, stream), "query_aux");
+    s = check_cuda(launch_row_aux(dev_u8_rows(), dq, (int)nq, row_words_, d_qaux_.p, stream), "query_aux");
     if (!s.ok()) return s;
     q_aux = d_qaux_.p;
     ++stats_.kernel_launches;
   }
   s = check_cuda(d_partial_.ensure(nq * (size_t)n_split * k * 8), "cudaMalloc(partial)");
   if (!s.ok()) return s;
-  const bool dominant = is_u8_ || force_exact_;
+  const bool dominant = force_exact_;
   if (dominant) scan_begin(stream);
   s = check_cuda(launch_scan_exact(mode, d_db_.p, dq, d_aux_.p, q_aux, (int)n_dev_, (int)nq, row_words_, (int)k,
                                    pos_base_, d_partial_.as<uint64_t>(), n_split, tiles_per_split, stream),

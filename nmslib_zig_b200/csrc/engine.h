@@ -124,7 +124,11 @@ class Engine {
   std::mutex& mutex() { return mu_; }
   size_t ef() const { return ef_; }
   int finalize_kind() const;
-  bool dev_u8_rows() const { return is_u8_ && method_ == METHOD_SEQ; }
+  // uint8 + seq_search normally runs on the tensor cores: rows widened to fp32 on upload (0..255 is TF32-exact
+  // and every partial sum stays an integer below 2^24, so the fp32 pipeline returns the int32 distances bit
+  // for bit).  NB200_FORCE_EXACT=1 keeps the byte rows and the dp4a scan (K2) instead.
+  bool dev_u8_rows() const { return is_u8_ && method_ == METHOD_SEQ && force_exact_; }
+  bool u8_widened() const { return is_u8_ && method_ == METHOD_SEQ && !force_exact_; }
 
  private:
   Status check_cuda(cudaError_t e, const char* what);
@@ -171,6 +175,7 @@ class Engine {
   void scan_end(cudaStream_t s);
   DevBuf d_db_, d_aux_, d_ids_;
   // tensor-core scan operands / scratch
+  DevBuf d_u8tmp_;                      // staging for uint8 rows / queries before they are widened
   DevBuf d_gthr_;                       // per-query threshold shared by the CTAs of one scan
   int tc_margin_ = 6;                   // survivors per compaction = k + margin (doubles when certificates fail)
   DevBuf d_plan_;                       // piece table of the TS scan (tc_ts_plan), cached per (nq, n, k)

@@ -35,6 +35,8 @@ cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int l
 int merge_topk_max_items();
 
 // gather rows idx[i] of a [*, row_words] array into dst[i] / scatter k-key rows back
+// uint8 rows [rows][dim] -> fp32 rows [rows][row_words] (padding columns are left untouched)
+cudaError_t launch_widen_u8(const uint8_t* src, size_t rows, int dim, int row_words, float* dst, cudaStream_t stream);
 cudaError_t launch_gather_rows(const uint32_t* src, const int* idx, int count, int row_words, uint32_t* dst,
                                cudaStream_t stream);
 cudaError_t launch_scatter_keys(const uint64_t* src, const int* idx, int count, int k, uint64_t* dst,

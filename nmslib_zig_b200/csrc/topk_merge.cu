@@ -4,6 +4,7 @@
 // It is used three ways: (1) to combine the per-split lists of one scan launch, (2) to
 // combine the per-GPU lists after the NVLink all-gather, (3) with lists == 1
 // as the plain "decode keys -> (id, float distance)" finaliser.
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -114,6 +115,27 @@ __global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, const int*
   dst[(size_t)idx[r] * k + e] = src[i];
 }
 }  // namespace
+
+namespace {
+__global__ void widen_u8_kernel(const uint8_t* __restrict__ src, size_t rows, int dim, int row_words,
+                                float* __restrict__ dst) {
+  const size_t total = rows * (size_t)(dim >> 2);  // one uchar4 per thread step
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / (dim >> 2), c = (i % (dim >> 2)) * 4;
+    const uchar4 v = *reinterpret_cast<const uchar4*>(src + r * dim + c);
+    *reinterpret_cast<float4*>(dst + r * row_words + c) = make_float4(v.x, v.y, v.z, v.w);
+  }
+}
+}  // namespace
+
+cudaError_t launch_widen_u8(const uint8_t* src, size_t rows, int dim, int row_words, float* dst, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  if (dim % 4 || row_words % 4) return cudaErrorInvalidValue;
+  const size_t total = rows * (size_t)(dim >> 2);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  widen_u8_kernel<<<blocks, 256, 0, stream>>>(src, rows, dim, row_words, dst);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_gather_rows(const uint32_t* src, const int* idx, int count, int row_words, uint32_t* dst,
                                cudaStream_t stream) {
