@@ -701,7 +701,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     stats_.kernel_launches += 3;
   }
   s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
-                                  mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)nq, row_words_, (int)k,
+                                  mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)n_dev_, (int)nq, row_words_,
+                                  (int)k,
                                   s_max, mode, pos_base_, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
                                   d_cand_thr_.as<float>(), x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(),
                                   stream),

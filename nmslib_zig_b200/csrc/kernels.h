@@ -84,8 +84,8 @@ cudaError_t launch_tc_prep_db_bf16(const float* db, int n, int n_pad, int row_wo
                                    void* out, void* nblock, void* ones, int* inexact_flag, cudaStream_t stream);
 cudaError_t launch_tc_prep_queries_bf16(const float* q, int q_pad, int row_words, int row_bf, float scale, void* out,
                                         int* inexact_flag, cudaStream_t stream);
-cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int nq, int row_words,
-                             int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
+cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int n, int nq,
+                             int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
                              uint64_t* out_keys, int* out_cert, cudaStream_t stream);
 

@@ -1168,25 +1168,30 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);          // [items_pow2] exact keys
   float* srank = reinterpret_cast<float*>(sk + items_pow2);       // [items_pow2] exact rank (certificate domain)
   uint32_t* spos = reinterpret_cast<uint32_t*>(srank);            // (the same words first hold the live positions)
-  __shared__ int s_cnt[65];
+  __shared__ int s_cnt[64];
   __shared__ int s_live;
-  __shared__ float s_minthr, s_qn2;
+  __shared__ float s_wmin[2], s_qn2;
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qb = q / TC_QB, row = q % TC_QB;
   const float* qv = p.queries + (size_t)q * p.row_words;
 
-  if (tid == 0) {
+  // one thread per candidate slot of this query (n_split <= 64): its key count and final threshold
+  if (tid < 64) {
     float mt = __int_as_float(0x7F800000);
-    for (int s = 0; s < p.n_split; ++s) {
-      const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
-      const int c = p.cand_cnt[slot];   // -1: slot unused (the host fills the array with 0xFF)
-      s_cnt[s] = max(c, 0);
-      if (c >= 0) mt = fminf(mt, p.cand_thr[slot]);  // +inf when the piece never dropped anything
+    int c = 0;
+    if (tid < p.n_split) {
+      const size_t slot = ((size_t)qb * p.n_split + tid) * TC_QB + row;
+      c = p.cand_cnt[slot];   // -1: slot unused (the host fills the array with 0xFF)
+      if (c >= 0) mt = p.cand_thr[slot];  // +inf when the piece never dropped anything
+      c = max(c, 0);
     }
-    s_minthr = mt;
-    s_live = 0;
+    s_cnt[tid] = c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(FULL, mt, o));
+    if (lane == 0) s_wmin[warp] = mt;
   }
-  if (warp == 1) {
+  if (tid == 0) s_live = 0;
+  if (warp == 2) {
     float s = 0.f;
     for (int c = lane; c < p.row_words; c += 32) s = fmaf(qv[c], qv[c], s);
     s = warp_sum_f(s);
@@ -1194,21 +1199,26 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   }
   __syncthreads();
   const float qn2 = s_qn2;
-  const float minthr = s_minthr;
+  const float minthr = fminf(s_wmin[0], s_wmin[1]);
   // Only candidates whose pass-1 rank lies below the smallest threshold any piece ended with can matter: if
   // the certificate below holds, every true neighbour has pass-1 rank < minthr, and if it does not
   // hold the query is re-run anyway.  With shared thresholds this is ~k' keys out of the few hundred appended.
-  for (int s = 0; s < p.n_split; ++s) {
+  // One warp per slot (round robin), so the slots' lists are read concurrently.
+  for (int s = warp; s < p.n_split; s += 4) {
     const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
     const uint64_t* cb = p.cand + slot * (size_t)p.cap;
     const int c = s_cnt[s];
-    for (int i = tid; i < c; i += blockDim.x) {
+    for (int i = lane; i < c; i += 32) {
       const uint64_t key = cb[i];
-      if (__uint_as_float((uint32_t)(key >> 32)) < minthr) spos[atomicAdd(&s_live, 1)] = (uint32_t)key;
+      if (__uint_as_float((uint32_t)(key >> 32)) < minthr) {
+        const int at = atomicAdd(&s_live, 1);
+        if (at < items_pow2) spos[at] = (uint32_t)key;
+      }
     }
   }
   __syncthreads();
-  const int total = s_live;
+  const bool overflow = s_live > items_pow2;  // more live keys than the sort buffer holds: not certifiable
+  const int total = min(s_live, items_pow2);
   int p2e = 32;
   while (p2e < total || p2e < p.k) p2e <<= 1;
   if (p2e > items_pow2) p2e = items_pow2;
@@ -1288,7 +1298,9 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   if (tid == 0) {
     // certificate: every non-candidate has approximate rank >= s_minthr, exact rank >= s_minthr - E
     int cert;
-    if (minthr == __int_as_float(0x7F800000)) {
+    if (overflow) {
+      cert = 0;
+    } else if (minthr == __int_as_float(0x7F800000)) {
       cert = 1;  // nothing was ever dropped in any split: the candidates are the whole shard
     } else if (total < p.k) {
       cert = 0;
@@ -1689,7 +1701,8 @@ void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int
   const int Bp = B - full;
   if (Bp > 0) {
     // (behind whole waves keep the lists per block few: every block's candidate buffers are sized by s_max)
-    int g = std::max(1, std::min(std::min(S / Bp, full > 0 ? 4 : max_pieces - 3), T));
+    // (and a piece should be long enough to pay for its start-up: >= 16 tiles unless the shard is tiny)
+    int g = std::max(1, std::min(std::min(S / Bp, full > 0 ? 4 : max_pieces - 3), std::max(1, T / 16)));
     int R = (g == S / Bp) ? S - g * Bp : 0;
     if (R > 0 && (Bp + R - 1) / R + 1 > TS_MAXP - 2) R = 0;   // too many blocks per left-over CTA
     long Wa = R > 0 ? ((long)T * Bp) / S : (T + g - 1) / g;
@@ -1833,8 +1846,8 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   return e;
 }
 
-cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int nq, int row_words,
-                             int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
+cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int n, int nq,
+                             int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
                              uint64_t* out_keys, int* out_cert, cudaStream_t stream) {
   if (nq <= 0) return cudaSuccess;
@@ -1863,7 +1876,9 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
   p.out_keys = out_keys;
   p.out_cert = out_cert;
   if (n_split > 64) return cudaErrorInvalidValue;
-  int items = n_split * p.cap;
+  // sort buffer: the live keys (pass-1 rank below the final threshold) are a few times k'; a query with more
+  // than this many is left uncertified and re-run exactly
+  int items = std::min(n_split * p.cap, std::max(std::max(2048, 4 * k), std::min(n, 8192)));  // (small shards: all rows)
   int p2 = 1;
   while (p2 < items || p2 < k) p2 <<= 1;
   const size_t smem = (size_t)p2 * 12 + 16;

@@ -76,6 +76,10 @@ def test_reference_own_test_vectors_through_seq_search():
     ("cosinesimil", 4_000, 33, 130, 25),
     ("negdotprod", 6_000, 768, 96, 100),     # config-5 shape: k = 100
     ("negdotprod", 2_000, 5, 40, 3),
+    ("l2", 9_000, 160, 40, 10),              # long rows, more live candidates than the re-rank buffer holds
+    ("l2", 40_000, 128, 2_600, 10),          # several query blocks x several pieces, shared thresholds
+    ("l2sqr", 70_000, 64, 700, 12),          # register top-16 list with margin 4; short rows
+    ("l2sqr", 30_000, 96, 500, 40),          # k > 12: append buffer + deferred compaction
 ])
 def test_float_spaces_match_oracle(space, n, dim, nq, k):
     if space == "negdotprod" and dim == 768:
