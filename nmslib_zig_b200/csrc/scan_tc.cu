@@ -1829,7 +1829,9 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
     const char* e2 = getenv("NB200_TC_NO_REG");
     return e2 && e2[0] == '1';
   }();
-  if (p.kprime <= TS_RK && p.cap == 256 && !no_reg) {
+  // register list (16 ranks): k <= 12 leaves the certificate a margin of >= 4 ranks; a margin raised by the
+  // engine (certificates failed on inexact data) selects the buffer path with its larger k'
+  if (k + 4 <= TS_RK && kprime <= k + 6 && p.cap == 256 && !no_reg) {
     p.kprime = TS_RK;  // the register list always holds 16
     p.slack = 8;
     NB_TS(8, true);
