@@ -292,6 +292,7 @@ def main():
             "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(q_np.nbytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
+            "uncertified_queries_per_step": (st1["fallback_queries"] - st0["fallback_queries"]) / args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf32_peak, "traffic": None, "kernel": "scan",
                          "kernel_ms": scan_ms,

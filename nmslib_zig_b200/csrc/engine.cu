@@ -483,7 +483,8 @@ Status Engine::upload_graph() {
     cudaMemcpyAsync(d_upper_.p, g.upper.data(), g.upper.size() * 4, cudaMemcpyHostToDevice, stream_);
   cudaMemcpyAsync(d_upper_off_.p, g.upper_off.data(), (size_t)g.total * 8, cudaMemcpyHostToDevice, stream_);
   // visited epoch arrays: one per resident warp slot (VisitedListPool, hnsw.h:598-639)
-  hnsw_slots_ = sm_count_ * 16;  // 16 warps per SM in flight
+  hnsw_slots_ = sm_count_ * 32;  // upper bound of warps per SM in flight (the launch uses one resident wave)
+  if (const char* e = getenv("NB200_HNSW_SLOTS")) hnsw_slots_ = sm_count_ * std::max(4, std::min(64, atoi(e)));
   const size_t vstride = round_up((size_t)g.total, 16);
   s = check_cuda(d_visited_.ensure(vstride * hnsw_slots_), "cudaMalloc(visited)");
   if (!s.ok()) return s;
@@ -491,9 +492,9 @@ Status Engine::upload_graph() {
   s = check_cuda(d_epoch_.ensure((size_t)hnsw_slots_ * 4), "cudaMalloc(epoch)");
   if (!s.ok()) return s;
   cudaMemsetAsync(d_epoch_.p, 0, (size_t)hnsw_slots_ * 4, stream_);
-  s = check_cuda(d_counters_.ensure(16), "cudaMalloc(counters)");
+  s = check_cuda(d_counters_.ensure(32), "cudaMalloc(counters)");
   if (!s.ok()) return s;
-  cudaMemsetAsync(d_counters_.p, 0, 16, stream_);
+  cudaMemsetAsync(d_counters_.p, 0, 32, stream_);
   s = check_cuda(cudaStreamSynchronize(stream_), "graph upload sync");
   if (!s.ok()) return s;
   graph_dirty_ = false;

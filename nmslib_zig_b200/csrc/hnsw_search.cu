@@ -19,6 +19,8 @@
 // loads (lane c reads float4 c, c+32, ...), four neighbours in flight per warp; the
 // level-0 adjacency row (maxM0 ints) is one coalesced 128-byte read.  The kernel is
 // bound by HBM random-gather bandwidth, not FLOPs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -58,47 +60,45 @@ __device__ __forceinline__ float fin_dist(float s) {
   else return -s;                                                               // NegativeDotProduct :70-73
 }
 
-// distances of up to four nodes (t[g] valid for g < cnt) to the query in shared memory
-template <int KIND>
-__device__ __forceinline__ void eval4(const float* __restrict__ vectors, int row_words,
-                                      const float4* __restrict__ q4, const int t[4], int cnt, int lane,
-                                      float out[4]) {
+// distances of up to G nodes (t[g] valid for g < cnt) to the query in shared memory: G independent row
+// gathers in flight per lane and loop iteration (the kernel waits on these loads ~80 % of the time, ncu)
+template <int KIND, int G>
+__device__ __forceinline__ void evalG(const float* __restrict__ vectors, int row_words,
+                                      const float4* __restrict__ q4, const int (&t)[G], int cnt, int lane,
+                                      float (&out)[G]) {
   const int rw4 = row_words >> 2;
-  const float4* x0 = reinterpret_cast<const float4*>(vectors + (size_t)t[0] * row_words);
-  const float4* x1 = reinterpret_cast<const float4*>(vectors + (size_t)t[cnt > 1 ? 1 : 0] * row_words);
-  const float4* x2 = reinterpret_cast<const float4*>(vectors + (size_t)t[cnt > 2 ? 2 : 0] * row_words);
-  const float4* x3 = reinterpret_cast<const float4*>(vectors + (size_t)t[cnt > 3 ? 3 : 0] * row_words);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  if (cnt == 4) {
+  const float4* x[G];
+  float s[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    x[g] = reinterpret_cast<const float4*>(vectors + (size_t)t[g < cnt ? g : 0] * row_words);
+    s[g] = 0.f;
+  }
+  if (cnt == G) {
 #pragma unroll 2
     for (int c = lane; c < rw4; c += 32) {
-      const float4 a0 = __ldg(x0 + c), a1 = __ldg(x1 + c), a2 = __ldg(x2 + c), a3 = __ldg(x3 + c);
+      float4 a[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) a[g] = __ldg(x[g] + c);
       const float4 q = q4[c];
-      acc4<KIND>(a0, q, s0);
-      acc4<KIND>(a1, q, s1);
-      acc4<KIND>(a2, q, s2);
-      acc4<KIND>(a3, q, s3);
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc4<KIND>(a[g], q, s[g]);
     }
   } else {
 #pragma unroll 2
     for (int c = lane; c < rw4; c += 32) {
       const float4 q = q4[c];
-      const float4 a0 = __ldg(x0 + c);
-      acc4<KIND>(a0, q, s0);
-      if (cnt > 1) {
-        const float4 a1 = __ldg(x1 + c);
-        acc4<KIND>(a1, q, s1);
-      }
-      if (cnt > 2) {
-        const float4 a2 = __ldg(x2 + c);
-        acc4<KIND>(a2, q, s2);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (g < cnt) {
+          const float4 a = __ldg(x[g] + c);
+          acc4<KIND>(a, q, s[g]);
+        }
       }
     }
   }
-  out[0] = fin_dist<KIND>(warp_sum(s0));
-  out[1] = fin_dist<KIND>(warp_sum(s1));
-  out[2] = fin_dist<KIND>(warp_sum(s2));
-  out[3] = fin_dist<KIND>(warp_sum(s3));
+#pragma unroll
+  for (int g = 0; g < G; ++g) out[g] = fin_dist<KIND>(warp_sum(s[g]));
 }
 
 // ascending bitonic sort of one 64-bit key per lane
@@ -117,8 +117,8 @@ __device__ __forceinline__ uint64_t warp_sort64(uint64_t v, int lane) {
   return v;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int KIND, int EVG, int MINB>  // EVG: neighbour vectors gathered at once per warp
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq, int k, int ef, int cap,
                    int cap_r, uint8_t* __restrict__ visited, size_t visited_stride,
                    int* __restrict__ slot_epoch, uint64_t* __restrict__ out_keys,
@@ -134,11 +134,15 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
   const float4* q4 = reinterpret_cast<const float4*>(qv);
 
   const int slot = blockIdx.x * WARPS + warp;
-  const int n_slots = gridDim.x * WARPS;
   uint8_t* vis = visited + (size_t)slot * visited_stride;
   unsigned long long n_eval = 0, n_exp = 0;
 
-  for (int qi = slot; qi < nq; qi += n_slots) {
+  // queries are handed out dynamically (they differ a lot in length): counters[2] is the next query index
+  for (;;) {
+    int qi = 0;
+    if (lane == 0) qi = (int)atomicAdd(&counters[2], 1ull);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= nq) break;
     // ---- visited epoch (VisitedList::reset, hnsw.h:575-582) ----
     int epoch = 0;
     if (lane == 0) epoch = slot_epoch[slot] + 1;
@@ -173,9 +177,9 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
     int cur_node = g.enterpoint;
     float cur_dist;
     {
-      int t[4] = {cur_node, 0, 0, 0};
-      float d[4];
-      eval4<KIND>(g.vectors, g.row_words, q4, t, 1, lane, d);
+      int t[EVG] = {cur_node};
+      float d[EVG];
+      evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, 1, lane, d);
       cur_dist = d[0];
       ++n_eval;
     }
@@ -190,9 +194,9 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
           unsigned mask = __ballot_sync(FULL, nb >= 0);
           float my_d = __int_as_float(0x7F800000);
           while (mask) {
-            int t[4], src[4], cnt = 0;
+            int t[EVG], src[EVG], cnt = 0;
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
+            for (int gq = 0; gq < EVG; ++gq) {
               src[gq] = 0;
               t[gq] = 0;
               if (mask) {
@@ -202,12 +206,12 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
               }
             }
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
-            float d[4];
-            eval4<KIND>(g.vectors, g.row_words, q4, t, cnt, lane, d);
+            for (int gq = 0; gq < EVG; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
+            float d[EVG];
+            evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, cnt, lane, d);
             n_eval += cnt;
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq)
+            for (int gq = 0; gq < EVG; ++gq)
               if (gq < cnt && lane == src[gq]) my_d = d[gq];
           }
           // sequential "if (d < curdist)" over j == first minimum over the list
@@ -258,9 +262,9 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
         unsigned mask = __ballot_sync(FULL, fresh);
         float my_d = __int_as_float(0x7F800000);
         while (mask) {
-          int t[4], src[4], cnt = 0;
+          int t[EVG], src[EVG], cnt = 0;
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
+          for (int gq = 0; gq < EVG; ++gq) {
             src[gq] = 0;
             t[gq] = 0;
             if (mask) {
@@ -270,12 +274,12 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
             }
           }
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
-          float d[4];
-          eval4<KIND>(g.vectors, g.row_words, q4, t, cnt, lane, d);
+          for (int gq = 0; gq < EVG; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
+          float d[EVG];
+          evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, cnt, lane, d);
           n_eval += cnt;
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq)
+          for (int gq = 0; gq < EVG; ++gq)
             if (gq < cnt && lane == src[gq]) my_d = d[gq];
         }
         const bool accept = fresh && (my_d < top_key || grow);
@@ -351,7 +355,7 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
     }
     __syncwarp();
   }
-  if (counters && lane == 0) {
+  if (lane == 0) {
     atomicAdd(&counters[0], n_eval);
     atomicAdd(&counters[1], n_exp);
   }
@@ -377,11 +381,33 @@ cudaError_t launch_hnsw_search(const HnswDeviceGraph& g, const float* queries, i
   if (blocks < 1) blocks = 1;
   const size_t vstride = round_up((size_t)g.n, 16);
   cudaError_t e;
-#define NB_HNSW(KIND)                                                                                    \
-  e = cudaFuncSetAttribute(hnsw_search_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-  if (e != cudaSuccess) return e;                                                                        \
-  hnsw_search_kernel<KIND><<<blocks, WARPS * 32, smem, stream>>>(g, queries, nq, k, ef, cap, cap_r, visited, \
-                                                                 vstride, slot_epoch, out_keys, counters);
+  static const int evg = [] {
+    const char* e2 = getenv("NB200_HNSW_G");
+    return e2 ? atoi(e2) : 4;
+  }();
+  static const int minb = [] {
+    const char* e2 = getenv("NB200_HNSW_MINB");
+    return e2 ? atoi(e2) : 6;
+  }();
+  cudaMemsetAsync(counters + 2, 0, 8, stream);  // next query index
+#define NB_HNSW3(KIND, G, MB)                                                                                   \
+  {                                                                                                             \
+    e = cudaFuncSetAttribute(hnsw_search_kernel<KIND, G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                             \
+    int occ = 0, dev = 0, sms = 0;                                                                              \
+    cudaGetDevice(&dev);                                                                                        \
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                                          \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hnsw_search_kernel<KIND, G, MB>, WARPS * 32, smem);      \
+    if (occ > 0 && blocks > occ * sms) blocks = occ * sms; /* one resident wave: a slot owns its visited array */ \
+    hnsw_search_kernel<KIND, G, MB><<<blocks, WARPS * 32, smem, stream>>>(g, queries, nq, k, ef, cap, cap_r,      \
+                                                                         visited, vstride, slot_epoch, out_keys, \
+                                                                         counters);                             \
+  }
+#define NB_HNSW(KIND)                                  \
+  if (evg == 8) NB_HNSW3(KIND, 8, 3)                   \
+  else if (evg == 2) NB_HNSW3(KIND, 2, 8)              \
+  else if (minb >= 8) NB_HNSW3(KIND, 4, 8)             \
+  else NB_HNSW3(KIND, 4, 6)
   switch (g.dist_kind) {
     case 0: NB_HNSW(0); break;
     case 1: NB_HNSW(1); break;
@@ -389,6 +415,7 @@ cudaError_t launch_hnsw_search(const HnswDeviceGraph& g, const float* queries, i
     default: return cudaErrorInvalidValue;
   }
 #undef NB_HNSW
+#undef NB_HNSW3
   return cudaGetLastError();
 }
 

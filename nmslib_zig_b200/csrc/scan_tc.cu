@@ -1834,6 +1834,7 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   if (k + 4 <= TS_RK && kprime <= k + 6 && p.cap == 256 && !no_reg) {
     p.kprime = TS_RK;  // the register list always holds 16
     p.slack = 8;
+    if (!getenv("NB200_TC_WARM")) p.warm_max = 0;  // exact thresholds make the cold start cheaper than the re-scan
     NB_TS(8, true);
   } else if (p.cap == 256) {
     NB_TS(8, false);
