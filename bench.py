@@ -280,6 +280,13 @@ def main():
         if world == 1 and not args.no_cpu:
             base = time_reference(w, min(args.cpu_sample, nq), 3, 1)
             cpu = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu capture of this workload (full-size, one GPU only)
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
+            if world == 1 and args.n is None and args.nq is None and w["name"] in tj:
+                traffic = tj[w["name"]]["bytes"]
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -294,7 +301,7 @@ def main():
             "gpu_launches": launches,
             "uncertified_queries_per_step": (st1["fallback_queries"] - st0["fallback_queries"]) / args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak, "traffic": None, "kernel": "scan",
+                         "frac": achieved / tf32_peak, "traffic": traffic, "kernel": "scan",
                          "kernel_ms": scan_ms,
                          "peak_src": f"{peaks['src']} bf16 burst {peaks['bf16_tflops']} TF/s / 2 (TF32 dense)"},
             "cpu_baseline": cpu, "clocks": clocks,

@@ -980,7 +980,20 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
           const uint32_t d1 = d0 + TS_BN;
           const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
           if (elect_one()) {
-            if (!(p.debug & 4)) {
+            if (p.debug & 256) {  // timing experiment: N = 128 MMAs on every other tile (same MAC count, garbage)
+              if (!(ti & 1)) {
+                constexpr uint32_t idesc2 = make_idesc_tf32(TC_BM, 128);
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                  const uint64_t db = make_smem_desc(sb + (uint32_t)kb * TS_CHUNK);
+                  const uint32_t a0 = tmem_base + (uint32_t)(kb * TC_KB);
+                  for (int j = 0; j < 4; ++j) umma_tf32_ts(d0, a0 + 8 * j, db + 2 * j, idesc2, (kb | j) != 0);
+                  for (int j = 0; j < 4; ++j) umma_tf32_ts(d0, a0 + 128u + 8 * j, db + 2 * j, idesc2, 1);
+                }
+                const uint64_t dbn = make_smem_desc(sb + (uint32_t)(p.n_kb - 1) * TS_CHUNK);
+                umma_tf32(d0, d_ones, dbn, idesc2, 1);
+                umma_tf32(d0, d_ones, dbn, idesc2, 1);
+              }
+            } else if (!(p.debug & 4)) {
               for (int kb = 0; kb < p.n_kb; ++kb) {
                 const uint64_t db = make_smem_desc(sb + (uint32_t)kb * TS_CHUNK);
                 const uint32_t a0 = tmem_base + (uint32_t)(kb * TC_KB);
