@@ -434,11 +434,15 @@ Status Engine::upload_data() {
     if (!s.ok()) return s;
     ++stats_.kernel_launches;
     unsigned bits = 0;
+    int inexact = 0;
     s = check_cuda(cudaMemcpyAsync(&bits, d_flags_.as<unsigned>() + 2, 4, cudaMemcpyDeviceToHost, stream_), "D2H(xmax)");
+    if (!s.ok()) return s;
+    s = check_cuda(cudaMemcpyAsync(&inexact, d_flags_.as<int>(), 4, cudaMemcpyDeviceToHost, stream_), "D2H(exact flag)");
     if (!s.ok()) return s;
     s = check_cuda(cudaStreamSynchronize(stream_), "upload sync");
     if (!s.ok()) return s;
     memcpy(&x_max_, &bits, 4);
+    db_inexact_ = inexact != 0;
   }
   s = check_cuda(cudaStreamSynchronize(stream_), "upload sync");
   if (!s.ok()) return s;
@@ -670,13 +674,16 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   if (!(s = check_cuda(cudaMemsetAsync(d_flags_.as<int>() + 1, 0, 4, stream), "memset(qflag)")).ok()) return s;
   const float scale = mode == SCAN_L2 ? -2.f : -1.f;
   const float* dbB = mode == SCAN_COSINE ? d_db_unit_.as<float>() : d_db_.as<float>();
+  if (!(s = check_cuda(d_gthr_.ensure(q_pad * 4), "cudaMalloc(gthr)")).ok()) return s;
+  if (!(s = check_cuda(cudaMemsetAsync(d_gthr_.p, 0xFF, q_pad * 4, stream), "memset(gthr)")).ok()) return s;
+  // survivors per compaction: k + margin.  Data that is not TF32-exact carries a pass-1 error of ~2^-9 |q||x|,
+  // which at k = 100 spans tens of ranks: start with half of k there (the margin doubles when certificates fail)
+  const int kprime_req = (int)k + (db_inexact_ ? std::max(tc_margin_, (int)k / 2) : tc_margin_);
   if (ts) {
     scan_begin(stream);
-    if (!(s = check_cuda(d_gthr_.ensure(q_pad * 4), "cudaMalloc(gthr)")).ok()) return s;
-    if (!(s = check_cuda(cudaMemsetAsync(d_gthr_.p, 0xFF, q_pad * 4, stream), "memset(gthr)")).ok()) return s;
     s = check_cuda(launch_tc_scan_ts(static_cast<const float*>(dq), dbB, n_pad,
                                      mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(),
-                                     (int)n_dev_, (int)nq, row_words_, (int)k, (int)k + tc_margin_, scale, pos_base_,
+                                     (int)n_dev_, (int)nq, row_words_, (int)k, kprime_req, scale, pos_base_,
                                      n_cta, s_max, d_plan_.as<int>(), d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
                                      d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), d_flags_.as<int>() + 1,
                                      stream),
@@ -694,8 +701,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad,
                                   mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(), (int)n_dev_,
                                   (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
-                                  /*bf16=*/0, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(),
-                                  stream),
+                                  /*bf16=*/0, kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                                  d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream),
                    "tc_scan");
     scan_end(stream);
     if (!s.ok()) return s;

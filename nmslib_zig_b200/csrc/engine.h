@@ -177,6 +177,7 @@ class Engine {
   // tensor-core scan operands / scratch
   DevBuf d_u8tmp_;                      // staging for uint8 rows / queries before they are widened
   DevBuf d_gthr_;                       // per-query threshold shared by the CTAs of one scan
+  bool db_inexact_ = false;             // the uploaded rows are not TF32-exact (read back once at upload)
   int tc_margin_ = 6;                   // survivors per compaction = k + margin (doubles when certificates fail)
   DevBuf d_plan_;                       // piece table of the TS scan (tc_ts_plan), cached per (nq, n, k)
   std::vector<int> h_plan_;

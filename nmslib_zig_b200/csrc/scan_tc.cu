@@ -279,6 +279,27 @@ __device__ __forceinline__ uint32_t compact_row(uint64_t* buf, int cnt, int kpri
   return t;
 }
 
+// A row's threshold after a compaction, shared with the other CTAs that scan other tile ranges for the same
+// query: any published cut has kprime points at or below it, so it bounds the query's kprime-th best rank over
+// the whole shard and every piece may prune with the smallest one seen so far.
+__device__ __forceinline__ float publish_thr(uint32_t* gthr, uint32_t t_ord) {
+  const uint32_t old = atomicMin(gthr, t_ord);
+  return f32_from_ordered(min(old, t_ord));
+}
+
+template <int KPL>
+__device__ __forceinline__ void compact_lane(int src, uint64_t* buf, int& cnt, float& thr, int kprime, int slack,
+                                             uint32_t* gthr, int lane) {
+  const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf, src);
+  const int c = __shfl_sync(FULL, cnt, src);
+  int kept;
+  const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, kprime, slack, lane, &kept);
+  if (lane == src) {
+    cnt = kept;
+    thr = publish_thr(gthr, t);
+  }
+}
+
 struct TcParams {
   int n, nq, n_kb;
   int n_tiles;             // 128-row tiles per query block (whole shard)
@@ -291,6 +312,8 @@ struct TcParams {
   int* cand_cnt;           // [q_blocks][s_max][256]   (zeroed by the host before the launch)
   float* cand_thr;         // [q_blocks][s_max][256]   final threshold (rank domain) of a piece that compacted
   int cap, kprime;
+  int slack, hwm;          // survivors of a compaction = kprime .. kprime + slack; deferred compaction above hwm keys
+  uint32_t* gthr;          // [q_pad] best threshold published per query (shared by all CTAs), 0xFF-filled
   int n_stage;             // shared-memory ring depth
   int a_resident;          // 1: both query tiles stay in shared memory while a piece is scanned (D <= 128)
   int use_nb;              // 1: an extra K=8 step adds |x|^2 (three TF32 pieces x 1.0) inside the MMA (l2)
@@ -530,6 +553,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = quarter * 32 + lane;       // row inside the 128-query half
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint64_t* buf = nullptr;
+    uint32_t* gthr = nullptr;
     int cnt = 0;
     float thr = 0.f;
     // KPL == 0 ("small k", k' = 16): the row's 16 best (rank, position) pairs live in registers as a
@@ -548,15 +572,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
-          const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf, src);
-          const int c = __shfl_sync(FULL, cnt, src);
-          int kept;
-          const uint32_t t = compact_row<(KPL > 0 ? KPL : 1)>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, p.kprime,
-                                                              16, lane, &kept);
-          if (lane == src) {
-            cnt = kept;
-            thr = f32_from_ordered(t);
-          }
+          compact_lane<(KPL > 0 ? KPL : 1)>(src, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
         }
       }
       float r[32];
@@ -632,6 +648,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const size_t unit = (size_t)qb * p.s_max + (p.aligned ? cta / p.q_blocks : cta - first_cta);
       const bool row_valid = qb * TC_QB + h * TC_BM + row < p.nq;
       buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
+      gthr = p.gthr + (qb * TC_QB + h * TC_BM + row);
       cnt = 0;
       thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
       if constexpr (SMALLK) {
@@ -682,6 +699,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           process(v2, pos_tile + 64, vtile - 64);
           process(v3, pos_tile + 96, vtile - 96);
         } else {
+          // what the other pieces of this query have found in the meantime (fminf ignores the NaN of "nothing yet")
+          if (((tile - t_begin) & 7) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
           tmem_ld32(tcol, v0);
 #pragma unroll 1
           for (int cp = 0; cp < TC_BN / 64; ++cp) {  // two chunks per iteration, next load in flight while computing
@@ -694,6 +713,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           tc_fence_before();
           mbar_arrive(&tempty_bar[b]);
+          // deferred compaction, one row per warp and tile (the TMEM buffer is already released)
+          const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);
+          if (pend) compact_lane<(KPL > 0 ? KPL : 1)>(__ffs(pend) - 1, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
         }
       }
       // publish this piece's per-row candidate count and final threshold
@@ -771,27 +793,6 @@ __device__ __forceinline__ int ts_warm_tiles(int warm_max, int len) {
 
 // one 32-column chunk of one row: fast path = min tree + one compare; survivors are appended to the row's
 // buffer, a full buffer is compacted warp-cooperatively first (see compact_row)
-// A row's threshold after a compaction, shared with the other CTAs that scan other tile ranges for the same
-// query: any published cut has kprime points at or below it, so it bounds the query's kprime-th best rank over
-// the whole shard and every piece may prune with the smallest one seen so far.
-__device__ __forceinline__ float publish_thr(uint32_t* gthr, uint32_t t_ord) {
-  const uint32_t old = atomicMin(gthr, t_ord);
-  return f32_from_ordered(min(old, t_ord));
-}
-
-template <int KPL>
-__device__ __forceinline__ void compact_lane(int src, uint64_t* buf, int& cnt, float& thr, int kprime, int slack,
-                                             uint32_t* gthr, int lane) {
-  const unsigned long long bp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)buf, src);
-  const int c = __shfl_sync(FULL, cnt, src);
-  int kept;
-  const uint32_t t = compact_row<KPL>(reinterpret_cast<uint64_t*>((uintptr_t)bp), c, kprime, slack, lane, &kept);
-  if (lane == src) {
-    cnt = kept;
-    thr = publish_thr(gthr, t);
-  }
-}
-
 constexpr int TS_RK = 16;  // register mode: ranks of a row's 16 best candidates, sorted, in registers
 
 // REG (kprime <= 16, i.e. k <= 10 with the default margin): the row's threshold is the exact 16th best rank seen,
@@ -1168,6 +1169,7 @@ struct RerankParams {
   const int* inexact_flags;       // [2]: nonzero if the database / this query batch is not TF32-exact
   uint64_t* out_keys;             // [nq][k]
   int* out_cert;                  // [nq] 1 = certified exact
+  int debug_cert;                 // NB200_TC_DEBUG_CERT: print the certificate inputs of the first queries
 };
 
 __device__ __forceinline__ float warp_sum_f(float v) {
@@ -1182,6 +1184,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   float* srank = reinterpret_cast<float*>(sk + items_pow2);       // [items_pow2] exact rank (certificate domain)
   uint32_t* spos = reinterpret_cast<uint32_t*>(srank);            // (the same words first hold the live positions)
   __shared__ int s_cnt[64];
+  __shared__ int s_red[4];
   __shared__ int s_live;
   __shared__ float s_wmin[2], s_qn2;
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1225,13 +1228,66 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
       const uint64_t key = cb[i];
       if (__uint_as_float((uint32_t)(key >> 32)) < minthr) {
         const int at = atomicAdd(&s_live, 1);
-        if (at < items_pow2) spos[at] = (uint32_t)key;
+        if (at < items_pow2) sk[at] = key;
       }
     }
   }
   __syncthreads();
   const bool overflow = s_live > items_pow2;  // more live keys than the sort buffer holds: not certifiable
-  const int total = min(s_live, items_pow2);
+  int total = min(s_live, items_pow2);
+  // pass-1 error bound of this query (same E as the certificate below)
+  const bool inexact_q = p.inexact_flags[0] != 0 || p.inexact_flags[1] != 0;
+  const float E_q = (inexact_q ? p.eps_inexact : p.eps_exact) * (p.mode == SCAN_L2 ? 2.f : 1.f) * sqrtf(qn2) * p.x_max + 1e-30f;
+  {
+    // Second filter.  Let a_k be the k-th smallest PASS-1 rank among the live keys.  The k keys at or below it
+    // have exact rank <= a_k + E, so the true k-th best exact rank is <= a_k + E and every true neighbour has
+    // pass-1 rank <= a_k + 2E: only those keys need the exact evaluation (k + a few instead of s_max * k').
+    uint32_t* sord = reinterpret_cast<uint32_t*>(srank);
+    for (int i = tid; i < total; i += blockDim.x) sord[i] = f32_ordered(__uint_as_float((uint32_t)(sk[i] >> 32)));
+    __syncthreads();
+    uint32_t cut = 0xFFFFFFFFu;
+    if (total > p.k) {
+      uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+      while (lo < hi) {  // smallest v with #(ord <= v) >= k
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+        for (int i = tid; i < total; i += blockDim.x) c += sord[i] <= mid ? 1 : 0;
+        c = __reduce_add_sync(FULL, c);
+        if (lane == 0) s_red[warp] = c;
+        __syncthreads();
+        c = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        __syncthreads();
+        if (c >= p.k) hi = mid; else lo = mid + 1;
+      }
+      const float a_k = f32_from_ordered(lo);
+      const float t2 = a_k + 2.f * E_q + fabsf(a_k) * 2e-6f;
+      if (t2 < minthr) cut = f32_ordered(t2);
+    }
+    // compact the positions of the keys at or below the cut (flags first, then an exclusive scan, then the moves:
+    // the destination aliases the array the flags are read from)
+    unsigned long long mask = 0ull;
+    int mine = 0;
+    for (int j = 0, i = tid; i < total; ++j, i += blockDim.x)
+      if (sord[i] <= cut) {
+        mask |= 1ull << j;
+        ++mine;
+      }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_red[warp] = incl;
+    __syncthreads();
+    int off = incl - mine;
+    for (int w = 0; w < warp; ++w) off += s_red[w];
+    const int kept = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    for (int j = 0, i = tid; i < total; ++j, i += blockDim.x)
+      if (mask >> j & 1ull) spos[off++] = (uint32_t)sk[i];
+    __syncthreads();
+    total = kept;
+  }
   int p2e = 32;
   while (p2e < total || p2e < p.k) p2e <<= 1;
   if (p2e > items_pow2) p2e = items_pow2;
@@ -1318,15 +1374,19 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
     } else if (total < p.k) {
       cert = 0;
     } else {
-      const bool inexact = p.inexact_flags[0] != 0 || p.inexact_flags[1] != 0;
-      const float a_norm = (p.mode == SCAN_L2 ? 2.f : 1.f) * sqrtf(qn2);
-      const float E = (inexact ? p.eps_inexact : p.eps_exact) * a_norm * p.x_max + 1e-30f;
+      const float E = E_q;
       // worst exact rank among the k answers (ranks are not exactly monotone in the key for cosine)
       float worst = __int_as_float(0xFF800000);
       for (int e = 0; e < p.k; ++e) worst = fmaxf(worst, srank[e]);
       cert = (worst + E + fabsf(worst) * 1e-6f < minthr) ? 1 : 0;
     }
     p.out_cert[q] = cert;
+    if (p.debug_cert && (q < 2 || (cert == 0 && q < 40))) {
+      float worst = __int_as_float(0xFF800000);
+      for (int e = 0; e < p.k && e < p2e; ++e) worst = fmaxf(worst, srank[e]);
+      printf("rerank q=%d cert=%d live=%d total=%d p2e=%d items=%d minthr=%g worst=%g qn2=%g n_split=%d cnt0=%d\n", q, cert,
+             s_live, total, p2e, items_pow2, minthr, worst, qn2, p.n_split, s_cnt[0]);
+    }
   }
 }
 
@@ -1537,7 +1597,7 @@ void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_p
   const long n_tiles = (n + bn - 1) / bn;
   const long total = q_blocks * n_tiles;
   // the re-rank sorts s_max * cap keys per query in shared memory: bound the pieces per query block
-  const long max_pieces = std::min<long>(64, std::max<long>(2, 16384 / cap));
+  const long max_pieces = std::min<long>(std::min<long>(64, std::max<long>(2, 16384 / cap)), std::max<long>(4, 3072 / kprime));
   if (q_blocks * 4 >= sm_count || q_blocks * n_tiles <= sm_count) {
     long best = 1;
     double best_eff = 0;
@@ -1609,8 +1669,8 @@ int tc_max_k() { return 256; }
 
 cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
                            const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_cta,
-                           int work_per_cta, int s_max, int aligned, int bf16, uint64_t* cand, int* cand_cnt,
-                           float* cand_thr, cudaStream_t stream) {
+                           int work_per_cta, int s_max, int aligned, int bf16, int kprime, uint64_t* cand,
+                           int* cand_cnt, float* cand_thr, uint32_t* gthr, cudaStream_t stream) {
   if (n <= 0 || nq <= 0) return cudaSuccess;
   // row_words counts ELEMENTS per operand row here: fp32 words, or bf16 halves when bf16 != 0
   const int kb_elems = bf16 ? 64 : TC_KB;
@@ -1642,7 +1702,18 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   p.cand = cand;
   p.cand_cnt = cand_cnt;
   p.cand_thr = cand_thr;
-  tc_candidate_shape(k, &p.kprime, &p.cap);
+  int kp_default;
+  tc_candidate_shape(k, &kp_default, &p.cap);
+  if (p.cap > 16) {
+    p.kprime = std::max(k + 1, std::min(kprime, kp_default));
+    p.slack = std::max(8, p.kprime / 4);
+    p.hwm = std::min(p.cap / 2, std::max(64, 2 * p.kprime));
+  } else {  // (opt-in register mode of this kernel)
+    p.kprime = kp_default;
+    p.slack = 16;
+    p.hwm = p.cap;
+  }
+  p.gthr = gthr;
   p.use_nb = use_nb ? 1 : 0;
   {
     const char* dbg = getenv("NB200_TC_DEBUG");
@@ -1699,7 +1770,9 @@ void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int
   const int B = (nq + TC_QB - 1) / TC_QB;
   const int T = (n + TS_BN - 1) / TS_BN;
   const int S = std::max(1, sm_count);
-  const int max_pieces = std::min(64, std::max(4, 16384 / cap));
+  // pieces per query block: bounded by the re-rank (64 lists) and by k' -- every piece ends with its own k' best
+  // below a threshold that is only as tight as the piece is long, and the re-rank sorts at most 8192 live keys
+  const int max_pieces = std::min(std::min(64, std::max(4, 16384 / cap)), std::max(4, 3072 / kprime));
   std::vector<std::vector<int4>> ctas;
   std::vector<int> slots(B, 0);
   auto add_piece = [&](std::vector<int4>& c, int qb, int t0, int t1) {
@@ -1891,6 +1964,7 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
   p.inexact_flags = inexact_flags;
   p.out_keys = out_keys;
   p.out_cert = out_cert;
+  p.debug_cert = getenv("NB200_TC_DEBUG_CERT") != nullptr;
   if (n_split > 64) return cudaErrorInvalidValue;
   // sort buffer: the live keys (pass-1 rank below the final threshold) are a few times k'; a query with more
   // than this many is left uncertified and re-run exactly
