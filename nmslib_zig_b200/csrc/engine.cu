@@ -96,6 +96,9 @@ Engine::~Engine() {
   for (auto& pr : scan_ev_)
     for (auto& e : pr)
       if (e) cudaEventDestroy(e);
+  for (auto& e : copy_ev_)
+    if (e) cudaEventDestroy(e);
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -807,12 +810,54 @@ Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_
     for (size_t i = 0; i < nq * elem_count; ++i) h_q_widen_[i] = (float)qs[i];
     queries = h_q_widen_.data();
   }
-  s = stage_queries_device(queries, false, nq, elem_count, stream_);
-  if (!s.ok()) return s;
-  cudaEventRecord(ev_[1], stream_);
-  s = run(d_q_.p, nq, k, d_out_ids_.as<int32_t>(), d_out_dists_.as<float>(), nullptr, d_out_counts_.as<int32_t>(),
-          stream_);
-  if (!s.ok()) return s;
+  // chunks of >= 16 K queries only: the search kernel wants a few queries per resident warp (3 552 of them),
+  // four chunks of a 10 K batch ran 17.8 ms against 11.5 ms in one launch (profiles/README.md)
+  const int n_chunks = (int)std::min<size_t>(kCopyChunks, nq / 16384);
+  if (method_ == METHOD_HNSW && n_chunks >= 2) {
+    // Graph search treats queries independently and its input is large (100 K x 960 floats = 384 MB): copy the
+    // batch in chunks on a second stream and search chunk i while chunk i + 1 is still on the bus.
+    const size_t bq = std::max(scan_exact_block_queries(), tc_block_queries());
+    const size_t row_bytes = (size_t)row_words_ * 4, src_row = elem_count * 4;
+    const size_t old_cap = d_q_.cap;
+    if (!(s = check_cuda(d_q_.ensure(round_up(nq, bq) * row_bytes), "cudaMalloc(queries)")).ok()) return s;
+    if (d_q_.cap != old_cap && !(s = check_cuda(cudaMemsetAsync(d_q_.p, 0, d_q_.cap, stream_), "memset(queries)")).ok())
+      return s;
+    if (!copy_stream_) {
+      if (!(s = check_cuda(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate")).ok()) return s;
+      for (auto& e : copy_ev_)
+        if (!(s = check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")).ok()) return s;
+    }
+    cudaEventRecord(copy_ev_[kCopyChunks], stream_);  // the buffer is ready (and the previous batch is done with it)
+    cudaStreamWaitEvent(copy_stream_, copy_ev_[kCopyChunks], 0);
+    const size_t chunk = round_up((nq + n_chunks - 1) / n_chunks, 64);
+    for (int c = 0; c < kCopyChunks; ++c) {
+      const size_t c0 = std::min(nq, (size_t)c * chunk), c1 = std::min(nq, c0 + chunk);
+      if (c1 > c0) {
+        s = check_cuda(cudaMemcpy2DAsync(d_q_.as<char>() + c0 * row_bytes, row_bytes,
+                                         static_cast<const char*>(queries) + c0 * src_row, src_row, src_row, c1 - c0,
+                                         cudaMemcpyHostToDevice, copy_stream_),
+                       "H2D(query chunk)");
+        if (!s.ok()) return s;
+      }
+      cudaEventRecord(copy_ev_[c], copy_stream_);
+    }
+    cudaEventRecord(ev_[1], stream_);
+    for (int c = 0; c < kCopyChunks; ++c) {
+      const size_t c0 = std::min(nq, (size_t)c * chunk), c1 = std::min(nq, c0 + chunk);
+      cudaStreamWaitEvent(stream_, copy_ev_[c], 0);
+      if (c1 <= c0) continue;
+      s = run(d_q_.as<char>() + c0 * row_bytes, c1 - c0, k, d_out_ids_.as<int32_t>() + c0 * k,
+              d_out_dists_.as<float>() + c0 * k, nullptr, d_out_counts_.as<int32_t>() + c0, stream_);
+      if (!s.ok()) return s;
+    }
+  } else {
+    s = stage_queries_device(queries, false, nq, elem_count, stream_);
+    if (!s.ok()) return s;
+    cudaEventRecord(ev_[1], stream_);
+    s = run(d_q_.p, nq, k, d_out_ids_.as<int32_t>(), d_out_dists_.as<float>(), nullptr, d_out_counts_.as<int32_t>(),
+            stream_);
+    if (!s.ok()) return s;
+  }
   cudaEventRecord(ev_[2], stream_);
   cudaMemcpyAsync(h_out_ids_.p, d_out_ids_.p, out_n * 4, cudaMemcpyDeviceToHost, stream_);
   cudaMemcpyAsync(h_out_dists_.p, d_out_dists_.p, out_n * 4, cudaMemcpyDeviceToHost, stream_);

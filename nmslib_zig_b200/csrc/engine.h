@@ -175,6 +175,9 @@ class Engine {
   void scan_end(cudaStream_t s);
   DevBuf d_db_, d_aux_, d_ids_;
   // tensor-core scan operands / scratch
+  static constexpr int kCopyChunks = 4;  // query chunks of a large HNSW batch (copy / search overlap)
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t copy_ev_[kCopyChunks + 1] = {};
   DevBuf d_u8tmp_;                      // staging for uint8 rows / queries before they are widened
   DevBuf d_gthr_;                       // per-query threshold shared by the CTAs of one scan
   bool db_inexact_ = false;             // the uploaded rows are not TF32-exact (read back once at upload)
