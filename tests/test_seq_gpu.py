@@ -234,3 +234,36 @@ def test_tensor_core_path_is_the_one_that_runs_and_certifies():
         assert st["fallback_queries"] <= 0.02 * len(q), f"{space}: {st['fallback_queries']} uncertified queries"
         assert st["scan_count"] >= 1 and st["last_scan_ms"] > 0
         idx.deinit()
+
+
+def test_uncertifiable_queries_are_rerun_exactly_and_the_margin_adapts():
+    """Rows that differ by less than the pass-1 error bound cannot be certified: those queries must come back
+    through the exact re-run (same answers as the oracle), and the engine must widen its candidate margin."""
+    rng = np.random.default_rng(11)
+    base = rng.random((1, 128), dtype=np.float32)
+    # 6000 near-duplicates of one point (differences ~1e-6 << the TF32 bound) + ordinary rows
+    dup = base + rng.normal(0, 1e-6, (6_000, 128)).astype(np.float32)
+    data = np.concatenate([dup, synth.uniform(14_000, 128, 1)]).astype(np.float32)
+    rng.shuffle(data, axis=0)
+    q = np.concatenate([base + rng.normal(0, 1e-6, (40, 128)).astype(np.float32), synth.uniform(300, 128, 2)])
+    idx = make_index("l2", data)
+    for rep in range(3):
+        r = idx.knnQueryBatch(q, 10)
+        oi, od, oc = O.seq_knn("l2", data, q, 10)
+        dist_of = lambda qi, i: O.pair_distance("l2", data[i], q[qi])
+        assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, dist_of=dist_of, what=f"near-duplicates rep {rep}")
+    st = idx.stats()
+    assert st["fallback_queries"] >= 40, "the near-duplicate queries cannot have been certified"
+    idx.deinit()
+
+
+def test_adversarial_order_every_row_is_a_new_best():
+    """Rows sorted by decreasing distance to the queries: every scanned value beats the running threshold
+    (worst case for the survivor path and its buffers).  Results must still be exact."""
+    q = np.zeros((70, 64), np.float32)
+    q[:, 0] = np.linspace(0, 1, 70)
+    n = 30_000
+    data = np.zeros((n, 64), np.float32)
+    data[:, 1] = np.linspace(500.0, 1.0, n)       # distance to every query decreases with the position
+    data[:, 2] = (np.arange(n) % 7).astype(np.float32)
+    check_against_oracle("l2sqr", data, q, 10, what="decreasing distances")
