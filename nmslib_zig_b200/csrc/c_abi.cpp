@@ -458,12 +458,22 @@ nmslib_error_t nmslib_range_query_get_size(nmslib_index_handle_t index, const vo
   *out_size = 128;  // ref :1046
   return NB_OK("Range query size estimated");
 }
-nmslib_error_t nmslib_range_query_fill(nmslib_index_handle_t index, const void* query, size_t, double,
-                                       nmslib_result_t* result, size_t) {
+nmslib_error_t nmslib_range_query_fill(nmslib_index_handle_t index, const void* query, size_t elem_count,
+                                       double radius, nmslib_result_t* result, size_t) {
   if (!index || !query || !result || result->capacity == 0)
-    return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid range fill inputs");
-  result->size = 0;
-  return NB_ERR(NMSLIB_ERROR_SPACE_INCOMPATIBLE, "Range query not supported by the B200 engine");
+    return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid range fill inputs");  // ref :1056-1060
+  if (!result->ids || !result->distances) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Result buffers invalid");
+  return guarded(
+      [&]() -> nmslib_error_t {
+        Engine* e = index->engine;
+        std::lock_guard<std::mutex> lock(e->mutex());
+        size_t found = 0;
+        Status s = e->range_host(query, elem_count, radius, result->capacity, result->ids, result->distances, &found);
+        result->size = s.ok() ? found : 0;
+        if (!s.ok()) return NB_STATUS(s);
+        return NB_OK("Range query filled successfully");
+      },
+      NMSLIB_ERROR_QUERY_EXECUTION_FAILED, "Range query failed");
 }
 nmslib_error_t nmslib_get_data_point_string(nmslib_index_handle_t index, size_t, const char** data, size_t* data_len,
                                             const nmslib_allocator_t* allocator) {

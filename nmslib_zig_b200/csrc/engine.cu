@@ -88,7 +88,7 @@ Engine::~Engine() {
   for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
                     &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
                     &d_out_counts_, &d_bias_, &d_db_unit_, &d_flags_, &d_qa_, &d_cand_, &d_cand_cnt_, &d_cand_thr_,
-                    &d_tc_keys_, &d_cert_, &d_plan_, &d_gthr_, &d_u8tmp_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_})
+                    &d_tc_keys_, &d_cert_, &d_plan_, &d_gthr_, &d_u8tmp_, &d_range_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_})
     b->release();
   for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_}) b->release();
   for (auto& e : ev_)
@@ -779,6 +779,53 @@ Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, s
   if (s.ok()) stats_.queries += nq;
   if (s.ok() && method_ == METHOD_SEQ) stats_.distance_evals += (uint64_t)nq * n_dev_;
   return s;
+}
+
+// SeqSearch::Search(RangeQuery*) (seqsearch.cc:108-141) through nmslib_range_query_fill (nmslib_c.cpp:1051-1153):
+// every object within the radius, in position order, truncated to the caller's capacity.
+Status Engine::range_host(const void* query, size_t elem_count, double radius, size_t capacity, int32_t* ids,
+                          float* dists, size_t* size) {
+  *size = 0;
+  if (!built_) return Status::Err(kErrBuild, "Index not built");
+  if (method_ != METHOD_SEQ)  // hnsw.cc: "Range search is not supported!" -> SPACE_INCOMPATIBLE (nmslib_c.cpp:1127-1137)
+    return Status::Err(kErrIncompat, "Range query not supported by method: Range search is not supported!");
+  Status s = prepare();
+  if (!s.ok()) return s;
+  if (n_dev_ == 0) return Status::OK();
+  if (elem_count != (size_t)dim_)
+    return Status::Err(kErrQuery, "query length " + std::to_string(elem_count) + " != index dimension " +
+                                      std::to_string(dim_));
+  if (dev_u8_rows()) return Status::Err(kErrIncompat, "range queries need the widened rows (unset NB200_FORCE_EXACT)");
+  const int cap = (int)std::min<size_t>(capacity, n_dev_);
+  s = stage_queries_device(query, false, 1, elem_count, stream_);
+  if (!s.ok()) return s;
+  const size_t tmp_bytes = round_up(n_dev_ * 4, 256), out_bytes = round_up((size_t)cap * 4, 256);
+  if (!(s = check_cuda(d_range_.ensure(tmp_bytes + 2 * out_bytes + 256), "cudaMalloc(range)")).ok()) return s;
+  float* d_tmp = d_range_.as<float>();
+  int32_t* d_ids = reinterpret_cast<int32_t*>(d_range_.as<char>() + tmp_bytes);
+  float* d_d = reinterpret_cast<float*>(d_range_.as<char>() + tmp_bytes + out_bytes);
+  int* d_cnt = reinterpret_cast<int*>(d_range_.as<char>() + tmp_bytes + 2 * out_bytes);
+  const int mode = space_ == SPACE_COSINE ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
+  // RangeQuery<int> compares with static_cast<int>(radius) (nmslib_c.cpp:1087-1088)
+  const float r = is_u8_ ? std::floor((float)radius) : (float)radius;
+  s = check_cuda(launch_range_scan(d_db_.as<float>(), d_q_.as<float>(), mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr,
+                                   d_ids_.as<int32_t>(), (int)n_dev_, row_words_, mode,
+                                   space_ == SPACE_L2 ? 1 : 0, r, cap, d_tmp, d_ids, d_d, d_cnt, stream_),
+                 "range_scan");
+  if (!s.ok()) return s;
+  stats_.kernel_launches += 2;
+  int found = 0;
+  cudaMemcpyAsync(&found, d_cnt, 4, cudaMemcpyDeviceToHost, stream_);
+  if (!(s = check_cuda(cudaStreamSynchronize(stream_), "range query")).ok()) return s;
+  if (found > 0) {
+    cudaMemcpyAsync(ids, d_ids, (size_t)found * 4, cudaMemcpyDeviceToHost, stream_);
+    cudaMemcpyAsync(dists, d_d, (size_t)found * 4, cudaMemcpyDeviceToHost, stream_);
+    if (!(s = check_cuda(cudaStreamSynchronize(stream_), "range query")).ok()) return s;
+  }
+  *size = (size_t)found;
+  stats_.queries += 1;
+  stats_.distance_evals += n_dev_;
+  return Status::OK();
 }
 
 Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_t k, const int32_t** ids,

@@ -115,6 +115,9 @@ class Engine {
   // host in / host out: ids/dists are [nq][k] staging arrays owned by the engine
   Status knn_host(const void* queries, size_t nq, size_t elem_count, size_t k, const int32_t** ids,
                   const float** dists, const int32_t** counts);
+  // range query of one object (seq_search only, like the reference): ids/dists are caller buffers of `capacity`
+  Status range_host(const void* query, size_t elem_count, double radius, size_t capacity, int32_t* ids, float* dists,
+                    size_t* size);
   // device in / device out
   Status knn_device(const void* d_queries, size_t nq, size_t elem_count, size_t k, int32_t* d_ids,
                     float* d_dists, uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream);
@@ -178,6 +181,7 @@ class Engine {
   static constexpr int kCopyChunks = 4;  // query chunks of a large HNSW batch (copy / search overlap)
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t copy_ev_[kCopyChunks + 1] = {};
+  DevBuf d_range_;                      // per-row distances of a range query + its outputs
   DevBuf d_u8tmp_;                      // staging for uint8 rows / queries before they are widened
   DevBuf d_gthr_;                       // per-query threshold shared by the CTAs of one scan
   bool db_inexact_ = false;             // the uploaded rows are not TF32-exact (read back once at upload)

@@ -89,6 +89,12 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
                              uint64_t* out_keys, int* out_cert, cudaStream_t stream);
 
+// ---- range_scan.cu (one query, every row within the radius, in position order) ----------
+// dist_tmp: [n] scratch; out_ids / out_dists: [capacity] device buffers; *out_count <= capacity
+cudaError_t launch_range_scan(const float* db, const float* query, const float* db_norm2, const int32_t* ext_ids, int n,
+                              int row_words, int mode, int take_sqrt, float radius, int capacity, float* dist_tmp,
+                              int32_t* out_ids, float* out_dists, int* out_count, cudaStream_t stream);
+
 // ---- hnsw_search.cu ------------------------------------------------------------------
 struct HnswDeviceGraph {
   const float* vectors;      // [n][row_words] (cosine: unit-norm rows, as the reference stores them)

@@ -380,16 +380,19 @@ class Index:
         sizes = tbl[:, 2].astype(np.int64)
         return BatchResult(ids, dists, sizes)
 
-    def rangeQuery(self, query, radius: float):
-        """lib.zig:933-974 -- outside the engine's path."""
+    def rangeQuery(self, query, radius: float, capacity: Optional[int] = None):
+        """lib.zig:933-974: size estimate (128, nmslib_c.cpp:1046), then fill.  Objects within the radius come
+        back in position order, truncated to the buffer (`capacity` overrides the estimate)."""
         L = lib()
-        q = np.ascontiguousarray(query, np.float32).reshape(-1)
+        if not self.built:
+            self.buildIndex(None, False)
+        q = np.ascontiguousarray(query, self._elem_dtype()).reshape(-1)
         need = C.c_size_t()
         _check(L.nmslib_range_query_get_size(self.handle, q.ctypes.data, q.size, radius, C.byref(need), 0))
-        ids = np.empty(need.value, np.int32)
-        dists = np.empty(need.value, np.float32)
-        res = Result(ids.ctypes.data_as(C.POINTER(C.c_int32)), dists.ctypes.data_as(C.POINTER(C.c_float)), 0,
-                     need.value)
+        cap = int(capacity) if capacity else need.value
+        ids = np.empty(cap, np.int32)
+        dists = np.empty(cap, np.float32)
+        res = Result(ids.ctypes.data_as(C.POINTER(C.c_int32)), dists.ctypes.data_as(C.POINTER(C.c_float)), 0, cap)
         _check(L.nmslib_range_query_fill(self.handle, q.ctypes.data, q.size, radius, C.byref(res), 0))
         return QueryResult(ids[: res.size], dists[: res.size])
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import nmslib_zig_b200 as nb
-from helpers import ATOL, ATOL_COSINE, assert_knn_matches
+from helpers import ATOL, ATOL_COSINE, RTOL, assert_knn_matches
 from nmslib_zig_b200 import synth
 from oracle import oracle as O
 
@@ -267,3 +267,46 @@ def test_adversarial_order_every_row_is_a_new_best():
     data[:, 1] = np.linspace(500.0, 1.0, n)       # distance to every query decreases with the position
     data[:, 2] = (np.arange(n) % 7).astype(np.float32)
     check_against_oracle("l2sqr", data, q, 10, what="decreasing distances")
+
+
+@pytest.mark.parametrize("space,dim", [("l2", 48), ("l2sqr", 128), ("cosinesimil", 33), ("negdotprod", 20),
+                                       ("l2sqr_sift", 128)])
+def test_range_query_matches_a_position_ordered_scan(space, dim):
+    """nmslib_range_query_fill (nmslib_c.cpp:1051-1153) over seq_search: every object with d <= radius, in
+    position order, truncated to the capacity; distances as IndexTimeDistance reports them."""
+    n = 6_000
+    if space == "l2sqr_sift":
+        data, q = synth.sift_like_u8(n, 7), synth.sift_like_u8(3, 8)
+    else:
+        data, q = synth.uniform(n, dim, 1) - 0.3, synth.uniform(3, dim, 2) - 0.3
+    ids = (np.arange(n, dtype=np.int32) * 3 + 7)
+    idx = make_index(space, data, ids)
+    oi, od, oc = O.seq_knn(space, data, q, n, ids)            # all objects, ascending distance
+    for qi in range(3):
+        d_sorted = od[qi]
+        ref_d = {int(i): float(d) for i, d in zip(oi[qi], od[qi])}
+        for want in (1, 57, 300, n // 2):
+            lo, hi = float(d_sorted[want - 1]), float(d_sorted[want])
+            # a radius strictly between two neighbouring distances (integer space: exactly on a value)
+            radius = lo if space == "l2sqr_sift" else (lo + hi) / 2
+            if radius < 0 or (space != "l2sqr_sift" and not hi > lo):
+                continue  # the ABI rejects negative radii (nmslib_c.cpp:1038); negdotprod has many
+            for cap in (200, 25):
+                r = idx.rangeQuery(q[qi], radius, capacity=cap)
+                inside = np.sort(oi[qi][d_sorted <= np.float32(radius)])     # ids grow with the position
+                assert np.array_equal(r.ids, inside[:cap]), f"{space} q{qi} radius {radius} cap {cap}"
+                got = np.array([ref_d[int(i)] for i in r.ids], np.float32)
+                assert np.allclose(r.distances, got, rtol=RTOL * 4, atol=ATOL_COSINE), f"{space}: distances differ"
+    idx.deinit()
+
+
+def test_range_query_errors_like_the_reference():
+    data = synth.uniform(500, 16, 1)
+    idx = make_index("l2", data)
+    with pytest.raises(nb.NmslibError) as e:
+        idx.rangeQuery(data[0], -1.0)
+    assert e.value.code == 2                      # INVALID_ARGUMENT, nmslib_c.cpp:1038-1042
+    with pytest.raises(nb.NmslibError) as e:
+        idx.rangeQuery(data[0, :8], 1.0)
+    assert e.value.code == 9                      # length mismatch -> QUERY_EXECUTION_FAILED
+    idx.deinit()
