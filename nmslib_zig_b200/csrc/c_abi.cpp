@@ -67,6 +67,9 @@ bool parse_space(const std::string& s, nb200::Space* out) {
   else if (s == "cosinesimil" || s == "cosine") *out = nb200::SPACE_COSINE;
   else if (s == "negdotprod") *out = nb200::SPACE_NEGDOT;
   else if (s == "l2sqr_sift") *out = nb200::SPACE_L2SQR_SIFT;
+  else if (s == "l1") *out = nb200::SPACE_L1;
+  else if (s == "linf") *out = nb200::SPACE_LINF;
+  else if (s == "angulardist") *out = nb200::SPACE_ANGULAR;
   else return false;
   return true;
 }
@@ -120,6 +123,9 @@ nmslib_error_t new_index(const std::string& space, const std::string& method, nm
   idx->method_served = true;
   if (method == "hnsw") m = nb200::METHOD_HNSW;
   else if (method != "seq_search" && method != "brute_force") idx->method_served = false;
+  // l1 / linf / angulardist are served by the exact scan only (the optimized HNSW index knows l2 / cosine / negdot)
+  if (m == nb200::METHOD_HNSW && (sp == nb200::SPACE_L1 || sp == nb200::SPACE_LINF || sp == nb200::SPACE_ANGULAR))
+    idx->method_served = false;
   idx->engine = new Engine(sp, m, u8, nb200::default_device());
   *out = idx;
   return NB_OK("Index created");

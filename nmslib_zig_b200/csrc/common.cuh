@@ -11,7 +11,10 @@ enum Space : int {
   SPACE_L2SQR = 1,     // sum (x-y)^2                     (distcomp_lp.cc:304-365)
   SPACE_COSINE = 2,    // max(0, 1 - clamp(x.y/|x|/|y|))  (distcomp_scalar.cc:84-168, 268-271)
   SPACE_NEGDOT = 3,    // -x.y                            (space_scalar.cc:60-68)
-  SPACE_L2SQR_SIFT = 4 // int32 n1 + n2 - 2 x.y           (distcomp_l2sqr_sift.cc:41-151)
+  SPACE_L2SQR_SIFT = 4,// int32 n1 + n2 - 2 x.y           (distcomp_l2sqr_sift.cc:41-151)
+  SPACE_L1 = 5,        // sum |x-y|                       (distcomp_lp.cc:190-251)      seq_search only
+  SPACE_LINF = 6,      // max |x-y|                       (distcomp_lp.cc:77-139)       seq_search only
+  SPACE_ANGULAR = 7    // acos(clamp(x.y/|x|/|y|))        (distcomp_scalar.cc:254-258)  seq_search only
 };
 
 // How the value stored in the upper half of a key becomes the reported float.

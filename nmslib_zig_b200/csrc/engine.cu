@@ -176,6 +176,13 @@ float Engine::host_distance(size_t a, size_t b) const {
   }
   const float *x = row_f32(a), *y = row_f32(b);
   float s = 0.f, n1 = 0.f, n2 = 0.f;
+  if (space_ == SPACE_L1 || space_ == SPACE_LINF) {
+    for (int i = 0; i < dim_; ++i) {
+      const float d = std::fabs(x[i] - y[i]);
+      s = space_ == SPACE_L1 ? s + d : std::max(s, d);
+    }
+    return s;
+  }
   for (int i = 0; i < dim_; ++i) {
     if (space_ == SPACE_L2 || space_ == SPACE_L2SQR) {
       float d = x[i] - y[i];
@@ -193,6 +200,7 @@ float Engine::host_distance(size_t a, size_t b) const {
     default: {
       const float eps = 2.0f * 1.17549435e-38f;
       float nsp = (n1 < eps || n2 < eps) ? 0.f : std::max(-1.f, std::min(1.f, s / std::sqrt(n1) / std::sqrt(n2)));
+      if (space_ == SPACE_ANGULAR) return std::acos(nsp);
       return std::max(0.f, 1.f - nsp);
     }
   }
@@ -401,7 +409,8 @@ Status Engine::upload_data() {
   if (!s.ok()) return s;
   s = check_cuda(cudaMemcpyAsync(d_ids_.p, h_ids_.data(), n_ * 4, cudaMemcpyHostToDevice, stream_), "H2D(ids)");
   if (!s.ok()) return s;
-  if (method_ == METHOD_SEQ && (space_ == SPACE_COSINE || dev_u8)) {
+  const bool cos_family = space_ == SPACE_COSINE || space_ == SPACE_ANGULAR;
+  if (method_ == METHOD_SEQ && (cos_family || dev_u8)) {
     s = check_cuda(d_aux_.ensure(n_pad * 4), "cudaMalloc(aux)");
     if (!s.ok()) return s;
     s = check_cuda(launch_row_aux(dev_u8, d_db_.p, (int)n_, row_words_, d_aux_.p, stream_), "row_aux");
@@ -409,10 +418,10 @@ Status Engine::upload_data() {
     ++stats_.kernel_launches;
   }
   x_max_ = 0.f;
-  if (!dev_u8 && method_ == METHOD_SEQ) {
+  if (!dev_u8 && method_ == METHOD_SEQ && space_ != SPACE_L1 && space_ != SPACE_LINF) {
     // operands of the tensor-core scan: bias (|x|^2 or 0, +inf on padding rows), the unit-norm copy
     // for cosine, max operand-row norm and the "is TF32-exact" flag (both feed the certificate)
-    const int mode = space_ == SPACE_COSINE ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
+    const int mode = cos_family ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
     if (!(s = check_cuda(d_bias_.ensure(n_pad * 4), "cudaMalloc(bias)")).ok()) return s;
     if (!(s = check_cuda(d_flags_.ensure(16), "cudaMalloc(flags)")).ok()) return s;
     if (!(s = check_cuda(cudaMemsetAsync(d_flags_.p, 0, 16, stream_), "memset(flags)")).ok()) return s;
@@ -580,7 +589,8 @@ Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d
   // ---- sequential search ----
   if (!(s = check_cuda(d_tc_keys_.ensure(nq * k * 8), "cudaMalloc(keys)")).ok()) return s;
   uint64_t* keys = d_tc_keys_.as<uint64_t>();
-  const bool use_tc = !dev_u8_rows() && !force_exact_ && k <= (size_t)tc_max_k();
+  const bool use_tc = !dev_u8_rows() && !force_exact_ && k <= (size_t)tc_max_k() && space_ != SPACE_L1 &&
+                      space_ != SPACE_LINF;  // (no dot-product form: exact CUDA-core scan)
   s = use_tc ? run_seq_tc(dq, nq, k, keys, stream) : run_seq_exact(dq, nq, k, keys, stream);
   if (!s.ok()) return s;
   // sorted (distance, position) keys -> external ids + float distances (extract_knn_results, nmslib_c.cpp:293-328)
@@ -611,10 +621,13 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
     case SPACE_L2SQR: mode = SCAN_L2; break;
     case SPACE_COSINE: mode = SCAN_COSINE; break;
     case SPACE_NEGDOT: mode = SCAN_NEGDOT; break;
+    case SPACE_L1: mode = SCAN_L1; break;
+    case SPACE_LINF: mode = SCAN_LINF; break;
+    case SPACE_ANGULAR: mode = SCAN_ANGULAR; break;
     default: mode = dev_u8_rows() ? SCAN_SIFT : SCAN_L2; break;  // widened uint8 rows: exact integers in fp32
   }
   const void* q_aux = nullptr;
-  if (mode == SCAN_COSINE || mode == SCAN_SIFT) {
+  if (mode == SCAN_COSINE || mode == SCAN_ANGULAR || mode == SCAN_SIFT) {
     s = check_cuda(d_qaux_.ensure(round_up(nq, bq) * 4), "cudaMalloc(qaux)");
     if (!s.ok()) return s;
     s = check_cuda(launch_row_aux(dev_u8_rows(), dq, (int)nq, row_words_, d_qaux_.p, stream), "query_aux");
@@ -624,7 +637,7 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
   }
   s = check_cuda(d_partial_.ensure(nq * (size_t)n_split * k * 8), "cudaMalloc(partial)");
   if (!s.ok()) return s;
-  const bool dominant = force_exact_;
+  const bool dominant = force_exact_ || space_ == SPACE_L1 || space_ == SPACE_LINF;
   if (dominant) scan_begin(stream);
   s = check_cuda(launch_scan_exact(mode, d_db_.p, dq, d_aux_.p, q_aux, (int)n_dev_, (int)nq, row_words_, (int)k,
                                    pos_base_, d_partial_.as<uint64_t>(), n_split, tiles_per_split, stream),
@@ -641,7 +654,9 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
 // Tensor-core candidates + exact fp32 re-rank + certificate; uncertified queries go to run_seq_exact.
 Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream) {
   Status s;
-  const int mode = space_ == SPACE_COSINE ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
+  const int mode = (space_ == SPACE_COSINE || space_ == SPACE_ANGULAR) ? SCAN_COSINE
+                   : space_ == SPACE_NEGDOT                             ? SCAN_NEGDOT
+                                                                        : SCAN_L2;
   const int qb = tc_block_queries(), bn = tc_block_points();
   const size_t q_pad = round_up(nq, qb);
   const size_t n_pad = round_up(n_dev_, bn);
@@ -713,8 +728,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   }
   s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
                                   mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)n_dev_, (int)nq, row_words_,
-                                  (int)k,
-                                  s_max, mode, pos_base_, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                                  (int)k, s_max, space_ == SPACE_ANGULAR ? SCAN_ANGULAR : mode, pos_base_,
+                                  d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
                                   d_cand_thr_.as<float>(), x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(),
                                   stream),
                  "tc_rerank");
@@ -805,10 +820,16 @@ Status Engine::range_host(const void* query, size_t elem_count, double radius, s
   int32_t* d_ids = reinterpret_cast<int32_t*>(d_range_.as<char>() + tmp_bytes);
   float* d_d = reinterpret_cast<float*>(d_range_.as<char>() + tmp_bytes + out_bytes);
   int* d_cnt = reinterpret_cast<int*>(d_range_.as<char>() + tmp_bytes + 2 * out_bytes);
-  const int mode = space_ == SPACE_COSINE ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
+  const int mode = space_ == SPACE_COSINE    ? SCAN_COSINE
+                   : space_ == SPACE_ANGULAR ? SCAN_ANGULAR
+                   : space_ == SPACE_NEGDOT  ? SCAN_NEGDOT
+                   : space_ == SPACE_L1      ? SCAN_L1
+                   : space_ == SPACE_LINF    ? SCAN_LINF
+                                             : SCAN_L2;
   // RangeQuery<int> compares with static_cast<int>(radius) (nmslib_c.cpp:1087-1088)
   const float r = is_u8_ ? std::floor((float)radius) : (float)radius;
-  s = check_cuda(launch_range_scan(d_db_.as<float>(), d_q_.as<float>(), mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr,
+  s = check_cuda(launch_range_scan(d_db_.as<float>(), d_q_.as<float>(),
+                                   (mode == SCAN_COSINE || mode == SCAN_ANGULAR) ? d_aux_.as<float>() : nullptr,
                                    d_ids_.as<int32_t>(), (int)n_dev_, row_words_, mode,
                                    space_ == SPACE_L2 ? 1 : 0, r, cap, d_tmp, d_ids, d_d, d_cnt, stream_),
                  "range_scan");

@@ -7,7 +7,8 @@
 namespace nb200 {
 
 // accumulate/epilogue flavours of the exact scan kernel
-enum ScanMode : int { SCAN_L2 = 0, SCAN_NEGDOT = 1, SCAN_COSINE = 2, SCAN_SIFT = 3 };
+enum ScanMode : int { SCAN_L2 = 0, SCAN_NEGDOT = 1, SCAN_COSINE = 2, SCAN_SIFT = 3, SCAN_L1 = 4, SCAN_LINF = 5,
+                      SCAN_ANGULAR = 6 };  // L1 / LINF: exact CUDA-core scan only; ANGULAR: cosine ranking, acos at the end
 
 // ---- scan_exact.cu -------------------------------------------------------------------
 // db: [n_pad][row_words] words (float32 or packed uint8), rows beyond n are zero padding up
@@ -87,7 +88,7 @@ cudaError_t launch_tc_prep_queries_bf16(const float* q, int q_pad, int row_words
 cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int n, int nq,
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
-                             uint64_t* out_keys, int* out_cert, cudaStream_t stream);
+                             uint64_t* out_keys, int* out_cert, cudaStream_t stream);  // mode may be SCAN_ANGULAR
 
 // ---- range_scan.cu (one query, every row within the radius, in position order) ----------
 // dist_tmp: [n] scratch; out_ids / out_dists: [capacity] device buffers; *out_count <= capacity

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) range_dist_kernel(const float* __restrict
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < n; row += warps) {
     const float4* x4 = reinterpret_cast<const float4*>(db + (size_t)row * row_words);
-    float acc = 0.f;
+    float acc = 0.f, nxs = 0.f, nqs = 0.f;
     for (int e = lane; e < rw4; e += 32) {
       const float4 x = __ldg(x4 + e), y = q4[e];
       if (mode == SCAN_L2) {
@@ -50,26 +50,50 @@ __global__ void __launch_bounds__(256) range_dist_kernel(const float* __restrict
         acc = fmaf(d1, d1, acc);
         acc = fmaf(d2, d2, acc);
         acc = fmaf(d3, d3, acc);
+      } else if (mode == SCAN_L1) {
+        acc += fabsf(x.x - y.x) + fabsf(x.y - y.y) + fabsf(x.z - y.z) + fabsf(x.w - y.w);
+      } else if (mode == SCAN_LINF) {
+        acc = fmaxf(acc, fmaxf(fmaxf(fabsf(x.x - y.x), fabsf(x.y - y.y)), fmaxf(fabsf(x.z - y.z), fabsf(x.w - y.w))));
       } else {
         acc = fmaf(x.x, y.x, acc);
         acc = fmaf(x.y, y.y, acc);
         acc = fmaf(x.z, y.z, acc);
         acc = fmaf(x.w, y.w, acc);
+        if (mode == SCAN_COSINE || mode == SCAN_ANGULAR) {  // one summation pattern for all three sums (see scan_tc.cu)
+          nxs = fmaf(x.x, x.x, nxs);
+          nxs = fmaf(x.y, x.y, nxs);
+          nxs = fmaf(x.z, x.z, nxs);
+          nxs = fmaf(x.w, x.w, nxs);
+          nqs = fmaf(y.x, y.x, nqs);
+          nqs = fmaf(y.y, y.y, nqs);
+          nqs = fmaf(y.z, y.z, nqs);
+          nqs = fmaf(y.w, y.w, nqs);
+        }
       }
     }
-    acc = warp_sum(acc);
+    if (mode == SCAN_LINF) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc = fmaxf(acc, __shfl_xor_sync(FULL, acc, o));
+    } else {
+      acc = warp_sum(acc);
+      if (mode == SCAN_COSINE || mode == SCAN_ANGULAR) {
+        nxs = warp_sum(nxs);
+        nqs = warp_sum(nqs);
+      }
+    }
     if (lane == 0) {
       float d;
       if (mode == SCAN_L2) {
         d = take_sqrt ? sqrtf(acc) : acc;
+      } else if (mode == SCAN_L1 || mode == SCAN_LINF) {
+        d = acc;
       } else if (mode == SCAN_NEGDOT) {
         d = -acc;
       } else {
-        const float nx = db_norm2[row];
         const float eps = 2.0f * 1.17549435e-38f;
         float nsp = 0.f;
-        if (!(nx < eps || qn2 < eps)) nsp = fmaxf(-1.f, fminf(1.f, acc / sqrtf(nx) / sqrtf(qn2)));
-        d = fmaxf(0.f, 1.f - nsp);
+        if (!(nxs < eps || nqs < eps)) nsp = fmaxf(-1.f, fminf(1.f, acc / sqrtf(nxs) / sqrtf(nqs)));
+        d = mode == SCAN_ANGULAR ? acosf(nsp) : fmaxf(0.f, 1.f - nsp);
       }
       dist[row] = d;
     }

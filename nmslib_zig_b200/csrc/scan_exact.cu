@@ -56,6 +56,16 @@ __device__ __forceinline__ void accum4(const uint4& a, const uint4& b, typename 
     acc = fmaf(d1, d1, acc);
     acc = fmaf(d2, d2, acc);
     acc = fmaf(d3, d3, acc);
+  } else if constexpr (MODE == SCAN_L1) {  // L1NormSIMD, distcomp_lp.cc:190-251
+    acc += fabsf(__uint_as_float(a.x) - __uint_as_float(b.x));
+    acc += fabsf(__uint_as_float(a.y) - __uint_as_float(b.y));
+    acc += fabsf(__uint_as_float(a.z) - __uint_as_float(b.z));
+    acc += fabsf(__uint_as_float(a.w) - __uint_as_float(b.w));
+  } else if constexpr (MODE == SCAN_LINF) {  // LInfNormSIMD, distcomp_lp.cc:77-139
+    acc = fmaxf(acc, fmaxf(fmaxf(fabsf(__uint_as_float(a.x) - __uint_as_float(b.x)),
+                                 fabsf(__uint_as_float(a.y) - __uint_as_float(b.y))),
+                           fmaxf(fabsf(__uint_as_float(a.z) - __uint_as_float(b.z)),
+                                 fabsf(__uint_as_float(a.w) - __uint_as_float(b.w)))));
   } else {
     acc = fmaf(__uint_as_float(a.x), __uint_as_float(b.x), acc);
     acc = fmaf(__uint_as_float(a.y), __uint_as_float(b.y), acc);
@@ -65,13 +75,16 @@ __device__ __forceinline__ void accum4(const uint4& a, const uint4& b, typename 
 }
 
 // exact cosine distance, data point left / query right (distcomp_scalar.cc:150-167, 268-271)
-__device__ __forceinline__ float cosine_exact(float dot, float n_x, float n_q) {
+__device__ __forceinline__ float nsp_exact(float dot, float n_x, float n_q) {
   const float eps = 2.0f * 1.17549435e-38f;
-  float nsp;
-  if (n_x < eps || n_q < eps) nsp = 0.f;
-  else nsp = fmaxf(-1.f, fminf(1.f, dot / sqrtf(n_x) / sqrtf(n_q)));
-  return fmaxf(0.f, 1.f - nsp);
+  if (n_x < eps || n_q < eps) return 0.f;
+  return fmaxf(-1.f, fminf(1.f, dot / sqrtf(n_x) / sqrtf(n_q)));
 }
+__device__ __forceinline__ float cosine_exact(float dot, float n_x, float n_q) {
+  return fmaxf(0.f, 1.f - nsp_exact(dot, n_x, n_q));
+}
+// AngularDistance, distcomp_scalar.cc:254-258
+__device__ __forceinline__ float angular_exact(float dot, float n_x, float n_q) { return acosf(nsp_exact(dot, n_x, n_q)); }
 
 template <int MODE>
 __global__ void __launch_bounds__(NT, (MODE == SCAN_SIFT) ? 1 : 1)
@@ -118,7 +131,7 @@ scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
     qaux_i[i] = 0;
     int q = q0 + ty + 16 * i;
     if (q < nq) {
-      if constexpr (MODE == SCAN_COSINE) qaux_f[i] = static_cast<const float*>(q_aux_v)[q];
+      if constexpr (MODE == SCAN_COSINE || MODE == SCAN_ANGULAR) qaux_f[i] = static_cast<const float*>(q_aux_v)[q];
       if constexpr (MODE == SCAN_SIFT) qaux_i[i] = static_cast<const int*>(q_aux_v)[q];
     }
   }
@@ -186,12 +199,12 @@ scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
       xaux_f[j] = 0.f;
       xaux_i[j] = 0;
       if (pvalid[j]) {
-        if constexpr (MODE == SCAN_COSINE) xaux_f[j] = static_cast<const float*>(db_aux_v)[p];
+        if constexpr (MODE == SCAN_COSINE || MODE == SCAN_ANGULAR) xaux_f[j] = static_cast<const float*>(db_aux_v)[p];
         if constexpr (MODE == SCAN_SIFT) xaux_i[j] = static_cast<const int*>(db_aux_v)[p];
       }
     }
     float rq[8], rx[8];
-    if constexpr (MODE == SCAN_COSINE) {
+    if constexpr (MODE == SCAN_COSINE || MODE == SCAN_ANGULAR) {
       const float eps = 2.0f * 1.17549435e-38f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) rq[i] = qaux_f[i] < eps ? 0.f : rsqrtf(qaux_f[i]);
@@ -209,7 +222,7 @@ scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
         if constexpr (MODE == SCAN_SIFT) {
           int r = xaux_i[j] + qaux_i[i] - 2 * acc[i][j];
           pass = r <= (int)tbits;
-        } else if constexpr (MODE == SCAN_L2) {
+        } else if constexpr (MODE == SCAN_L2 || MODE == SCAN_L1 || MODE == SCAN_LINF) {
           pass = acc[i][j] <= __uint_as_float(tbits);
         } else if constexpr (MODE == SCAN_NEGDOT) {
           pass = -acc[i][j] <= __uint_as_float(tbits);
@@ -232,8 +245,9 @@ scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
           if (pend & bit) {
             uint32_t ord;
             if constexpr (MODE == SCAN_SIFT) ord = i32_ordered(xaux_i[j] + qaux_i[i] - 2 * acc[i][j]);
-            else if constexpr (MODE == SCAN_L2) ord = f32_ordered(acc[i][j]);
+            else if constexpr (MODE == SCAN_L2 || MODE == SCAN_L1 || MODE == SCAN_LINF) ord = f32_ordered(acc[i][j]);
             else if constexpr (MODE == SCAN_NEGDOT) ord = f32_ordered(-acc[i][j]);
+            else if constexpr (MODE == SCAN_ANGULAR) ord = f32_ordered(angular_exact(acc[i][j], xaux_f[j], qaux_f[i]));
             else ord = f32_ordered(cosine_exact(acc[i][j], xaux_f[j], qaux_f[i]));
             const int row = ty + 16 * i;
             const uint64_t key = make_key(ord, pos_base + (uint32_t)(tile * BN + tx + 16 * j));
@@ -278,6 +292,8 @@ scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
             if constexpr (MODE == SCAN_SIFT) thr_fast[tid] = (uint32_t)i32_from_ordered(hi);
             else if constexpr (MODE == SCAN_COSINE)
               thr_fast[tid] = __float_as_uint(f32_from_ordered(hi) + 4e-6f);  // fast formula slack
+            else if constexpr (MODE == SCAN_ANGULAR)  // the fast filter works on 1 - nsp: 1 - cos(angle) + slack
+              thr_fast[tid] = __float_as_uint(1.f - cosf(f32_from_ordered(hi)) + 2e-5f);
             else thr_fast[tid] = __float_as_uint(f32_from_ordered(hi));
           }
         }
@@ -334,6 +350,9 @@ cudaError_t launch_scan_exact(int mode, const void* db, const void* queries, con
     case SCAN_NEGDOT: NB_LAUNCH(SCAN_NEGDOT); break;
     case SCAN_COSINE: NB_LAUNCH(SCAN_COSINE); break;
     case SCAN_SIFT: NB_LAUNCH(SCAN_SIFT); break;
+    case SCAN_L1: NB_LAUNCH(SCAN_L1); break;
+    case SCAN_LINF: NB_LAUNCH(SCAN_LINF); break;
+    case SCAN_ANGULAR: NB_LAUNCH(SCAN_ANGULAR); break;
     default: return cudaErrorInvalidValue;
   }
 #undef NB_LAUNCH

@@ -1301,7 +1301,8 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
     const uint32_t pos = spos[i0];
     const size_t local = (size_t)(pos - p.pos_base);
     const float4* x4 = reinterpret_cast<const float4*>(p.db + local * p.row_words);
-    float acc = 0.f;
+    float acc = 0.f, nxs = 0.f, nqs = 0.f;
+    const bool cosfam = p.mode == SCAN_COSINE || p.mode == SCAN_ANGULAR;
     for (int e = lane; e < rw4; e += 32) {
       const float4 x = __ldg(x4 + e), y = q4[e];
       if (p.mode == SCAN_L2) {
@@ -1315,9 +1316,25 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
         acc = fmaf(x.y, y.y, acc);
         acc = fmaf(x.z, y.z, acc);
         acc = fmaf(x.w, y.w, acc);
+        if (cosfam) {
+          // the three sums of NormScalarProductSIMD (distcomp_scalar.cc:84-168) with ONE summation pattern, as
+          // in the reference: identical vectors then give x.y == |x|^2 == |y|^2 bit for bit and nsp = 1 +- 1 ulp
+          nxs = fmaf(x.x, x.x, nxs);
+          nxs = fmaf(x.y, x.y, nxs);
+          nxs = fmaf(x.z, x.z, nxs);
+          nxs = fmaf(x.w, x.w, nxs);
+          nqs = fmaf(y.x, y.x, nqs);
+          nqs = fmaf(y.y, y.y, nqs);
+          nqs = fmaf(y.z, y.z, nqs);
+          nqs = fmaf(y.w, y.w, nqs);
+        }
       }
     }
     acc = warp_sum_f(acc);
+    if (cosfam) {
+      nxs = warp_sum_f(nxs);
+      nqs = warp_sum_f(nqs);
+    }
     float dist, rank;
     if (p.mode == SCAN_L2) {
       dist = acc;                 // sum (x-y)^2, the reference's formula (distcomp_lp.cc:304-365)
@@ -1326,11 +1343,11 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
       dist = -acc;
       rank = -acc;
     } else {
-      const float nx = p.db_norm2[local];
+      const float nx = nxs;
       const float eps = 2.0f * 1.17549435e-38f;
       float nsp = 0.f;
-      if (!(nx < eps || qn2 < eps)) nsp = fmaxf(-1.f, fminf(1.f, acc / sqrtf(nx) / sqrtf(qn2)));
-      dist = fmaxf(0.f, 1.f - nsp);
+      if (!(nx < eps || nqs < eps)) nsp = fmaxf(-1.f, fminf(1.f, acc / sqrtf(nx) / sqrtf(nqs)));
+      dist = p.mode == SCAN_ANGULAR ? acosf(nsp) : fmaxf(0.f, 1.f - nsp);  // AngularDistance, distcomp_scalar.cc:254-258
       rank = (nx < eps) ? 0.f : -acc * rsqrtf(nx);   // pass 1 ranks by -q.x / |x|
     }
     __syncwarp();  // every lane has read spos[i0] before the slot is reused for the rank

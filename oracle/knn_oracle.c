@@ -101,6 +101,32 @@ float orc_cosine(const float* a, const float* b, size_t d) {
   return v > 0.f ? v : 0.f;
 }
 
+/* AngularDistance, src/distcomp_scalar.cc:254-258: acos of the clamped normalised scalar product. */
+float orc_angular(const float* a, const float* b, size_t d) { return acosf(orc_norm_scalar_product(a, b, d)); }
+
+/* L1NormSIMD<float>, src/distcomp_lp.cc:190-251 (the SSE2 branch, which is what x86 builds run): four
+ * lanes of |a - b| (16-float unrolled, then 4-float groups), lanes summed t0+t1+t2+t3 into a double, the
+ * scalar tail accumulated in that double. */
+float orc_l1(const float* a, const float* b, size_t d) {
+  float lane[4] = {0.f, 0.f, 0.f, 0.f};
+  size_t d4 = (d / 4) * 4, i = 0;
+  for (; i < d4; i += 4)
+    for (int j = 0; j < 4; ++j) lane[j] = lane[j] + fabsf(a[i + j] - b[i + j]);
+  double res = lane[0] + lane[1] + lane[2] + lane[3];
+  for (; i < d; ++i) res += fabs(a[i] - b[i]);
+  return (float)res;
+}
+
+/* LInfNormSIMD, src/distcomp_lp.cc:77-139: max |a_i - b_i| (exact whatever the order). */
+float orc_linf(const float* a, const float* b, size_t d) {
+  float res = 0.f;
+  for (size_t i = 0; i < d; ++i) {
+    const float v = fabsf(a[i] - b[i]);
+    if (v > res) res = v;
+  }
+  return res;
+}
+
 /* SpaceNegativeScalarProduct::HiddenDistance, src/space/space_scalar.cc:60-68. */
 float orc_negdot(const float* a, const float* b, size_t d) { return -orc_dot(a, b, d); }
 
@@ -233,7 +259,7 @@ static size_t q_drain_ascending(knnq_t* q, qitem_t* out) {
 int orc_seq_knn(int space, const void* data, size_t n, size_t dim, const int32_t* ext_ids,
                 const void* queries, size_t nq, size_t k, int32_t* out_ids, float* out_dists,
                 int32_t* out_counts, int threads) {
-  if (space < ORC_SPACE_L2 || space > ORC_SPACE_L2SQR_SIFT || k == 0) return -1;
+  if (space < ORC_SPACE_L2 || space > ORC_SPACE_ANGULAR || k == 0) return -1;
   if (space == ORC_SPACE_L2SQR_SIFT && dim != 128) return -2; /* space_l2sqr_sift.cc:137 CHECK */
   if (threads < 1) threads = 1;
   int failed = 0;
@@ -264,6 +290,9 @@ int orc_seq_knn(int space, const void* data, size_t n, size_t dim, const int32_t
               case ORC_SPACE_L2: d = orc_l2(x, qv, dim); break;
               case ORC_SPACE_L2SQR: d = orc_l2sqr(x, qv, dim); break;
               case ORC_SPACE_COSINE: d = orc_cosine(x, qv, dim); break;
+              case ORC_SPACE_L1: d = orc_l1(x, qv, dim); break;
+              case ORC_SPACE_LINF: d = orc_linf(x, qv, dim); break;
+              case ORC_SPACE_ANGULAR: d = orc_angular(x, qv, dim); break;
               default: d = orc_negdot(x, qv, dim); break;
             }
             q_push(&q, (double)d, (int64_t)i);

@@ -14,7 +14,10 @@ enum {
   ORC_SPACE_L2SQR = 1,       /* sum (x-y)^2 (L2SqrSIMD directly)   distcomp_lp.cc:304-365 */
   ORC_SPACE_COSINE = 2,      /* max(0, 1 - nsp)                    distcomp_scalar.cc:268-271 */
   ORC_SPACE_NEGDOT = 3,      /* -dot                               space_scalar.cc:60-68 */
-  ORC_SPACE_L2SQR_SIFT = 4   /* n1 + n2 - 2 dot, int32             distcomp_l2sqr_sift.cc:41-50 */
+  ORC_SPACE_L2SQR_SIFT = 4,  /* n1 + n2 - 2 dot, int32             distcomp_l2sqr_sift.cc:41-50 */
+  ORC_SPACE_L1 = 5,          /* L1NormSIMD                         distcomp_lp.cc:190-251 */
+  ORC_SPACE_LINF = 6,        /* LInfNormSIMD                       distcomp_lp.cc:77-139 */
+  ORC_SPACE_ANGULAR = 7      /* acos(nsp)                          distcomp_scalar.cc:254-258 */
 };
 
 /* pairwise distances */
@@ -23,6 +26,9 @@ float orc_l2(const float* a, const float* b, size_t d);
 float orc_norm_scalar_product(const float* a, const float* b, size_t d);
 float orc_cosine(const float* a, const float* b, size_t d);
 float orc_negdot(const float* a, const float* b, size_t d);
+float orc_l1(const float* a, const float* b, size_t d);
+float orc_linf(const float* a, const float* b, size_t d);
+float orc_angular(const float* a, const float* b, size_t d);
 int32_t orc_l2sqr_sift(const uint8_t* a, const uint8_t* b); /* 128-D */
 /* HNSW optimized-index kernels (8-lane AVX summation order) */
 float orc_hnsw_l2sqr(const float* a, const float* b, size_t d);

@@ -16,7 +16,8 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-SPACE_CODES = {"l2": 0, "l2sqr": 1, "cosinesimil": 2, "cosine": 2, "negdotprod": 3, "l2sqr_sift": 4}
+SPACE_CODES = {"l2": 0, "l2sqr": 1, "cosinesimil": 2, "cosine": 2, "negdotprod": 3, "l2sqr_sift": 4, "l1": 5, "linf": 6,
+               "angulardist": 7}
 
 _i32p = C.POINTER(C.c_int32)
 _f32p = C.POINTER(C.c_float)
@@ -45,7 +46,7 @@ def port():
             build(ref=False)
         L = C.CDLL(str(so))
         for name in ("orc_l2sqr", "orc_l2", "orc_norm_scalar_product", "orc_cosine", "orc_negdot",
-                     "orc_hnsw_l2sqr", "orc_hnsw_dot"):
+                     "orc_hnsw_l2sqr", "orc_hnsw_dot", "orc_l1", "orc_linf", "orc_angular"):
             f = getattr(L, name)
             f.restype = C.c_float
             f.argtypes = [_f32p, _f32p, C.c_size_t]
@@ -77,7 +78,8 @@ def pair_distance(space: str, a: np.ndarray, b: np.ndarray):
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
     fn = {"l2": L.orc_l2, "l2sqr": L.orc_l2sqr, "cosinesimil": L.orc_cosine, "cosine": L.orc_cosine,
-          "negdotprod": L.orc_negdot, "hnsw_l2sqr": L.orc_hnsw_l2sqr, "hnsw_dot": L.orc_hnsw_dot}[space]
+          "negdotprod": L.orc_negdot, "hnsw_l2sqr": L.orc_hnsw_l2sqr, "hnsw_dot": L.orc_hnsw_dot,
+          "l1": L.orc_l1, "linf": L.orc_linf, "angulardist": L.orc_angular}[space]
     return float(fn(_ptr(a, _f32p), _ptr(b, _f32p), a.size))
 
 

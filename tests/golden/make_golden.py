@@ -133,8 +133,26 @@ def hnsw_case(name, space, data, queries, k, params, efs, ids=None):
     print(f"hnsw_{name}: n={n} dim={data.shape[1]} file={path.stat().st_size} B")
 
 
+def extra_spaces():
+    """l1 / linf / angulardist over seq_search; `make_golden.py extra` regenerates only these."""
+    seq_case("l1_u128", "l1", synth.uniform(600, 128, 51) - 0.3, synth.uniform(16, 128, 52) - 0.3, 10)
+    seq_case("l1_ragged19", "l1", synth.uniform(400, 19, 53), synth.uniform(12, 19, 54), 7, ids=np.arange(400) * 3 + 1)
+    seq_case("linf_u64", "linf", synth.uniform(500, 64, 55) - 0.5, synth.uniform(16, 64, 56) - 0.5, 10)
+    seq_case("angular_ragged37", "angulardist", synth.uniform(500, 37, 57) - 0.3, synth.uniform(16, 37, 58) - 0.3, 10)
+    d = synth.uniform(200, 16, 59)
+    d[50:60] = d[10:20]
+    d[100] = 0.0
+    q = np.concatenate([d[10:14], synth.uniform(4, 16, 60), np.zeros((1, 16), np.float32)])
+    seq_case("angular_zero", "angulardist", d, q, 10)
+    seq_case("l1_ties", "l1", d, q, 10)
+
+
 def main():
     assert O.ref_available(), "build oracle/_ref first: make -C oracle ref"
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        extra_spaces()
+        return
+    extra_spaces()
     rng = np.random.Generator(np.random.Philox(key=1234))
 
     # the reference's own pinned assertions (lib.zig:1292-1299): 3 unit vectors, ids 10/20/30

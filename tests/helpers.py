@@ -11,6 +11,16 @@ ATOL = 1e-6   # +1e-6 absolute for values near 0 (the reference's cos
 ATOL_COSINE = 1e-5
 
 
+def comparable(space: str, d):
+    """Distances in the domain where the tolerance applies.  angulardist = acos(nsp) is ill-conditioned near
+    0 (an nsp of 1 - 1 ulp is already 3.5e-4 rad, and the reference itself returns 0 or 3.5e-4 for identical
+    vectors depending on how S / sqrt(S) / sqrt(S) rounds), so it is compared as 1 - cos(d), i.e. as the cosine
+    distance it was computed from."""
+    if space == "angulardist":
+        return 1.0 - np.cos(np.asarray(d, np.float64))
+    return d
+
+
 def close(a, b, rtol=RTOL, atol=ATOL):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import nmslib_zig_b200 as nb
-from helpers import ATOL, ATOL_COSINE, RTOL, assert_knn_matches
+from helpers import ATOL, ATOL_COSINE, RTOL, assert_knn_matches, comparable
 from nmslib_zig_b200 import synth
 from oracle import oracle as O
 
@@ -32,9 +32,10 @@ def check_against_oracle(space, data, queries, k, ids=None, what=""):
     oi, od, oc = O.seq_knn(space, data, queries, k, ids)
     ids_arr = np.arange(len(data)) if ids is None else np.asarray(ids)
     pos_of = {int(v): i for i, v in enumerate(ids_arr)}
-    dist_of = lambda q, i: O.pair_distance(space, data[pos_of[i]], queries[q])
-    assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, exact=(space == "l2sqr_sift"), dist_of=dist_of,
-                       what=what or space, atol=ATOL_COSINE if space.startswith("cos") else ATOL)
+    dist_of = lambda q, i: comparable(space, O.pair_distance(space, data[pos_of[i]], queries[q]))
+    assert_knn_matches(r.ids, comparable(space, r.distances), r.sizes, oi, comparable(space, od), oc,
+                       exact=(space == "l2sqr_sift"), dist_of=dist_of,
+                       what=what or space, atol=ATOL_COSINE if space.startswith(("cos", "angular")) else ATOL)
     idx.deinit()
     return r
 
@@ -49,10 +50,10 @@ def test_matches_reference_golden(case):
     if space == "l2sqr":  # golden distances come from the reference's l2
         ref_d = (ref_d.astype(np.float64) ** 2).astype(np.float32)
     pos_of = {int(v): i for i, v in enumerate(g["ids"])}
-    dist_of = lambda q, i: O.pair_distance(space, g["data"][pos_of[i]], g["queries"][q])
-    assert_knn_matches(r.ids, r.distances, r.sizes, g["ref_ids"], ref_d, g["ref_counts"],
-                       exact=(space == "l2sqr_sift"), dist_of=dist_of, what=case,
-                       atol=ATOL_COSINE if space.startswith("cos") else ATOL)
+    dist_of = lambda q, i: comparable(space, O.pair_distance(space, g["data"][pos_of[i]], g["queries"][q]))
+    assert_knn_matches(r.ids, comparable(space, r.distances), r.sizes, g["ref_ids"], comparable(space, ref_d),
+                       g["ref_counts"], exact=(space == "l2sqr_sift"), dist_of=dist_of, what=case,
+                       atol=ATOL_COSINE if space.startswith(("cos", "angular")) else ATOL)
     # the single-query entry (lib.zig knnQuery -> get_size + fill) is a batch of one
     one = idx.knnQuery(g["queries"][0], k)
     assert np.array_equal(one.ids, r.ids[0, : r.sizes[0]]) and np.array_equal(one.distances, r.distances[0, : r.sizes[0]])
@@ -80,6 +81,11 @@ def test_reference_own_test_vectors_through_seq_search():
     ("l2", 40_000, 128, 2_600, 10),          # several query blocks x several pieces, shared thresholds
     ("l2sqr", 70_000, 64, 700, 12),          # register top-16 list with margin 4; short rows
     ("l2sqr", 30_000, 96, 500, 40),          # k > 12: append buffer + deferred compaction
+    ("l1", 9_000, 128, 200, 10),             # exact CUDA-core scan (no dot-product form)
+    ("l1", 2_000, 19, 50, 7),
+    ("linf", 9_000, 64, 200, 10),
+    ("angulardist", 20_000, 128, 300, 10),   # cosine ranking on the tensor cores, acos in the re-rank
+    ("angulardist", 3_000, 200, 64, 25),
 ])
 def test_float_spaces_match_oracle(space, n, dim, nq, k):
     if space == "negdotprod" and dim == 768:
@@ -125,7 +131,7 @@ def test_duplicates_zero_rows_and_tie_order():
         r = idx.knnQueryBatch(q, 8)
         oi, od, oc = O.seq_knn(space, d, q, 8)
         assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, what=f"ties/{space}",
-                           atol=ATOL_COSINE if space.startswith("cos") else ATOL)
+                           atol=ATOL_COSINE if space.startswith(("cos", "angular")) else ATOL)
         if space in ("l2", "l2sqr"):
             assert np.array_equal(r.ids[:10, 0], np.arange(10, 20))          # the earlier duplicate wins
             assert np.array_equal(r.ids[:10, 1], np.arange(500, 510))
@@ -270,7 +276,7 @@ def test_adversarial_order_every_row_is_a_new_best():
 
 
 @pytest.mark.parametrize("space,dim", [("l2", 48), ("l2sqr", 128), ("cosinesimil", 33), ("negdotprod", 20),
-                                       ("l2sqr_sift", 128)])
+                                       ("l2sqr_sift", 128), ("l1", 40), ("linf", 24), ("angulardist", 33)])
 def test_range_query_matches_a_position_ordered_scan(space, dim):
     """nmslib_range_query_fill (nmslib_c.cpp:1051-1153) over seq_search: every object with d <= radius, in
     position order, truncated to the capacity; distances as IndexTimeDistance reports them."""
@@ -296,7 +302,8 @@ def test_range_query_matches_a_position_ordered_scan(space, dim):
                 inside = np.sort(oi[qi][d_sorted <= np.float32(radius)])     # ids grow with the position
                 assert np.array_equal(r.ids, inside[:cap]), f"{space} q{qi} radius {radius} cap {cap}"
                 got = np.array([ref_d[int(i)] for i in r.ids], np.float32)
-                assert np.allclose(r.distances, got, rtol=RTOL * 4, atol=ATOL_COSINE), f"{space}: distances differ"
+                assert np.allclose(comparable(space, r.distances), comparable(space, got), rtol=RTOL * 4,
+                                   atol=ATOL_COSINE), f"{space}: distances differ"
     idx.deinit()
 
 
