@@ -719,7 +719,7 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad,
                                   mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(), (int)n_dev_,
                                   (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
-                                  /*bf16=*/0, kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                                  kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
                                   d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream),
                    "tc_scan");
     scan_end(stream);

@@ -72,19 +72,12 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
                               float* cand_thr, uint32_t* gthr, int* inexact_flag, cudaStream_t stream);
 cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, float scale, int* inexact_flag,
                                    cudaStream_t stream);
-// qa: prepared queries [q_pad][row_words]; dbB: B operand rows [n_pad][row_words] (row_words = elements per
-// operand row: fp32 words, or bf16 halves when bf16 != 0);
+// qa: prepared queries [q_pad][row_words]; dbB: B operand rows [n_pad][row_words];
 // cand: [q_blocks][s_max][256][cap] keys, cand_cnt (zeroed by the caller) / cand_thr: [q_blocks][s_max][256]
 cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
                            const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_cta,
-                           int work_per_cta, int s_max, int aligned, int bf16, int kprime, uint64_t* cand,
-                           int* cand_cnt, float* cand_thr, uint32_t* gthr, cudaStream_t stream);
-// BF16 operand copies for data that is BF16-exact (e.g. SIFT-shaped small integers): row_bf = elements per
-// bf16 row (multiple of 64); nblock / ones as above but [.][64] bf16; the flag is set if any element is inexact
-cudaError_t launch_tc_prep_db_bf16(const float* db, int n, int n_pad, int row_words, int row_bf, int with_norm,
-                                   void* out, void* nblock, void* ones, int* inexact_flag, cudaStream_t stream);
-cudaError_t launch_tc_prep_queries_bf16(const float* q, int q_pad, int row_words, int row_bf, float scale, void* out,
-                                        int* inexact_flag, cudaStream_t stream);
+                           int work_per_cta, int s_max, int aligned, int kprime, uint64_t* cand, int* cand_cnt,
+                           float* cand_thr, uint32_t* gthr, cudaStream_t stream);
 cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int n, int nq,
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,

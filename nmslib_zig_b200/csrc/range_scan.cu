@@ -22,20 +22,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// dist[i] = distance(row i, query); mode SCAN_L2 (sqrt when take_sqrt), SCAN_COSINE, SCAN_NEGDOT.
+// dist[i] = distance(row i, query); mode SCAN_L2 (sqrt when take_sqrt), SCAN_L1, SCAN_LINF, SCAN_COSINE,
+// SCAN_ANGULAR, SCAN_NEGDOT.  (db_norm2 is unused: the cosine family recomputes all three sums per pair.)
 __global__ void __launch_bounds__(256) range_dist_kernel(const float* __restrict__ db, const float* __restrict__ q,
                                                          const float* __restrict__ db_norm2, int n, int row_words,
                                                          int mode, int take_sqrt, float* __restrict__ dist) {
-  __shared__ float s_qn2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp == 0) {
-    float s = 0.f;
-    for (int c = lane; c < row_words; c += 32) s = fmaf(q[c], q[c], s);
-    s = warp_sum(s);
-    if (lane == 0) s_qn2 = s;
-  }
-  __syncthreads();
-  const float qn2 = s_qn2;
   const int rw4 = row_words >> 2;
   const float4* q4 = reinterpret_cast<const float4*>(q);
   const int warps = (gridDim.x * blockDim.x) >> 5;

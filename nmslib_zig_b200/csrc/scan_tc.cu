@@ -17,18 +17,17 @@
 //        the TF32 error of pass 1.  If the exact k-th rank + E < thr the answer is provably the
 //        exact top-k; otherwise the query is re-run by the exact scan (scan_exact.cu).
 //
-// Kernel anatomy (one CTA per SM, 320 threads, no cluster):
-//   warp 0   TMA producer: cp.async.bulk.tensor (128B-swizzled 128-row x 32-float boxes) into a
-//            ring of shared-memory stages, mbarrier complete_tx
-//   warp 1   TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer.  A CTA owns 256
-//            queries = two M=128 operand tiles, so every 128-row database tile that reaches
-//            shared memory feeds two MMAs (halves L2->SM traffic per flop); four 128-column fp32
-//            accumulators = all 512 TMEM columns, double buffered against the epilogue
-//   warps 2-9 epilogue (two per scheduler, one query row per thread): tcgen05.ld 32 columns at a
-//            time with the next load in flight, + bias, 3-input min tree, one compare per 32
-//            values; survivors (rare once the threshold is warm) are appended to the row's
-//            candidate buffer; a full buffer is compacted warp-cooperatively (ballot-based
-//            radix select of the k'-th smallest rank).
+// Two kernels share the TMA / mbarrier / tcgen05 plumbing and the epilogue (epi_process):
+//   tc_scan_ts_kernel  rows of <= 128 floats: the CTA's 256 prepared queries live in TENSOR MEMORY (TS-mode MMA),
+//                      one stage = one whole 64-row database tile, N = 64 accumulators double buffered
+//   tc_scan_kernel     longer rows: query and database k-blocks stream through shared memory together (SS mode),
+//                      N = 128 accumulators double buffered
+// Both: one CTA per SM, 320 threads, warp-specialised -- a TMA producer warp (cp.async.bulk.tensor, 128B swizzle,
+// mbarrier complete_tx), an MMA warp (TMEM allocation + tcgen05.mma.kind::tf32 issued by one elected lane of a
+// warp-uniform loop) and eight epilogue warps (thread = TMEM lane = query row): tcgen05.ld 32 columns at a
+// time, min tree, one compare per 32 values with the row's threshold; survivors (rare once the threshold is
+// warm) go to the row's candidate buffer.  Thresholds: exact 16th best in a register list for k <= 12,
+// otherwise tightened by warp-cooperative compaction of the buffer; shared between the CTAs of one query.
 #include <cuda.h>
 
 #include <algorithm>
@@ -97,14 +96,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// pull a box into L2 only (no shared-memory slot needed): issued a couple of tiles ahead of the real
-// load so that the ring of shared-memory stages only ever waits for L2-hit latency
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -135,18 +126,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// same with BF16 inputs (kind::f16): K = 16 per instruction, twice the MACs per operand byte
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // A operand from tensor memory (lanes = rows, one 32-bit column per tf32 element)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -158,11 +137,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
-}
-__device__ __forceinline__ void umma(bool bf16, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                     uint32_t accumulate) {
-  if (bf16) umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
-  else umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -205,9 +179,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // Instruction descriptor for kind::tf32: D = F32 (1 @4), A = B = TF32 (2 @7, 2 @10), both K-major,
 // N >> 3 @17, M >> 4 @24.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {  // kind::f16: A = B = BF16 (1), D = F32
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
@@ -300,6 +271,85 @@ __device__ __forceinline__ void compact_lane(int src, uint64_t* buf, int& cnt, f
   }
 }
 
+constexpr int TS_RK = 16;  // register mode: ranks of a row's 16 best candidates, sorted, in registers
+
+// REG (kprime <= 16, i.e. k <= 10 with the default margin): the row's threshold is the exact 16th best rank seen,
+// kept as a sorted register list of RANKS only (insertion = a 16-step min/max chain); the (rank, position) keys
+// themselves are appended to the row's buffer, which then only ever receives the ~k ln(N) true improvements
+// and needs no compaction.  !REG: the threshold tightens when the buffer is compacted (compact_row).
+template <int KPL, bool REG>
+__device__ __forceinline__ void epi_process(const uint32_t (&v)[32], uint32_t pos0, int vcols, uint64_t* buf, int& cnt,
+                                            float& thr, float (&tk)[TS_RK], int cap, int kprime, int slack,
+                                            uint32_t* gthr, int lane, unsigned (&ctr)[4]) {
+  unsigned need = __ballot_sync(FULL, cnt > cap - 32);
+  while (need) {  // about to overflow: compact at once (!REG: normally the deferred path keeps rows far from here)
+    ++ctr[2];
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const float keep = thr;
+    compact_lane<KPL>(src, buf, cnt, thr, kprime, slack, gthr, lane);
+    if (REG) thr = fminf(thr, keep);  // (the cut is never below the 16th best, the list stays authoritative)
+  }
+  float r[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+  if (vcols < 32) {  // rows past the end of the shard: never candidates
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j >= vcols) r[j] = __int_as_float(0x7F800000);
+  }
+  float g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    g[q] = min3(min3(r[8 * q], r[8 * q + 1], r[8 * q + 2]), min3(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
+                fminf(r[8 * q + 6], r[8 * q + 7]));
+  const float m = fminf(min3(g[0], g[1], g[2]), g[3]);
+  if (m < thr) {
+    ++ctr[1];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (g[q] < thr) {
+        if constexpr (REG) {
+          // which of the group's 8 values pass, then ONE copy of the insertion code per group, run per survivor
+          unsigned mk = 0;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] < thr ? 1u : 0u) << jj;
+#pragma unroll 1
+          while (mk) {
+            const int jj = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const float lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
+            const float hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
+            const float x = (jj & 4) ? hi4 : lo4;
+            if (x < thr) {
+              buf[cnt] = ((uint64_t)__float_as_uint(x) << 32) | (uint64_t)(pos0 + 8 * q + jj);
+              ++cnt;
+              float t = x;  // sorted insertion: every slot keeps the smaller of (itself, what is carried)
+#pragma unroll
+              for (int i = 0; i < TS_RK; ++i) {
+                const float lo = fminf(tk[i], t);
+                t = fmaxf(tk[i], t);
+                tk[i] = lo;
+              }
+              if (tk[TS_RK - 1] < thr) {
+                thr = tk[TS_RK - 1];
+                atomicMin(gthr, f32_ordered(thr));  // (result unused: a fire-and-forget reduction)
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 8 * q; j < 8 * q + 8; ++j) {
+            const bool hit = r[j] < thr;
+            if (hit) buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
+            cnt += hit ? 1 : 0;
+          }
+        }
+      }
+    }
+  }
+}
+
 struct TcParams {
   int n, nq, n_kb;
   int n_tiles;             // 128-row tiles per query block (whole shard)
@@ -318,9 +368,6 @@ struct TcParams {
   int a_resident;          // 1: both query tiles stay in shared memory while a piece is scanned (D <= 128)
   int use_nb;              // 1: an extra K=8 step adds |x|^2 (three TF32 pieces x 1.0) inside the MMA (l2)
   int aligned;             // 1: CTA = (segment, query block) with common tile boundaries; 0: equal linear ranges
-  int bf16;                // 1: operands are BF16 (data proven BF16-exact), kind::f16; 0: TF32
-  int kb_elems;            // elements per 128-byte k-block: 32 (fp32/TF32) or 64 (BF16)
-  int l2_ahead;            // tiles of L2 prefetch distance (0 = off)
   int debug;               // NB200_TC_DEBUG bit 0: epilogue drains TMEM without selecting (timing experiments only)
 };
 
@@ -418,16 +465,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(afull_bar, (uint32_t)a_bytes);
             for (int h = 0; h < 2; ++h)
               for (int kb = 0; kb < p.n_kb; ++kb)
-                tma_load_2d(&tmA, afull_bar, smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES, kb * p.kb_elems,
+                tma_load_2d(&tmA, afull_bar, smem_a + (size_t)(h * p.n_kb + kb) * CHUNK_BYTES, kb * TC_KB,
                             q0 + h * TC_BM);
           }
           __syncwarp();
         }
         for (int t = t_begin; t < t_end; ++t) {
-          if (p.l2_ahead > 0 && t + p.l2_ahead < t_end && elect_one()) {
-            for (int kb = 0; kb < p.n_kb; ++kb) tma_prefetch_l2_2d(&tmB, kb * p.kb_elems, (t + p.l2_ahead) * TC_BN);
-            if (p.use_nb) tma_prefetch_l2_2d(&tmN, 0, (t + p.l2_ahead) * TC_BN);
-          }
           for (int kb = 0; kb < n_kb_all; ++kb) {
             mbar_wait(&empty_bar[s], ph ^ 1);
             unsigned char* st = smem_st + (size_t)s * stage_bytes;
@@ -436,10 +479,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_arrive(&full_bar[s]);
               } else if (kb < p.n_kb) {
                 mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                tma_load_2d(&tmB, &full_bar[s], st, kb * p.kb_elems, t * TC_BN);
+                tma_load_2d(&tmB, &full_bar[s], st, kb * TC_KB, t * TC_BN);
                 if (!p.a_resident) {
-                  tma_load_2d(&tmA, &full_bar[s], st + CHUNK_BYTES, kb * p.kb_elems, q0);
-                  tma_load_2d(&tmA, &full_bar[s], st + 2 * CHUNK_BYTES, kb * p.kb_elems, q0 + TC_BM);
+                  tma_load_2d(&tmA, &full_bar[s], st + CHUNK_BYTES, kb * TC_KB, q0);
+                  tma_load_2d(&tmA, &full_bar[s], st + 2 * CHUNK_BYTES, kb * TC_KB, q0 + TC_BM);
                 }
               } else {  // the |x|^2 block of this tile
                 mbar_expect_tx(&full_bar[s], CHUNK_BYTES);
@@ -459,8 +502,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
     if (w_begin < w_end) {
-      const bool bf = p.bf16 != 0;
-      const uint32_t idesc = bf ? make_idesc_bf16(TC_BM, TC_BN) : make_idesc_tf32(TC_BM, TC_BN);
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
       // The issuing lane must keep the tensor pipe fed (8 MMAs of 64 cycles per k-block): everything outside
       // the elected region is warp-uniform, so descriptors live in uniform registers (no ELECT/R2UR loop per
       // MMA), and the loop carries ring position / phase incrementally: no division, no rebuild.
@@ -492,22 +534,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 make_smem_desc(a_res ? a_base + (uint32_t)(p.n_kb + kb) * CHUNK_BYTES : sb + 2 * CHUNK_BYTES);
             const uint32_t acc = kb != 0;
             if (elect_one()) {
-              if (p.debug & 8) {  // timing experiment: A operand read from tensor memory (garbage values)
-                const uint32_t idx = (p.debug & 32) ? make_idesc_tf32(TC_BM, 64)
-                                     : (p.debug & 64) ? make_idesc_tf32(TC_BM, 48) : idesc;
-                for (int j = 0; j < 4; ++j) umma_tf32_ts(tmem_d0, tmem_base + 8 * j, db + 2 * j, idx, acc | j);
-                for (int j = 0; j < 4; ++j)
-                  umma_tf32_ts(tmem_d0 + TC_BN, tmem_base + 32 + 8 * j, db + 2 * j, idx, acc | j);
-              } else if (!(p.debug & 4)) {  // (bit 2 set: timing experiment without the MMAs, TMA traffic only)
+              if (!(p.debug & 4)) {  // (bit 2 set: timing experiment without the MMAs, TMA traffic only)
                 // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (address >> 4) field
-                umma(bf, tmem_d0, da0, db, idesc, acc);
-                umma(bf, tmem_d0, da0 + 2, db + 2, idesc, 1);
-                umma(bf, tmem_d0, da0 + 4, db + 4, idesc, 1);
-                umma(bf, tmem_d0, da0 + 6, db + 6, idesc, 1);
-                umma(bf, tmem_d0 + TC_BN, da1, db, idesc, acc);
-                umma(bf, tmem_d0 + TC_BN, da1 + 2, db + 2, idesc, 1);
-                umma(bf, tmem_d0 + TC_BN, da1 + 4, db + 4, idesc, 1);
-                umma(bf, tmem_d0 + TC_BN, da1 + 6, db + 6, idesc, 1);
+                umma_tf32(tmem_d0, da0, db, idesc, acc);
+                umma_tf32(tmem_d0, da0 + 2, db + 2, idesc, 1);
+                umma_tf32(tmem_d0, da0 + 4, db + 4, idesc, 1);
+                umma_tf32(tmem_d0, da0 + 6, db + 6, idesc, 1);
+                umma_tf32(tmem_d0 + TC_BN, da1, db, idesc, acc);
+                umma_tf32(tmem_d0 + TC_BN, da1 + 2, db + 2, idesc, 1);
+                umma_tf32(tmem_d0 + TC_BN, da1 + 4, db + 4, idesc, 1);
+                umma_tf32(tmem_d0 + TC_BN, da1 + 6, db + 6, idesc, 1);
               }
               tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
             }
@@ -522,8 +558,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint64_t db = make_smem_desc(st_base + (uint32_t)s * (uint32_t)stage_bytes);
             if (elect_one()) {
-              umma(bf, tmem_d0, d_ones, db, idesc, 1);
-              umma(bf, tmem_d0 + TC_BN, d_ones, db, idesc, 1);
+              umma_tf32(tmem_d0, d_ones, db, idesc, 1);
+              umma_tf32(tmem_d0 + TC_BN, d_ones, db, idesc, 1);
               tc_commit(&empty_bar[s]);
             }
             __syncwarp();
@@ -546,97 +582,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue: 8 warps (2 per scheduler), thread == one query row ==========
     // Warps 2-5 read operand half 0, warps 6-9 half 1; a warp may only touch the TMEM lane quarter
     // (warp index % 4).  The warps never synchronise with each other.  The accumulator already holds
-    // the rank (bias folded into the MMA), so the fast path is: tcgen05.ld, min tree, one compare.
+    // the rank (bias folded into the MMA), so the fast path is: tcgen05.ld, min tree, one compare
+    // (epi_process: append buffer + warp-cooperative compaction, thresholds shared between CTAs).
     const int e = warp - 2;
     const int h = e >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;       // row inside the 128-query half
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint64_t* buf = nullptr;
-    uint32_t* gthr = nullptr;
-    int cnt = 0;
-    float thr = 0.f;
-    // KPL == 0 ("small k", k' = 16): the row's 16 best (rank, position) pairs live in registers as a
-    // sorted list, so the threshold is always the exact 16th best seen so far (fewest possible appends,
-    // no buffer, no compaction).  KPL > 0: append buffer in global memory + warp-cooperative compaction.
-    constexpr bool SMALLK = (KPL == 0);
-    constexpr int RK = 16;
-    float tk[RK];
-    uint32_t tp[RK];
-
-    // one 32-column chunk; `vcols` = number of valid columns in it (< 32 only in the shard's last tile)
-    auto process = [&](const uint32_t (&v)[32], uint32_t pos0, int vcols) {
-      if constexpr (!SMALLK) {
-        // make room first: a chunk may append up to 32 keys to a row
-        unsigned need = __ballot_sync(FULL, cnt > p.cap - 32);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          compact_lane<(KPL > 0 ? KPL : 1)>(src, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
-        }
-      }
-      float r[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
-      if (vcols < 32) {  // padding rows of the database: never candidates
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j >= vcols) r[j] = __int_as_float(0x7F800000);
-      }
-      float g[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        g[q] = min3(min3(r[8 * q], r[8 * q + 1], r[8 * q + 2]), min3(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
-                    fminf(r[8 * q + 6], r[8 * q + 7]));
-      const float m = fminf(min3(g[0], g[1], g[2]), g[3]);
-      if (m < thr) {  // some value of this row beats its threshold: look only into the groups that do
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (g[q] < thr) {
-            if constexpr (SMALLK) {
-              // which of the 8 values pass; then ONE copy of the insertion code per group, run per survivor
-              // (a predicated 32-fold unroll of the insertion would execute ~100 instructions per value)
-              unsigned mk = 0;
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] < thr ? 1u : 0u) << jj;
-#pragma unroll 1
-              while (mk) {
-                const int jj = __ffs(mk) - 1;
-                mk &= mk - 1;
-                const float lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
-                const float hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
-                const float x = (jj & 4) ? hi4 : lo4;
-                if (x < thr) {
-                  const uint32_t xp = pos0 + 8 * q + jj;
-                  // branch-free sorted insertion: slot i takes its left neighbour if that one is worse than
-                  // the newcomer, the newcomer if it is the first slot worse than it, else stays
-#pragma unroll
-                  for (int i = RK - 1; i >= 1; --i) {
-                    const bool shift = tk[i - 1] > x;
-                    const bool here = tk[i] > x;
-                    tp[i] = shift ? tp[i - 1] : (here ? xp : tp[i]);
-                    tk[i] = shift ? tk[i - 1] : (here ? x : tk[i]);
-                  }
-                  if (tk[0] > x) {
-                    tk[0] = x;
-                    tp[0] = xp;
-                  }
-                  thr = tk[RK - 1];
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 8 * q; j < 8 * q + 8; ++j) {
-                if (r[j] < thr) {
-                  buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
-                  ++cnt;
-                }
-              }
-            }
-          }
-        }
-      }
-    };
+    float tk_unused[TS_RK] = {};               // (the register list is a mode of the TS kernel only)
+    unsigned ctr[4] = {0, 0, 0, 0};
 
     int ti = 0;
     for (long w = w_begin; w < w_end;) {
@@ -647,17 +601,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int first_cta = (int)(((long)qb * p.n_tiles) / p.work_per_cta);
       const size_t unit = (size_t)qb * p.s_max + (p.aligned ? cta / p.q_blocks : cta - first_cta);
       const bool row_valid = qb * TC_QB + h * TC_BM + row < p.nq;
-      buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
-      gthr = p.gthr + (qb * TC_QB + h * TC_BM + row);
-      cnt = 0;
-      thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
-      if constexpr (SMALLK) {
-#pragma unroll
-        for (int i = 0; i < RK; ++i) {
-          tk[i] = __int_as_float(0x7F800000);
-          tp[i] = 0;
-        }
-      }
+      uint64_t* buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
+      uint32_t* gthr = p.gthr + (qb * TC_QB + h * TC_BM + row);
+      int cnt = 0;
+      float thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
       for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
         const int b = ti & 1;
         mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
@@ -669,67 +616,33 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.debug & 1) {  // timing experiment: touch the accumulators, select nothing
           tmem_ld32(tcol, v0);
           tmem_ld_wait();
-          if (p.debug & 16) {  // ... all of them
-            tmem_ld32(tcol + 32u, v1);
-            tmem_ld32(tcol + 64u, v0);
-            tmem_ld_wait();
-            tmem_ld32(tcol + 96u, v1);
-            tmem_ld_wait();
-            if (__uint_as_float(v1[3]) == 1.2345e-30f) thr = 0.f;
-          }
           if (__uint_as_float(v0[0]) == 1.2345e-30f) thr = 0.f;
           tc_fence_before();
           mbar_arrive(&tempty_bar[b]);
           continue;
         }
-        if constexpr (SMALLK) {
-          // Drain first: pull the row's whole 128-column slice into registers and hand the TMEM buffer
-          // back to the MMA at once, so that a warp inside a long insertion does not hold up the other
-          // seven warps and the tensor pipe through the 2-deep TMEM ring.
-          uint32_t v2[32], v3[32];
-          tmem_ld32(tcol, v0);
-          tmem_ld32(tcol + 32u, v1);
-          tmem_ld32(tcol + 64u, v2);
-          tmem_ld32(tcol + 96u, v3);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[b]);
-          process(v0, pos_tile, vtile);
-          process(v1, pos_tile + 32, vtile - 32);
-          process(v2, pos_tile + 64, vtile - 64);
-          process(v3, pos_tile + 96, vtile - 96);
-        } else {
-          // what the other pieces of this query have found in the meantime (fminf ignores the NaN of "nothing yet")
-          if (((tile - t_begin) & 7) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
-          tmem_ld32(tcol, v0);
+        // what the other pieces of this query have found in the meantime (fminf ignores the NaN of "nothing yet")
+        if (((tile - t_begin) & 7) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
+        tmem_ld32(tcol, v0);
 #pragma unroll 1
-          for (int cp = 0; cp < TC_BN / 64; ++cp) {  // two chunks per iteration, next load in flight while computing
-            tmem_ld_wait();
-            tmem_ld32(tcol + (uint32_t)(cp * 64 + 32), v1);
-            process(v0, pos_tile + cp * 64, vtile - cp * 64);
-            tmem_ld_wait();
-            if (cp + 1 < TC_BN / 64) tmem_ld32(tcol + (uint32_t)(cp * 64 + 64), v0);
-            process(v1, pos_tile + cp * 64 + 32, vtile - cp * 64 - 32);
-          }
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[b]);
-          // deferred compaction, one row per warp and tile (the TMEM buffer is already released)
-          const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);
-          if (pend) compact_lane<(KPL > 0 ? KPL : 1)>(__ffs(pend) - 1, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
+        for (int cp = 0; cp < TC_BN / 64; ++cp) {  // two chunks per iteration, next load in flight while computing
+          tmem_ld_wait();
+          tmem_ld32(tcol + (uint32_t)(cp * 64 + 32), v1);
+          epi_process<KPL, false>(v0, pos_tile + cp * 64, vtile - cp * 64, buf, cnt, thr, tk_unused, p.cap, p.kprime,
+                                  p.slack, gthr, lane, ctr);
+          tmem_ld_wait();
+          if (cp + 1 < TC_BN / 64) tmem_ld32(tcol + (uint32_t)(cp * 64 + 64), v0);
+          epi_process<KPL, false>(v1, pos_tile + cp * 64 + 32, vtile - cp * 64 - 32, buf, cnt, thr, tk_unused, p.cap,
+                                  p.kprime, p.slack, gthr, lane, ctr);
         }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[b]);
+        // deferred compaction, one row per warp and tile (the TMEM buffer is already released)
+        const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);
+        if (pend) compact_lane<KPL>(__ffs(pend) - 1, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
       }
       // publish this piece's per-row candidate count and final threshold
       const size_t slot = unit * TC_QB + h * TC_BM + row;
-      if constexpr (SMALLK) {
-        cnt = 0;
-#pragma unroll
-        for (int i = 0; i < RK; ++i) {
-          if (tk[i] < __int_as_float(0x7F800000)) {
-            buf[i] = ((uint64_t)__float_as_uint(tk[i]) << 32) | (uint64_t)tp[i];
-            cnt = i + 1;
-          }
-        }
-      }
       p.cand_cnt[slot] = row_valid ? cnt : 0;
       p.cand_thr[slot] = thr;
       w += t_end - t_begin;
@@ -793,85 +706,6 @@ __device__ __forceinline__ int ts_warm_tiles(int warm_max, int len) {
 
 // one 32-column chunk of one row: fast path = min tree + one compare; survivors are appended to the row's
 // buffer, a full buffer is compacted warp-cooperatively first (see compact_row)
-constexpr int TS_RK = 16;  // register mode: ranks of a row's 16 best candidates, sorted, in registers
-
-// REG (kprime <= 16, i.e. k <= 10 with the default margin): the row's threshold is the exact 16th best rank seen,
-// kept as a sorted register list of RANKS only (insertion = a 16-step min/max chain); the (rank, position) keys
-// themselves are appended to the row's buffer, which then only ever receives the ~k ln(N) true improvements
-// and needs no compaction.  !REG: the threshold tightens when the buffer is compacted (compact_row).
-template <int KPL, bool REG>
-__device__ __forceinline__ void epi_process(const uint32_t (&v)[32], uint32_t pos0, int vcols, uint64_t* buf, int& cnt,
-                                            float& thr, float (&tk)[TS_RK], int cap, int kprime, int slack,
-                                            uint32_t* gthr, int lane, unsigned (&ctr)[4]) {
-  unsigned need = __ballot_sync(FULL, cnt > cap - 32);
-  while (need) {  // about to overflow: compact at once (!REG: normally the deferred path keeps rows far from here)
-    ++ctr[2];
-    const int src = __ffs(need) - 1;
-    need &= need - 1;
-    const float keep = thr;
-    compact_lane<KPL>(src, buf, cnt, thr, kprime, slack, gthr, lane);
-    if (REG) thr = fminf(thr, keep);  // (the cut is never below the 16th best, the list stays authoritative)
-  }
-  float r[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
-  if (vcols < 32) {  // rows past the end of the shard: never candidates
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j >= vcols) r[j] = __int_as_float(0x7F800000);
-  }
-  float g[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    g[q] = min3(min3(r[8 * q], r[8 * q + 1], r[8 * q + 2]), min3(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
-                fminf(r[8 * q + 6], r[8 * q + 7]));
-  const float m = fminf(min3(g[0], g[1], g[2]), g[3]);
-  if (m < thr) {
-    ++ctr[1];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (g[q] < thr) {
-        if constexpr (REG) {
-          // which of the group's 8 values pass, then ONE copy of the insertion code per group, run per survivor
-          unsigned mk = 0;
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] < thr ? 1u : 0u) << jj;
-#pragma unroll 1
-          while (mk) {
-            const int jj = __ffs(mk) - 1;
-            mk &= mk - 1;
-            const float lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
-            const float hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
-            const float x = (jj & 4) ? hi4 : lo4;
-            if (x < thr) {
-              buf[cnt] = ((uint64_t)__float_as_uint(x) << 32) | (uint64_t)(pos0 + 8 * q + jj);
-              ++cnt;
-              float t = x;  // sorted insertion: every slot keeps the smaller of (itself, what is carried)
-#pragma unroll
-              for (int i = 0; i < TS_RK; ++i) {
-                const float lo = fminf(tk[i], t);
-                t = fmaxf(tk[i], t);
-                tk[i] = lo;
-              }
-              if (tk[TS_RK - 1] < thr) {
-                thr = tk[TS_RK - 1];
-                atomicMin(gthr, f32_ordered(thr));  // (result unused: a fire-and-forget reduction)
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 8 * q; j < 8 * q + 8; ++j) {
-            const bool hit = r[j] < thr;
-            if (hit) buf[cnt] = ((uint64_t)__float_as_uint(r[j]) << 32) | (uint64_t)(pos0 + j);
-            cnt += hit ? 1 : 0;
-          }
-        }
-      }
-    }
-  }
-}
-
 template <int KPL, bool REG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmN,
@@ -1472,62 +1306,6 @@ __global__ void tc_prep_db_kernel(const float* __restrict__ db, int n, int n_pad
   }
 }
 
-// ---- BF16 operand copies (only made when every element is BF16-exact: low 16 bits zero) ----
-__device__ __forceinline__ uint16_t bf16_bits(float v) { return (uint16_t)(__float_as_uint(v) >> 16); }
-
-// database rows -> [n_pad][row_bf] bf16 (zero padded), |x|^2 -> three bf16 pieces in [n_pad][64]; flag if inexact
-__global__ void tc_prep_db_bf16_kernel(const float* __restrict__ db, int n, int n_pad, int row_words, int row_bf,
-                                       int with_norm, uint16_t* __restrict__ out, uint16_t* __restrict__ nblock,
-                                       int* __restrict__ inexact_flag) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n_pad) return;
-  uint16_t* o = out + (size_t)warp * row_bf;
-  float s = 0.f;
-  unsigned bad = 0;
-  for (int c = lane; c < row_bf; c += 32) {
-    const float v = (warp < n && c < row_words) ? db[(size_t)warp * row_words + c] : 0.f;
-    bad |= __float_as_uint(v) & 0xFFFFu;
-    s = fmaf(v, v, s);
-    o[c] = bf16_bits(v);
-  }
-  s = warp_sum_f(s);
-  bad = __reduce_or_sync(FULL, bad);
-  if (nblock) {
-    float piece = 0.f;
-    if (with_norm && warp < n) {  // 8 + 8 + 8 significant bits: hi + mid + lo == s exactly
-      const float hi = __uint_as_float(__float_as_uint(s) & 0xFFFF0000u);
-      const float r1 = s - hi;
-      const float mid = __uint_as_float(__float_as_uint(r1) & 0xFFFF0000u);
-      const float lo = r1 - mid;
-      if (__float_as_uint(lo) & 0xFFFFu) bad = 1;  // cannot happen for 24-bit norms; keeps the flag honest
-      piece = lane == 0 ? hi : lane == 1 ? mid : lane == 2 ? lo : 0.f;
-    }
-    nblock[(size_t)warp * 64 + lane] = bf16_bits(piece);
-    nblock[(size_t)warp * 64 + 32 + lane] = 0;
-  }
-  if (lane == 0 && bad) atomicOr(inexact_flag, 1);
-}
-
-// A' = scale * q as bf16 into [q_pad][row_bf]; flags a batch that is not BF16-exact
-__global__ void tc_prep_queries_bf16_kernel(const float* __restrict__ q, int q_pad, int row_words, int row_bf,
-                                            float scale, uint16_t* __restrict__ out, int* __restrict__ inexact_flag) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= q_pad) return;
-  unsigned bad = 0;
-  for (int c = lane; c < row_bf; c += 32) {
-    const float v = c < row_words ? q[(size_t)warp * row_words + c] : 0.f;
-    bad |= __float_as_uint(v) & 0xFFFFu;
-    out[(size_t)warp * row_bf + c] = bf16_bits(v * scale);
-  }
-  bad = __reduce_or_sync(FULL, bad);
-  if (lane == 0 && bad) atomicOr(inexact_flag, 1);
-}
-
-__global__ void tc_fill_ones_bf16_kernel(uint16_t* __restrict__ ones) {  // [128][64]: 1.0 in columns 0..2
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < TC_BM * 64) ones[i] = (i % 64) < 3 ? (uint16_t)0x3F80 : (uint16_t)0;
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1545,16 +1323,15 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // rows x row_words fp32, row-major; box = 128 rows x 32 floats, 128B swizzle
-bool make_tmap(CUtensorMap* map, const void* base, size_t rows, int row_elems, bool bf16 = false,
-               int box_rows = TC_BM) {
+bool make_tmap(CUtensorMap* map, const void* base, size_t rows, int row_elems, int box_rows = TC_BM) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
-  const int esz = bf16 ? 2 : 4;
+  const int esz = 4;
   cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)row_elems * esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -1581,25 +1358,6 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
   tc_prep_db_kernel<<<blocks, threads, 0, stream>>>(db, n, n_pad, row_words, mode, bias, norm2, db_unit, nblock,
                                                     max_norm_bits, inexact_flag);
   if (ones) tc_fill_ones_kernel<<<(TC_BM * TC_KB + 255) / 256, 256, 0, stream>>>(ones);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_tc_prep_db_bf16(const float* db, int n, int n_pad, int row_words, int row_bf, int with_norm,
-                                   void* out, void* nblock, void* ones, int* inexact_flag, cudaStream_t stream) {
-  const int threads = 256;
-  const int blocks = (int)(((size_t)n_pad * 32 + threads - 1) / threads);
-  tc_prep_db_bf16_kernel<<<blocks, threads, 0, stream>>>(db, n, n_pad, row_words, row_bf, with_norm,
-                                                         static_cast<uint16_t*>(out), static_cast<uint16_t*>(nblock),
-                                                         inexact_flag);
-  if (ones) tc_fill_ones_bf16_kernel<<<(TC_BM * 64 + 255) / 256, 256, 0, stream>>>(static_cast<uint16_t*>(ones));
-  return cudaGetLastError();
-}
-cudaError_t launch_tc_prep_queries_bf16(const float* q, int q_pad, int row_words, int row_bf, float scale, void* out,
-                                        int* inexact_flag, cudaStream_t stream) {
-  const int threads = 256;
-  const int blocks = (int)(((size_t)q_pad * 32 + threads - 1) / threads);
-  tc_prep_queries_bf16_kernel<<<blocks, threads, 0, stream>>>(q, q_pad, row_words, row_bf, scale,
-                                                              static_cast<uint16_t*>(out), inexact_flag);
   return cudaGetLastError();
 }
 
@@ -1664,16 +1422,6 @@ cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, flo
 
 // cand capacity per (unit,row) and survivors per compaction for a given k
 void tc_candidate_shape(int k, int* kprime, int* cap) {
-  static const bool smallk = [] {
-    const char* e = getenv("NB200_TC_SMALLK");
-    return e && e[0] == '1';
-  }();
-  if (smallk && k <= 12) {  // register-resident exact top-16 per row (tc_scan_kernel<0>); experimental: the
-                            // long insertion path of one warp stalls the CTA-wide TMEM ring, see profiles/README.md
-    *kprime = 16;
-    *cap = 16;
-    return;
-  }
   int kp = k + 22 < 2 * k ? k + 22 + (k / 4) : 2 * k;  // headroom for the certificate
   if (kp < k + 22) kp = k + 22;
   kp = (kp + 31) / 32 * 32;
@@ -1686,19 +1434,15 @@ int tc_max_k() { return 256; }
 
 cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
                            const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_cta,
-                           int work_per_cta, int s_max, int aligned, int bf16, int kprime, uint64_t* cand,
-                           int* cand_cnt, float* cand_thr, uint32_t* gthr, cudaStream_t stream) {
+                           int work_per_cta, int s_max, int aligned, int kprime, uint64_t* cand, int* cand_cnt,
+                           float* cand_thr, uint32_t* gthr, cudaStream_t stream) {
   if (n <= 0 || nq <= 0) return cudaSuccess;
-  // row_words counts ELEMENTS per operand row here: fp32 words, or bf16 halves when bf16 != 0
-  const int kb_elems = bf16 ? 64 : TC_KB;
-  if (row_words % kb_elems) return cudaErrorInvalidValue;
+  if (row_words % TC_KB) return cudaErrorInvalidValue;
   CUtensorMap tmA, tmB, tmN, tmO;
-  if (!make_tmap(&tmA, qa, q_pad, row_words, bf16) || !make_tmap(&tmB, dbB, n_pad, row_words, bf16))
-    return cudaErrorUnknown;
+  if (!make_tmap(&tmA, qa, q_pad, row_words) || !make_tmap(&tmB, dbB, n_pad, row_words)) return cudaErrorUnknown;
   const bool use_nb = nblock != nullptr;
   if (use_nb) {
-    if (!make_tmap(&tmN, nblock, n_pad, kb_elems, bf16) || !make_tmap(&tmO, ones, TC_BM, kb_elems, bf16))
-      return cudaErrorUnknown;
+    if (!make_tmap(&tmN, nblock, n_pad, TC_KB) || !make_tmap(&tmO, ones, TC_BM, TC_KB)) return cudaErrorUnknown;
   } else {
     tmN = tmB;
     tmO = tmA;
@@ -1706,9 +1450,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   TcParams p;
   p.n = n;
   p.nq = nq;
-  p.n_kb = row_words / kb_elems;
-  p.bf16 = bf16 ? 1 : 0;
-  p.kb_elems = kb_elems;
+  p.n_kb = row_words / TC_KB;
   p.n_tiles = (n + TC_BN - 1) / TC_BN;
   p.q_blocks = (nq + TC_QB - 1) / TC_QB;
   p.work_per_cta = work_per_cta;
@@ -1721,22 +1463,14 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   p.cand_thr = cand_thr;
   int kp_default;
   tc_candidate_shape(k, &kp_default, &p.cap);
-  if (p.cap > 16) {
-    p.kprime = std::max(k + 1, std::min(kprime, kp_default));
-    p.slack = std::max(8, p.kprime / 4);
-    p.hwm = std::min(p.cap / 2, std::max(64, 2 * p.kprime));
-  } else {  // (opt-in register mode of this kernel)
-    p.kprime = kp_default;
-    p.slack = 16;
-    p.hwm = p.cap;
-  }
+  p.kprime = std::max(k + 1, std::min(kprime, kp_default));
+  p.slack = std::max(8, p.kprime / 4);
+  p.hwm = std::min(p.cap / 2, std::max(64, 2 * p.kprime));
   p.gthr = gthr;
   p.use_nb = use_nb ? 1 : 0;
   {
     const char* dbg = getenv("NB200_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
-    const char* la = getenv("NB200_TC_L2AHEAD");
-    p.l2_ahead = la ? atoi(la) : 0;  // measured: prefetching ahead into L2 does not help (profiles/README.md)
   }
   p.a_resident = (2 * p.n_kb * CHUNK_BYTES <= 128 * 1024) ? 1 : 0;
   const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;
@@ -1752,11 +1486,10 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   e = cudaFuncSetAttribute(tc_scan_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
   if (e != cudaSuccess) return e;                                                                         \
   tc_scan_kernel<KPL><<<n_cta, TC_THREADS, smem, stream>>>(tmA, tmB, tmN, tmO, p);
-  switch (p.cap) {
-    case 16: NB_TC(0); break;
-    case 128: NB_TC(4); break;
-    case 256: NB_TC(8); break;
-    default: NB_TC(16); break;
+  if (p.cap == 256) {
+    NB_TC(8);
+  } else {
+    NB_TC(16);
   }
 #undef NB_TC
   e = cudaGetLastError();
@@ -1856,10 +1589,10 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   if (n <= 0 || nq <= 0) return cudaSuccess;
   if (!tc_ts_supported(row_words)) return cudaErrorInvalidValue;
   CUtensorMap tmB, tmN, tmO;
-  if (!make_tmap(&tmB, dbB, n_pad, row_words, false, TS_BN)) return cudaErrorUnknown;
+  if (!make_tmap(&tmB, dbB, n_pad, row_words, TS_BN)) return cudaErrorUnknown;
   const bool use_nb = nblock != nullptr;
   if (use_nb) {
-    if (!make_tmap(&tmN, nblock, n_pad, TC_KB, false, TS_BN) || !make_tmap(&tmO, ones, TC_BM, TC_KB)) return cudaErrorUnknown;
+    if (!make_tmap(&tmN, nblock, n_pad, TC_KB, TS_BN) || !make_tmap(&tmO, ones, TC_BM, TC_KB)) return cudaErrorUnknown;
   } else {
     tmN = tmB;
     tmO = tmB;
