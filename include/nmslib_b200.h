@@ -271,6 +271,13 @@ typedef struct {
   double last_scan_ms;       /* CUDA-event time of the dominant kernel alone (scan / beam search) */
   double scan_ms_sum;        /* sum of that time over all launches resolved so far */
   uint64_t scan_count;       /* number of launches in scan_ms_sum */
+  /* device-side HNSW construction (hnsw_build_gpu.cu); all zero when the graph was imported or built on the host */
+  double build_total_ms;     /* whole build, CUDA events */
+  double build_scan_ms;      /* candidate generation: prefix kNN on the tensor cores */
+  double build_select_ms;    /* heuristic-2 neighbour selection of the new points */
+  double build_link_ms;      /* back links: sort + append / re-prune */
+  uint64_t build_batches;    /* insertion batches over all levels */
+  uint64_t build_prunes;     /* neighbour lists re-pruned because they overflowed */
 } nmslib_b200_stats_t;
 nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_stats_t* out);
 

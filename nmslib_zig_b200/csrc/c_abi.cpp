@@ -166,7 +166,8 @@ nmslib_error_t nmslib_create_index(nmslib_index_handle_t index, nmslib_params_ha
         // AnyParamManager::CheckUnused throws on unknown names (params.h:241-251) -> error 8
         static const char* seq_names[] = {"copyMem", "multiThread", "threadQty"};  // seqsearch.cc:63-68
         static const char* hnsw_names[] = {"M", "efConstruction", "maxM", "maxM0", "mult", "delaunay_type", "post",
-                                           "indexThreadQty", "skip_optimized_index", "searchMethod"};  // hnsw.cc:189-208
+                                           "indexThreadQty", "skip_optimized_index", "searchMethod",
+                                           "b200_build"};  // hnsw.cc:189-208 + where to build (extension)
         for (const std::string& p : params_of(index_params)) {
           const std::string name = p.substr(0, p.find('='));
           bool known = false;
@@ -589,7 +590,7 @@ nmslib_error_t nmslib_save_index(nmslib_index_handle_t index, const char* path, 
         }
         if (e->method() == nb200::METHOD_HNSW) {
           if (e->graph().empty()) {  // not queried yet: build now (the reference builds at create_index time)
-            Status ps = e->ensure_graph_host();
+            Status ps = e->ensure_graph();
             if (!ps.ok()) return NB_STATUS(ps);
           }
           Status s = nb200::write_hnsw_file(path, e->graph(), e->hnsw_rows_for_save(), e->graph().ext_ids.data());
@@ -755,6 +756,13 @@ nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_st
   out->last_scan_ms = s.last_scan_ms;
   out->scan_ms_sum = s.scan_ms_sum;
   out->scan_count = s.scan_count;
+  const nb200::HnswBuildInfo& bi = index->engine->build_info();
+  out->build_total_ms = bi.total_ms;
+  out->build_scan_ms = bi.scan_ms;
+  out->build_select_ms = bi.select_ms;
+  out->build_link_ms = bi.link_ms;
+  out->build_batches = (uint64_t)bi.batches;
+  out->build_prunes = bi.prunes;
   return NMSLIB_SUCCESS;
 }
 

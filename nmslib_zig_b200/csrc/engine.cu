@@ -35,13 +35,16 @@ bool device_available() {
 
 cudaError_t DevBuf::ensure(size_t bytes, bool zero_new, cudaStream_t s) {
   if (bytes <= cap) return cudaSuccess;
+  if (borrowed) return cudaErrorInvalidValue;  // a borrowed range cannot grow
+  size_t want = round_up(bytes, 256);
   if (p) {
+    // a buffer that grows once tends to grow again (batches of rising size): 1.5x steps, not one realloc per call
+    want = std::max(want, round_up(cap + cap / 2, 256));
     cudaError_t e = cudaFree(p);
     p = nullptr;
     cap = 0;
     if (e != cudaSuccess) return e;
   }
-  size_t want = round_up(bytes, 256);
   cudaError_t e = cudaMalloc(&p, want);
   if (e != cudaSuccess) {
     p = nullptr;
@@ -52,16 +55,26 @@ cudaError_t DevBuf::ensure(size_t bytes, bool zero_new, cudaStream_t s) {
   return cudaSuccess;
 }
 void DevBuf::release() {
-  if (p) cudaFree(p);
+  if (p && !borrowed) cudaFree(p);
   p = nullptr;
   cap = 0;
+  borrowed = false;
+}
+void DevBuf::borrow(void* ptr, size_t bytes) {
+  release();
+  p = ptr;
+  cap = bytes;
+  borrowed = true;
 }
 cudaError_t PinBuf::ensure(size_t bytes) {
   if (bytes <= cap) return cudaSuccess;
-  if (p) cudaFreeHost(p);
+  size_t want = round_up(bytes, 4096);
+  if (p) {
+    want = std::max(want, round_up(cap + cap / 2, 4096));
+    cudaFreeHost(p);
+  }
   p = nullptr;
   cap = 0;
-  size_t want = round_up(bytes, 4096);
   cudaError_t e = cudaMallocHost(&p, want);
   if (e != cudaSuccess) {
     p = nullptr;
@@ -375,18 +388,21 @@ Status Engine::upload_data() {
   // pipeline stage (64 B) and the row count to a whole tile, so no kernel needs edge code.
   // float rows are padded to 128 bytes (one TMA / UMMA swizzle row of the tensor-core scan)
   const bool dev_u8 = dev_u8_rows();
-  row_words_ = (int)round_up(dev_u8 ? (size_t)dim_ / 4 : (size_t)dim_, dev_u8 ? stage : tc_kblock_words());
+  if (!rows_borrowed_)
+    row_words_ = (int)round_up(dev_u8 ? (size_t)dim_ / 4 : (size_t)dim_, dev_u8 ? stage : tc_kblock_words());
   if (dev_u8 && dim_ % 4) return Status::Err(kErrInvalid, "uint8 dimension must be a multiple of 4");
   const size_t n_pad = round_up(n_, bn);
   const size_t row_bytes = (size_t)row_words_ * 4;
   Status s = check_cuda(d_db_.ensure(n_pad * row_bytes), "cudaMalloc(data)");
   if (!s.ok()) return s;
-  s = check_cuda(cudaMemsetAsync(d_db_.p, 0, n_pad * row_bytes, stream_), "memset(data)");
+  if (!rows_borrowed_) s = check_cuda(cudaMemsetAsync(d_db_.p, 0, n_pad * row_bytes, stream_), "memset(data)");
   if (!s.ok()) return s;
   const size_t src_row = dev_u8 ? (size_t)dim_ : (size_t)dim_ * 4;
   const void* src = dev_u8 ? (const void*)h_u8_.data() : (const void*)h_f32_.data();
   if (method_ == METHOD_HNSW) src = hnsw_host_rows();  // float rows; cosine: unit-normalised (hnsw.cc:441-446)
-  if (u8_widened()) {  // bytes up in 1 M-row chunks, widened to fp32 rows on the device
+  if (rows_borrowed_) {
+    // (adopt_device_rows: the padded rows are already in HBM; ids = positions)
+  } else if (u8_widened()) {  // bytes up in 1 M-row chunks, widened to fp32 rows on the device
     const size_t chunk = 1u << 20;
     if (!(s = check_cuda(d_u8tmp_.ensure(std::min(n_, chunk) * (size_t)dim_), "cudaMalloc(u8 staging)")).ok()) return s;
     for (size_t r0 = 0; r0 < n_; r0 += chunk) {
@@ -405,10 +421,12 @@ Status Engine::upload_data() {
                    "H2D(data)");
     if (!s.ok()) return s;
   }
-  s = check_cuda(d_ids_.ensure(n_ * 4), "cudaMalloc(ids)");
-  if (!s.ok()) return s;
-  s = check_cuda(cudaMemcpyAsync(d_ids_.p, h_ids_.data(), n_ * 4, cudaMemcpyHostToDevice, stream_), "H2D(ids)");
-  if (!s.ok()) return s;
+  if (!rows_borrowed_) {
+    s = check_cuda(d_ids_.ensure(n_ * 4), "cudaMalloc(ids)");
+    if (!s.ok()) return s;
+    s = check_cuda(cudaMemcpyAsync(d_ids_.p, h_ids_.data(), n_ * 4, cudaMemcpyHostToDevice, stream_), "H2D(ids)");
+    if (!s.ok()) return s;
+  }
   const bool cos_family = space_ == SPACE_COSINE || space_ == SPACE_ANGULAR;
   if (method_ == METHOD_SEQ && (cos_family || dev_u8)) {
     s = check_cuda(d_aux_.ensure(n_pad * 4), "cudaMalloc(aux)");
@@ -478,7 +496,53 @@ Status Engine::ensure_graph_host() {
   return Status::OK();
 }
 
+// Graph construction on the device (hnsw_build_gpu.cu) over the rows upload_data() has just put in HBM.
+Status Engine::build_graph_device() {
+  HnswBuildParams bp;
+  std::string err;
+  if (!parse_hnsw_build_params(index_params_, &bp, &err)) return Status::Err(kErrBuild, err);
+  const int dist_func = space_ == SPACE_COSINE ? 3 : space_ == SPACE_NEGDOT ? 4 : (dim_ % 16 == 0 ? 1 : 2);
+  HnswGraph g;
+  Status bs = build_hnsw_device(d_db_.as<float>(), n_, dim_, row_words_, dist_func, h_ids_.data(), bp, device_, &g,
+                                &build_info_);
+  if (!bs.ok()) return bs;
+  graph_ = std::move(g);
+  graph_dirty_ = true;
+  return Status::OK();
+}
+
+Status Engine::ensure_graph() {
+  if (method_ != METHOD_HNSW || !graph_.empty()) return Status::OK();
+  if (device_available()) {  // prepare() uploads the rows and builds on the device when the parameters allow it
+    Status s = prepare();
+    if (s.ok() || !graph_.empty()) return s;
+  }
+  return ensure_graph_host();
+}
+
+Status Engine::adopt_device_rows(const float* d_rows, size_t n, int dim, int row_words) {
+  if (method_ != METHOD_SEQ || is_u8_) return Status::Err(kErrIncompat, "adopt_device_rows: float seq_search only");
+  n_ = n;
+  dim_ = dim;
+  row_words_ = row_words;
+  rows_borrowed_ = true;
+  d_db_.borrow(const_cast<float*>(d_rows), round_up(n, scan_exact_block_points()) * (size_t)row_words * 4);
+  data_dirty_ = true;
+  built_ = true;
+  return Status::OK();
+}
+
 Status Engine::upload_graph() {
+  if (graph_.empty() && n_ > 0) {
+    HnswBuildParams bp;
+    std::string err;
+    if (!parse_hnsw_build_params(index_params_, &bp, &err)) return Status::Err(kErrBuild, err);
+    const bool on_device = bp.where == 1 || (bp.where < 0 && n_ >= 16384);
+    if (on_device && bp.M <= 64 && bp.maxM <= 64 && bp.maxM0 <= 64 && bp.delaunay_type != 0) {
+      Status bs = build_graph_device();
+      if (!bs.ok()) return bs;
+    }
+  }
   {
     Status bs = ensure_graph_host();
     if (!bs.ok()) return bs;
@@ -521,7 +585,7 @@ Status Engine::upload_graph() {
 
 // ------------------------------------------------------------------------------------ query
 Status Engine::stage_queries_device(const void* src, bool src_on_device, size_t nq, size_t elem_count,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, size_t src_pitch) {
   const size_t bq = std::max(scan_exact_block_queries(), tc_block_queries());
   const size_t q_pad = round_up(nq, bq);
   const size_t row_bytes = (size_t)row_words_ * 4;
@@ -544,7 +608,7 @@ Status Engine::stage_queries_device(const void* src, bool src_on_device, size_t 
                       "widen_u8(queries)");
   }
   const size_t src_row = dev_u8_rows() ? elem_count : elem_count * 4;
-  return check_cuda(cudaMemcpy2DAsync(d_q_.p, row_bytes, src, src_row, src_row, nq,
+  return check_cuda(cudaMemcpy2DAsync(d_q_.p, row_bytes, src, src_pitch ? src_pitch : src_row, src_row, nq,
                                       src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream),
                     "copy(queries)");
 }
@@ -696,7 +760,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   if (!(s = check_cuda(cudaMemsetAsync(d_gthr_.p, 0xFF, q_pad * 4, stream), "memset(gthr)")).ok()) return s;
   // survivors per compaction: k + margin.  Data that is not TF32-exact carries a pass-1 error of ~2^-9 |q||x|,
   // which at k = 100 spans tens of ranks: start with half of k there (the margin doubles when certificates fail)
-  const int kprime_req = (int)k + (db_inexact_ ? std::max(tc_margin_, (int)k / 2) : tc_margin_);
+  // (approx_ok_: graph construction takes the tensor-core ranking as it is -- small margin, no error band in the re-rank)
+  const int kprime_req = (int)k + (db_inexact_ && !approx_ok_ ? std::max(tc_margin_, (int)k / 2) : tc_margin_);
   if (ts) {
     scan_begin(stream);
     s = check_cuda(launch_tc_scan_ts(static_cast<const float*>(dq), dbB, n_pad,
@@ -730,7 +795,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
                                   mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)n_dev_, (int)nq, row_words_,
                                   (int)k, s_max, space_ == SPACE_ANGULAR ? SCAN_ANGULAR : mode, pos_base_,
                                   d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
-                                  d_cand_thr_.as<float>(), x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(),
+                                  d_cand_thr_.as<float>(), approx_ok_ ? 0.f : x_max_, d_flags_.as<int>(), out_keys,
+                                  d_cert_.as<int>(),
                                   stream),
                  "tc_rerank");
   if (!s.ok()) return s;
@@ -745,6 +811,7 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     if (!cert[i]) fb.push_back((int)i);
   if (fb.empty()) return Status::OK();
   stats_.fallback_queries += fb.size();
+  if (approx_ok_) return Status::OK();  // (graph construction: the re-ranked candidates are good enough)
   // the thresholds sat too close to the k-th answer for this data's pass-1 error bound: keep more survivors per
   // compaction from the next batch on (costs candidates, buys certificate margin)
   if (fb.size() * 64 > nq && tc_margin_ < 128) tc_margin_ *= 2;
@@ -773,7 +840,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
 }
 
 Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, size_t k, int32_t* d_ids,
-                          float* d_dists, uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream) {
+                          float* d_dists, uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream,
+                          size_t src_pitch) {
   if (!built_) return Status::Err(kErrBuild, "Index not built");
   if (nq == 0 || k == 0) return Status::Err(kErrInvalid, "empty query batch or k == 0");
   Status s = prepare();
@@ -782,13 +850,16 @@ Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, s
   if (elem_count != (size_t)dim_)  // the reference CHECKs equal lengths (space_lp.cc:29) -> error 9
     return Status::Err(kErrQuery, "query length " + std::to_string(elem_count) + " != index dimension " +
                                       std::to_string(dim_));
-  if (method_ == METHOD_SEQ && k > (size_t)scan_exact_max_k())
+  // (graph construction: tensor-core candidates are taken as they are, so the exact re-run path and its limit on
+  // k never come into play)
+  const bool approx_tc = approx_ok_ && !force_exact_ && k <= (size_t)tc_max_k();
+  if (method_ == METHOD_SEQ && !approx_tc && k > (size_t)scan_exact_max_k())
     return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported yet");
   if (method_ == METHOD_HNSW && k > (size_t)hnsw_max_ef()) return Status::Err(kErrTooLarge, "k too large for hnsw");
   if (is_u8_ && method_ == METHOD_HNSW)
     return Status::Err(kErrIncompat, "device-resident uint8 queries are not supported for hnsw (use the host entry)");
   cudaStream_t st = stream ? stream : stream_;
-  s = stage_queries_device(d_queries, true, nq, elem_count, st);
+  s = stage_queries_device(d_queries, true, nq, elem_count, st, src_pitch);
   if (!s.ok()) return s;
   s = run(d_q_.p, nq, k, d_ids, d_dists, d_keys, d_counts, st);
   if (s.ok()) stats_.queries += nq;

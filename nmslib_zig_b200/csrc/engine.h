@@ -36,7 +36,9 @@ struct Status {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool borrowed = false;  // memory owned by someone else (hnsw_build_gpu.cu scans the rows of the index in place)
   cudaError_t ensure(size_t bytes, bool zero_new = false, cudaStream_t s = nullptr);
+  void borrow(void* ptr, size_t bytes);
   void release();
   template <typename T>
   T* as() const { return static_cast<T*>(p); }
@@ -72,6 +74,24 @@ Status build_hnsw_host(const float* rows, size_t n, int dim, int dist_func, cons
                        const std::vector<std::string>& params, HnswGraph* out);
 Status write_hnsw_file(const std::string& path, const HnswGraph& g, const float* vectors,
                        const int32_t* ext_ids);
+
+// index-time parameters of Hnsw::CreateIndex (hnsw.cc:185-205) + where to build (b200_build=auto|host|device)
+struct HnswBuildParams {
+  int M = 16, efConstruction = 200, maxM = 16, maxM0 = 32, delaunay_type = 2, threads = 0;
+  double mult = 0;
+  int where = -1;  // -1 auto (device for >= 16384 points when a GPU is present), 0 host, 1 device
+};
+bool parse_hnsw_build_params(const std::vector<std::string>& params, HnswBuildParams* bp, std::string* err);
+std::vector<int> hnsw_assign_levels(size_t n, double mult);  // getRandomLevel (hnsw.h:476-480), seed 0 (init.cc:34)
+struct HnswBuildInfo {
+  double scan_ms = 0, select_ms = 0, link_ms = 0, total_ms = 0;
+  int batches = 0, levels = 0;
+  uint64_t reverse_edges = 0, prunes = 0;
+};
+// device-side graph construction (hnsw_build_gpu.cu): d_rows = [n_pad][row_words] float rows already in HBM
+// (cosine: unit-normalised), n_pad = n rounded up to 128 rows.  The graph comes back as a host image.
+Status build_hnsw_device(const float* d_rows, size_t n, int dim, int row_words, int dist_func, const int32_t* ext_ids,
+                         const HnswBuildParams& bp, int device, HnswGraph* out, HnswBuildInfo* info);
 
 struct Stats {
   uint64_t queries = 0, kernel_launches = 0, distance_evals = 0, hnsw_expansions = 0;
@@ -110,6 +130,12 @@ class Engine {
   void set_pos_base(uint32_t b) { pos_base_ = b; }
   Status prepare();  // lazy upload; idempotent
   Status ensure_graph_host();  // hnsw: build the graph on the host if none was imported (no GPU needed)
+  Status ensure_graph();       // hnsw: build it where the index parameters say (device when one is present)
+  const HnswBuildInfo& build_info() const { return build_info_; }
+  // ---- internal users (hnsw_build_gpu.cu): a seq_search engine over rows that already live in HBM ----
+  Status adopt_device_rows(const float* d_rows, size_t n, int dim, int row_words);
+  void set_scan_rows(size_t n) { n_dev_ = n < n_ ? n : n_; }  // scan only the first n rows (prefix kNN)
+  void set_approx_ok(bool v) { approx_ok_ = v; }              // keep uncertified tensor-core answers (no exact re-run)
 
   // ---- queries ----
   // host in / host out: ids/dists are [nq][k] staging arrays owned by the engine
@@ -119,8 +145,9 @@ class Engine {
   Status range_host(const void* query, size_t elem_count, double radius, size_t capacity, int32_t* ids, float* dists,
                     size_t* size);
   // device in / device out
+  // src_pitch: bytes between query rows (0 = dense rows of elem_count elements)
   Status knn_device(const void* d_queries, size_t nq, size_t elem_count, size_t k, int32_t* d_ids,
-                    float* d_dists, uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream);
+                    float* d_dists, uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream, size_t src_pitch = 0);
 
   Stats stats();  // also resolves the dominant-kernel event pair if it has completed
   int device() const { return device_; }
@@ -143,7 +170,8 @@ class Engine {
   Status run(const void* d_queries_padded, size_t nq, size_t k, int32_t* d_ids, float* d_dists,
              uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream);
   Status stage_queries_device(const void* src, bool src_on_device, size_t nq, size_t elem_count,
-                              cudaStream_t stream);
+                              cudaStream_t stream, size_t src_pitch = 0);
+  Status build_graph_device();
 
   Space space_;
   Method method_;
@@ -195,6 +223,8 @@ class Engine {
   PinBuf h_cert_;
   float x_max_ = 0.f;
   bool force_exact_ = false;
+  bool approx_ok_ = false, rows_borrowed_ = false;
+  HnswBuildInfo build_info_;
   size_t n_dev_ = 0;
   DevBuf d_links0_, d_links0_cnt_, d_upper_, d_upper_off_, d_visited_, d_epoch_, d_counters_;
   int hnsw_slots_ = 0;

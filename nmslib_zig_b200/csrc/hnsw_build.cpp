@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <queue>
 #include <random>
@@ -29,18 +30,18 @@
 namespace nb200 {
 namespace {
 
-struct BuildParams {
-  int M = 16, efConstruction = 200, maxM = 16, maxM0 = 32, delaunay_type = 2, threads = 0;
-  double mult = 0;
-};
+typedef HnswBuildParams BuildParams;
 
-bool parse_build_params(const std::vector<std::string>& params, BuildParams* bp, std::string* err) {
+}  // namespace
+
+bool parse_hnsw_build_params(const std::vector<std::string>& params, HnswBuildParams* bp, std::string* err) {
   bool has_maxM = false, has_maxM0 = false, has_mult = false;
   for (const std::string& p : params) {
     const size_t eq = p.find('=');
     if (eq == std::string::npos) continue;
     const std::string name = p.substr(0, eq);
-    std::stringstream ss(p.substr(eq + 1));
+    const std::string val = p.substr(eq + 1);
+    std::stringstream ss(val);
     double v = 0;
     ss >> v;
     if (name == "M") bp->M = (int)v;
@@ -50,6 +51,12 @@ bool parse_build_params(const std::vector<std::string>& params, BuildParams* bp,
     else if (name == "mult") { bp->mult = v; has_mult = true; }
     else if (name == "delaunay_type") bp->delaunay_type = (int)v;
     else if (name == "indexThreadQty") bp->threads = (int)v;
+    else if (name == "b200_build") bp->where = val == "device" || val == "gpu" ? 1 : val == "host" || val == "cpu" ? 0 : -1;
+  }
+  if (const char* e = getenv("NB200_HNSW_BUILD")) {  // A/B switch for the tools
+    const std::string v(e);
+    if (v == "device" || v == "gpu") bp->where = 1;
+    else if (v == "host" || v == "cpu") bp->where = 0;
   }
   if (bp->M < 2 || bp->efConstruction < 1) {
     *err = "HNSW needs M >= 2 and efConstruction >= 1";
@@ -64,6 +71,22 @@ bool parse_build_params(const std::vector<std::string>& params, BuildParams* bp,
   }
   return true;
 }
+
+std::vector<int> hnsw_assign_levels(size_t n, double mult) {
+  std::vector<int> level(n);
+  std::mt19937 rng(0);  // the reference seeds with 0 as well (init.cc:34)
+  std::uniform_real_distribution<double> uni(0.0, 1.0);
+  for (size_t i = 0; i < n; ++i) {
+    double u = uni(rng);
+    if (u < 1e-300) u = 1e-300;
+    int l = (int)(-std::log(u) * mult);  // getRandomLevel, hnsw.h:476-480
+    if (l > 30) l = 30;
+    level[i] = l;
+  }
+  return level;
+}
+
+namespace {
 
 struct Builder {
   const float* data;  // [n][dim] (cosine: unit-normalised copy)
@@ -231,7 +254,7 @@ Status build_hnsw_host(const float* rows, size_t n, int dim, int dist_func, cons
                        const std::vector<std::string>& params, HnswGraph* out) {
   BuildParams bp;
   std::string err;
-  if (!parse_build_params(params, &bp, &err)) return Status::Err(8, err);
+  if (!parse_hnsw_build_params(params, &bp, &err)) return Status::Err(8, err);
   if (n == 0) return Status::Err(8, "cannot build an HNSW graph over an empty data set");
   if (n > 0x7FFFFFF0ull) return Status::Err(6, "too many points for an HNSW graph");
   Builder b;
@@ -240,20 +263,11 @@ Status build_hnsw_host(const float* rows, size_t n, int dim, int dist_func, cons
   b.dim = dim;
   b.kind = dist_func == 3 ? 1 : dist_func == 4 ? 2 : 0;
   b.bp = bp;
-  b.level.resize(n);
   b.links.resize(n);
   std::vector<std::mutex> locks(n);
   b.locks.swap(locks);
-  std::mt19937 rng(0);  // the reference seeds with 0 as well (init.cc:34)
-  std::uniform_real_distribution<double> uni(0.0, 1.0);
-  for (size_t i = 0; i < n; ++i) {
-    double u = uni(rng);
-    if (u < 1e-300) u = 1e-300;
-    int l = (int)(-std::log(u) * bp.mult);  // getRandomLevel, hnsw.h:476-480
-    if (l > 30) l = 30;
-    b.level[i] = l;
-    b.links[i].resize(l + 1);
-  }
+  b.level = hnsw_assign_levels(n, bp.mult);
+  for (size_t i = 0; i < n; ++i) b.links[i].resize(b.level[i] + 1);
   int threads = bp.threads > 0 ? bp.threads : (int)std::thread::hardware_concurrency();
   if (threads < 1) threads = 1;
   if (n < 2048) threads = 1;

@@ -63,7 +63,9 @@ class Stats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("kernel_launches", C.c_uint64), ("distance_evals", C.c_uint64),
                 ("hnsw_expansions", C.c_uint64), ("last_kernel_ms", C.c_double), ("last_total_ms", C.c_double),
                 ("fallback_queries", C.c_uint64), ("device_bytes", C.c_uint64), ("last_scan_ms", C.c_double),
-                ("scan_ms_sum", C.c_double), ("scan_count", C.c_uint64)]
+                ("scan_ms_sum", C.c_double), ("scan_count", C.c_uint64), ("build_total_ms", C.c_double),
+                ("build_scan_ms", C.c_double), ("build_select_ms", C.c_double), ("build_link_ms", C.c_double),
+                ("build_batches", C.c_uint64), ("build_prunes", C.c_uint64)]
 
 
 # every symbol include/nmslib_b200.h declares (the CPU-side test checks this list against the header)

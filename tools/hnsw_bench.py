@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--shape", default="gist")
     ap.add_argument("--efs", default="50,100,200,400")
     ap.add_argument("--cpu-queries", type=int, default=2000)
+    ap.add_argument("--build", default="ref", choices=["ref", "device"],
+                    help="ref: graph built by the unmodified reference and imported (same-graph parity run); "
+                         "device: graph built by csrc/hnsw_build_gpu.cu (recall-parity run, no reference timing)")
     args = ap.parse_args()
     threads = os.cpu_count() or 1
     if args.shape == "gist":
@@ -45,11 +48,13 @@ def main():
     else:
         data, q = synth.embedding_like(args.n, args.dim, 9), synth.embedding_like(args.nq, args.dim, 10)
 
-    t0 = time.perf_counter()
-    ref = O.RefIndex(args.space, "hnsw").add(data).build(f"M=16,efConstruction=200,indexThreadQty={threads}")
-    build_s = time.perf_counter() - t0
-    path = "/tmp/nb200_bench.hnsw"
-    ref.save(path)
+    ref = None
+    if args.build == "ref":
+        t0 = time.perf_counter()
+        ref = O.RefIndex(args.space, "hnsw").add(data).build(f"M=16,efConstruction=200,indexThreadQty={threads}")
+        build_s = time.perf_counter() - t0
+        path = "/tmp/nb200_bench.hnsw"
+        ref.save(path)
 
     # ground truth from the exact GPU scan (itself parity-tested against the oracle)
     ex = nb.Index(args.space, None, "seq_search")
@@ -59,8 +64,18 @@ def main():
     ex.deinit()
 
     idx = nb.Index(args.space, None, "hnsw")
-    idx.importHnsw(path)
-    idx.prepare()
+    build_info = {}
+    if ref is not None:
+        idx.importHnsw(path)
+        idx.prepare()
+    else:
+        idx.addDenseBatch(data)
+        idx.buildIndex(nb.Params({"M": 16, "efConstruction": 200, "b200_build": "device"}))
+        t0 = time.perf_counter()
+        idx.prepare()                      # upload + device build
+        build_s = time.perf_counter() - t0
+        st = idx.stats()
+        build_info = {k_: st[k_] for k_ in st if k_.startswith("build_")}
     out = []
     for ef in [int(e) for e in args.efs.split(",")]:
         idx.setQueryTimeParams(nb.Params({"efSearch": ef}))
@@ -75,11 +90,21 @@ def main():
         evals = s1["distance_evals"] - s0["distance_evals"]
         exps = s1["hnsw_expansions"] - s0["hnsw_expansions"]
         gbytes = (evals * 4.0 * args.dim + exps * 4.0 * 32) / 1e9
-        ref.set_query_params(f"efSearch={ef}")
         nqc = min(args.cpu_queries, args.nq)
-        t0 = time.perf_counter()
-        ri, rd, rc = ref.knn(q[:nqc], args.k, threads=threads)
-        cpu_s = time.perf_counter() - t0
+        if ref is not None:
+            ref.set_query_params(f"efSearch={ef}")
+            t0 = time.perf_counter()
+            ri, rd, rc = ref.knn(q[:nqc], args.k, threads=threads)
+            cpu_s = time.perf_counter() - t0
+        else:
+            line = {"space": args.space, "n": args.n, "dim": args.dim, "nq": args.nq, "k": args.k, "ef": ef,
+                    "graph": "device-built", "recall_gpu": recall(r.ids, exact_ids),
+                    "gpu_kernel_ms": kern_ms, "gpu_kernel_qps": args.nq / (kern_ms * 1e-3),
+                    "gpu_e2e_qps": args.nq / e2e_s, "evals_per_query": evals / args.nq,
+                    "expansions_per_query": exps / args.nq, "gather_GBps": gbytes / (kern_ms * 1e-3),
+                    "build_s_device_incl_upload": build_s, **build_info}
+            print(json.dumps(line), flush=True)
+            continue
         line = {"space": args.space, "n": args.n, "dim": args.dim, "nq": args.nq, "k": args.k, "ef": ef,
                 "recall_gpu": recall(r.ids, exact_ids), "recall_ref": recall(ri, exact_ids[:nqc]),
                 "recall_gpu_same_queries": recall(r.ids[:nqc], exact_ids[:nqc]),
