@@ -727,6 +727,7 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   const int q_blocks = (int)(q_pad / qb);
   // equal linear ranges of the (query block x tile) grid, one CTA per SM (scan_tc.cu tc_plan)
   const bool ts = tc_ts_supported(row_words_);  // rows <= 128 floats: queries live in tensor memory
+  const bool pair = !ts && tc_pair_enabled() && sm_count_ >= 2;
   int n_cta, work_per_cta = 0, s_max, aligned = 0;
   if (ts) {
     if (plan_key_[0] != nq || plan_key_[1] != n_dev_ || plan_key_[2] != k) {
@@ -741,6 +742,9 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     }
     n_cta = plan_n_cta_;
     s_max = plan_s_max_;
+  } else if (pair) {  // long rows: CTA pairs, two candidate lists (column halves) per piece
+    tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_ / 2, tc_pair_block_points(), &n_cta, &work_per_cta, &s_max, &aligned, 2);
+    s_max *= 2;
   } else {
     tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_, bn, &n_cta, &work_per_cta, &s_max, &aligned);
   }
@@ -781,12 +785,12 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
                    "tc_prep_queries");
     if (!s.ok()) return s;
     scan_begin(stream);
-    s = check_cuda(launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad,
-                                  mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(), (int)n_dev_,
-                                  (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
-                                  kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
-                                  d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream),
-                   "tc_scan");
+    s = check_cuda((pair ? launch_tc_scan_pair : launch_tc_scan)(
+                       d_qa_.as<float>(), q_pad, dbB, n_pad, mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr,
+                       d_ones_.as<float>(), (int)n_dev_, (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta,
+                       s_max, aligned, kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                       d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream),
+                   pair ? "tc_scan_pair" : "tc_scan");
     scan_end(stream);
     if (!s.ok()) return s;
     stats_.kernel_launches += 3;

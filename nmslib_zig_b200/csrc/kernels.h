@@ -57,7 +57,16 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
                               int* inexact_flag, cudaStream_t stream);
 // balanced (query block x tile) decomposition: CTAs, work items per CTA, candidate pieces per query block
 // bn = database rows per tile of the kernel that will run (tc_block_points() or tc_ts_block_points())
-void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned);
+void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned,
+             int lists_per_piece = 1);
+// long rows on CTA pairs (cta_group::2 MMAs, M256 x N256): plan with tc_plan(nq, n, k, sm_count / 2,
+// tc_pair_block_points(), &n_pairs, &work_per_pair, &pieces, &aligned, 2) and pass s_max = 2 * pieces
+bool tc_pair_enabled();   // NB200_TC_PAIR=0 switches back to the single-CTA kernel (A/B runs)
+int tc_pair_block_points();
+cudaError_t launch_tc_scan_pair(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
+                                const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_pairs,
+                                int work_per_pair, int s_max, int aligned, int kprime, uint64_t* cand, int* cand_cnt,
+                                float* cand_thr, uint32_t* gthr, cudaStream_t stream);
 // rows of at most 128 floats: the prepared queries live in tensor memory (tc_scan_ts_kernel); q = the ORIGINAL
 // queries [q_pad][row_words], scaled on the fly; sets *inexact_flag when a valid query row is not TF32-exact
 bool tc_ts_supported(int row_words);

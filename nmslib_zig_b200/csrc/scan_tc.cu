@@ -657,6 +657,328 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------- K1 for long rows on CTA PAIRS (cta_group::2)
+// Same contract as tc_scan_kernel, for rows of more than 128 floats.  Measured on the config-5 shape
+// (profiles/README.md): the single-CTA kernel streams 48 KB (16 KB of database + 32 KB of query tile) through
+// the L2 for every 8 M128 x N128 x K8 MMAs, which is what bounds it (~12 TB/s chip-wide), and with both operands
+// in shared memory each of those MMAs takes 96 cycles instead of 64 because the operand reads saturate the
+// shared-memory port.  A CTA pair (two SMs of one TPC) issues ONE M256 x N256 x K8 MMA for both SMs:
+//   * CTA r holds query rows [r*128, r*128+128) of the 256-query block (A) and database rows
+//     [t*256 + r*128, +128) of the 256-row tile (its half of B); the tensor cores read B from both SMs, so a
+//     k-block costs each SM 16 KB + 16 KB from the L2 instead of 48 KB for the same number of MACs, and each
+//     MMA reads 8 KB of shared memory per SM for twice the work;
+//   * accumulators: 128 lanes x 256 columns per SM, two buffers = the whole tensor memory;
+//   * only the leader (cluster rank 0) issues MMAs; both CTAs issue their own TMA loads, which signal the
+//     LEADER's full barrier; the leader's commits are multicast to both CTAs' empty / tfull barriers; the
+//     epilogue warps of both CTAs release an accumulator buffer by arriving on the leader's tempty barrier.
+// The epilogue is the one of tc_scan_kernel: thread = query row, warps 2-5 select over columns 0-127 and warps
+// 6-9 over columns 128-255 of the tile, each (row, column half) with its own candidate list.
+constexpr int TP_BN = 256;  // database rows per pair tile
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAITC_DONE;\n\t"
+      "bra WAITC_LOOP;\n\t"
+      "WAITC_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// this CTA's box into its own shared memory, completion bytes on the barrier at cluster address `bar_cluster`
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// TcParams as for tc_scan_kernel with: n_tiles = 256-row tiles, work_per_cta / total_work / aligned = the plan over
+// PAIRS (blockIdx.x / 2), s_max = candidate lists per query block = 2 x the pairs that may share a block.
+template <int KPL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmN, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: [ones chunk] [stages: n_stage * (B half + A half)] [barriers]  (identical offsets in both CTAs)
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int ones_bytes = p.use_nb ? CHUNK_BYTES : 0;
+  constexpr int stage_bytes = 2 * CHUNK_BYTES;
+  unsigned char* smem_ones = smem;
+  unsigned char* smem_st = smem + ones_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + (size_t)p.n_stage * stage_bytes);
+  uint64_t* full_bar = bars;                   // [n_stage] leader: both CTAs' loads of the stage have landed
+  uint64_t* empty_bar = bars + p.n_stage;      // [n_stage] each CTA: the MMAs have read the stage
+  uint64_t* tfull_bar = bars + 2 * p.n_stage;  // [2] each CTA: accumulators of a tile are complete
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] leader: both CTAs' epilogue warps have drained the buffer
+  uint64_t* ones_bar = tempty_bar + 2;         // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ones_bar + 1);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(FULL, tid >> 5, 0), lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  long w_begin, w_end;
+  if (p.aligned) {
+    const int qb_a = pair % p.q_blocks, seg = pair / p.q_blocks;
+    w_begin = (long)qb_a * p.n_tiles + min((long)seg * p.work_per_cta, (long)p.n_tiles);
+    w_end = (long)qb_a * p.n_tiles + min((long)(seg + 1) * p.work_per_cta, (long)p.n_tiles);
+  } else {
+    w_begin = (long)pair * p.work_per_cta;
+    w_end = min(w_begin + (long)p.work_per_cta, (long)p.total_work);
+  }
+  const int n_kb_all = p.n_kb + p.use_nb;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.n_stage; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 16);  // 8 epilogue warps of each CTA
+    }
+    mbar_init(ones_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (p.use_nb) prefetch_tmap(&tmN);
+  }
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before anything remote touches them
+  if (warp == 1) tmem_alloc_2sm(tmem_holder, 512);
+  if (warp == 0 && p.use_nb) {  // the constant tile of ones (A operand of the |x|^2 step), one copy per CTA
+    if (elect_one()) {
+      mbar_expect_tx(ones_bar, CHUNK_BYTES);
+      tma_load_2d(&tmO, ones_bar, smem_ones, 0, 0);
+    }
+    __syncwarp();
+    mbar_wait(ones_bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // tensor memory allocated and the ones tiles resident in BOTH CTAs before the first MMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; completion bytes go to the leader's full barrier) ==========
+    if (w_begin < w_end) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long w = w_begin; w < w_end;) {
+        const int qb = (int)(w / p.n_tiles);
+        const int t_begin = (int)(w - (long)qb * p.n_tiles);
+        const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
+        const int q0 = qb * TC_QB + (int)rank * TC_BM;
+        for (int t = t_begin; t < t_end; ++t) {
+          const int r0 = t * TP_BN + (int)rank * TC_BM;
+          for (int kb = 0; kb < n_kb_all; ++kb) {
+            mbar_wait_cluster(&empty_bar[s], ph ^ 1);
+            unsigned char* st = smem_st + (size_t)s * stage_bytes;
+            const uint32_t fb = mapa_cluster(smem_u32(&full_bar[s]), 0);
+            if (elect_one()) {
+              if (kb < p.n_kb) {
+                if (leader) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)stage_bytes);
+                tma_load_2d_2sm(&tmB, fb, st, kb * TC_KB, r0);
+                tma_load_2d_2sm(&tmA, fb, st + CHUNK_BYTES, kb * TC_KB, q0);
+              } else {  // the |x|^2 block of this CTA's half of the tile
+                if (leader) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)CHUNK_BYTES);
+                tma_load_2d_2sm(&tmN, fb, st, 0, r0);
+              }
+            }
+            __syncwarp();
+            if (++s == p.n_stage) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+        w += t_end - t_begin;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && w_begin < w_end) {
+      constexpr uint32_t idesc = make_idesc_tf32(2 * TC_BM, TP_BN);
+      const uint32_t st_base = smem_u32(smem_st);
+      const uint64_t d_ones = make_smem_desc(smem_u32(smem_ones));
+      int s = 0;
+      uint32_t ph = 0;
+      int ti = 0;
+      for (long w = w_begin; w < w_end;) {
+        const int qb = (int)(w / p.n_tiles);
+        const int t_begin = (int)(w - (long)qb * p.n_tiles);
+        const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
+        for (int t = t_begin; t < t_end; ++t, ++ti) {
+          const int b = ti & 1;
+          mbar_wait_cluster(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d0 = tmem_base + (uint32_t)(b * TP_BN);
+          for (int kb = 0; kb < p.n_kb; ++kb) {
+            mbar_wait_cluster(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
+            const uint64_t db = make_smem_desc(sb);
+            const uint64_t da = make_smem_desc(sb + CHUNK_BYTES);
+            const uint32_t acc = kb != 0;
+            if (elect_one()) {
+              umma_tf32_2sm(tmem_d0, da, db, idesc, acc);
+              umma_tf32_2sm(tmem_d0, da + 2, db + 2, idesc, 1);
+              umma_tf32_2sm(tmem_d0, da + 4, db + 4, idesc, 1);
+              umma_tf32_2sm(tmem_d0, da + 6, db + 6, idesc, 1);
+              tc_commit_2sm(&empty_bar[s], 3);  // frees the stage in both CTAs once these MMAs have read it
+            }
+            __syncwarp();
+            if (++s == p.n_stage) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+          if (p.use_nb) {  // + 1.0 * (hi + mid + lo pieces of |x|^2)
+            mbar_wait_cluster(&full_bar[s], ph);
+            tc_fence_after();
+            const uint64_t db = make_smem_desc(st_base + (uint32_t)s * (uint32_t)stage_bytes);
+            if (elect_one()) {
+              umma_tf32_2sm(tmem_d0, d_ones, db, idesc, 1);
+              tc_commit_2sm(&empty_bar[s], 3);
+            }
+            __syncwarp();
+            if (++s == p.n_stage) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+          if (elect_one()) tc_commit_2sm(&tfull_bar[b], 3);  // accumulators of this tile are complete, in both CTAs
+          __syncwarp();
+        }
+        w += t_end - t_begin;
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps per CTA, thread == one query row x one column half ==========
+    const int e = warp - 2;
+    const int ch = e >> 2;                     // column half of the 256-row tile
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may touch
+    const int row = quarter * 32 + lane;       // row inside this CTA's 128 queries
+    const int row_in_block = (int)rank * TC_BM + row;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t te_addr0 = mapa_cluster(smem_u32(&tempty_bar[0]), 0), te_addr1 = mapa_cluster(smem_u32(&tempty_bar[1]), 0);
+    float tk_unused[TS_RK] = {};
+    unsigned ctr[4] = {0, 0, 0, 0};
+
+    int ti = 0;
+    for (long w = w_begin; w < w_end;) {
+      const int qb = (int)(w / p.n_tiles);
+      const int t_begin = (int)(w - (long)qb * p.n_tiles);
+      const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
+      const int first_pair = (int)(((long)qb * p.n_tiles) / p.work_per_cta);
+      const size_t unit = (size_t)qb * p.s_max + 2 * (p.aligned ? pair / p.q_blocks : pair - first_pair) + ch;
+      const bool row_valid = qb * TC_QB + row_in_block < p.nq;
+      uint64_t* buf = p.cand + (unit * TC_QB + row_in_block) * (size_t)p.cap;
+      uint32_t* gthr = p.gthr + (qb * TC_QB + row_in_block);
+      int cnt = 0;
+      float thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+      for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
+        const int b = ti & 1;
+        mbar_wait_cluster(&tfull_bar[b], (ti >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tcol = trow + (uint32_t)(b * TP_BN + ch * TC_BN);
+        const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TP_BN + ch * TC_BN);
+        const int vtile = p.n - tile * TP_BN - ch * TC_BN;  // >= 128 except at the end of the shard
+        uint32_t v0[32], v1[32];
+        if (p.debug & 1) {  // timing experiment: touch the accumulators, select nothing
+          tmem_ld32(tcol, v0);
+          tmem_ld_wait();
+          if (__uint_as_float(v0[0]) == 1.2345e-30f) thr = 0.f;
+        } else {
+          if (((tile - t_begin) & 7) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
+          tmem_ld32(tcol, v0);
+#pragma unroll 1
+          for (int cp = 0; cp < TC_BN / 64; ++cp) {
+            tmem_ld_wait();
+            tmem_ld32(tcol + (uint32_t)(cp * 64 + 32), v1);
+            epi_process<KPL, false>(v0, pos_tile + cp * 64, vtile - cp * 64, buf, cnt, thr, tk_unused, p.cap, p.kprime,
+                                    p.slack, gthr, lane, ctr);
+            tmem_ld_wait();
+            if (cp + 1 < TC_BN / 64) tmem_ld32(tcol + (uint32_t)(cp * 64 + 64), v0);
+            epi_process<KPL, false>(v1, pos_tile + cp * 64 + 32, vtile - cp * 64 - 32, buf, cnt, thr, tk_unused, p.cap,
+                                    p.kprime, p.slack, gthr, lane, ctr);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(b ? te_addr1 : te_addr0);  // this warp is done with the buffer (one arrival per warp)
+        if (!(p.debug & 1)) {
+          const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);
+          if (pend) compact_lane<KPL>(__ffs(pend) - 1, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
+        }
+      }
+      const size_t slot = unit * TC_QB + row_in_block;
+      p.cand_cnt[slot] = row_valid ? cnt : 0;
+      p.cand_thr[slot] = thr;
+      w += t_end - t_begin;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's MMAs / loads / arrivals that touch this CTA are all done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------- K1 for D <= 128: A operand in tensor memory
 // Same contract as tc_scan_kernel, different data path.  Measured on config 2 (profiles/README.md): with both
 // operands in shared memory an M=128 x N=128 x K=8 TF32 MMA takes ~96 cycles instead of the 64-cycle floor
@@ -1365,14 +1687,16 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
 //  * aligned: every query block is cut into the same `s` segments; q_blocks * s CTAs.  Chosen when some s
 //    fills >= 80 % of the last wave: co-scheduled CTAs then stream the same tiles and share them in L2.
 //  * linear (few query blocks): equal linear ranges, `sm_count` CTAs, a CTA may span two query blocks.
-void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned) {
+void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned,
+             int lists_per_piece) {
   int kprime, cap;
   tc_candidate_shape(k, &kprime, &cap);
   const long q_blocks = (nq + TC_QB - 1) / TC_QB;
   const long n_tiles = (n + bn - 1) / bn;
   const long total = q_blocks * n_tiles;
   // the re-rank sorts s_max * cap keys per query in shared memory: bound the pieces per query block
-  const long max_pieces = std::min<long>(std::min<long>(64, std::max<long>(2, 16384 / cap)), std::max<long>(4, 3072 / kprime));
+  long max_pieces = std::min<long>(std::min<long>(64, std::max<long>(2, 16384 / cap)), std::max<long>(4, 3072 / kprime));
+  max_pieces = std::max<long>(1, max_pieces / std::max(1, lists_per_piece));  // (pair kernel: two lists per piece)
   if (q_blocks * 4 >= sm_count || q_blocks * n_tiles <= sm_count) {
     long best = 1;
     double best_eff = 0;
@@ -1496,6 +1820,82 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   if (e != cudaSuccess)
     fprintf(stderr, "nmslib_b200: tc_scan launch (grid %d, smem %zu, stages %d) failed: %s\n", n_cta, smem, p.n_stage,
             cudaGetErrorString(e));
+  return e;
+}
+
+bool tc_pair_enabled() {
+  static const bool off = [] {
+    const char* e = getenv("NB200_TC_PAIR");
+    return e && e[0] == '0';
+  }();
+  return !off;
+}
+int tc_pair_block_points() { return TP_BN; }
+
+// CTA-pair kernel for long rows: n_pairs / work_per_pair / aligned from tc_plan(.., sm_count / 2, TP_BN, .., 2);
+// s_max = candidate lists per query block = 2 x the plan's pieces per block
+cudaError_t launch_tc_scan_pair(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
+                                const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_pairs,
+                                int work_per_pair, int s_max, int aligned, int kprime, uint64_t* cand, int* cand_cnt,
+                                float* cand_thr, uint32_t* gthr, cudaStream_t stream) {
+  if (n <= 0 || nq <= 0) return cudaSuccess;
+  if (row_words % TC_KB) return cudaErrorInvalidValue;
+  CUtensorMap tmA, tmB, tmN, tmO;
+  if (!make_tmap(&tmA, qa, q_pad, row_words) || !make_tmap(&tmB, dbB, n_pad, row_words)) return cudaErrorUnknown;
+  const bool use_nb = nblock != nullptr;
+  if (use_nb) {
+    if (!make_tmap(&tmN, nblock, n_pad, TC_KB) || !make_tmap(&tmO, ones, TC_BM, TC_KB)) return cudaErrorUnknown;
+  } else {
+    tmN = tmB;
+    tmO = tmA;
+  }
+  TcParams p;
+  p.n = n;
+  p.nq = nq;
+  p.n_kb = row_words / TC_KB;
+  p.n_tiles = (n + TP_BN - 1) / TP_BN;
+  p.q_blocks = (nq + TC_QB - 1) / TC_QB;
+  p.work_per_cta = work_per_pair;
+  p.total_work = p.q_blocks * p.n_tiles;
+  p.s_max = s_max;
+  p.aligned = aligned;
+  p.pos_base = pos_base;
+  p.cand = cand;
+  p.cand_cnt = cand_cnt;
+  p.cand_thr = cand_thr;
+  int kp_default;
+  tc_candidate_shape(k, &kp_default, &p.cap);
+  p.kprime = std::max(k + 1, std::min(kprime, kp_default));
+  p.slack = std::max(8, p.kprime / 4);
+  p.hwm = std::min(p.cap / 2, std::max(64, 2 * p.kprime));
+  p.gthr = gthr;
+  p.use_nb = use_nb ? 1 : 0;
+  {
+    const char* dbg = getenv("NB200_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  p.a_resident = 0;
+  const int ones_bytes = use_nb ? CHUNK_BYTES : 0;
+  const int stage_bytes = 2 * CHUNK_BYTES;
+  const int budget = 214 * 1024;
+  p.n_stage = (budget - ones_bytes) / stage_bytes;
+  if (p.n_stage > 8) p.n_stage = 8;
+  const size_t smem = 1024 + (size_t)ones_bytes + (size_t)p.n_stage * stage_bytes + (2 * 8 + 8) * 8 + 16;
+  cudaError_t e;
+#define NB_TP(KPL)                                                                                            \
+  e = cudaFuncSetAttribute(tc_scan_pair_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e != cudaSuccess) return e;                                                                             \
+  tc_scan_pair_kernel<KPL><<<2 * n_pairs, TC_THREADS, smem, stream>>>(tmA, tmB, tmN, tmO, p);
+  if (p.cap == 256) {
+    NB_TP(8);
+  } else {
+    NB_TP(16);
+  }
+#undef NB_TP
+  e = cudaGetLastError();
+  if (e != cudaSuccess)
+    fprintf(stderr, "nmslib_b200: tc_scan_pair launch (grid %d, smem %zu, stages %d) failed: %s\n", 2 * n_pairs, smem,
+            p.n_stage, cudaGetErrorString(e));
   return e;
 }
 
