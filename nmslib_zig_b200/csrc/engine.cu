@@ -729,9 +729,10 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   const bool ts = tc_ts_supported(row_words_);  // rows <= 128 floats: queries live in tensor memory
   const bool pair = !ts && tc_pair_enabled() && sm_count_ >= 2;
   int n_cta, work_per_cta = 0, s_max, aligned = 0;
-  if (ts) {
+  if (ts || pair) {  // host-made piece table (pair: units are CTA pairs over 256-row tiles, two lists per piece)
     if (plan_key_[0] != nq || plan_key_[1] != n_dev_ || plan_key_[2] != k) {
-      tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &h_plan_, &plan_n_cta_, &plan_s_max_);
+      if (ts) tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &h_plan_, &plan_n_cta_, &plan_s_max_, 0, 1, &plan_single_);
+      else tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_ / 2, &h_plan_, &plan_n_cta_, &plan_s_max_, tc_pair_block_points(), 2, &plan_single_);
       if (!(s = check_cuda(d_plan_.ensure(h_plan_.size() * 4), "cudaMalloc(plan)")).ok()) return s;
       s = check_cuda(cudaMemcpyAsync(d_plan_.p, h_plan_.data(), h_plan_.size() * 4, cudaMemcpyHostToDevice, stream),
                      "H2D(plan)");
@@ -741,10 +742,7 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
       plan_key_[2] = k;
     }
     n_cta = plan_n_cta_;
-    s_max = plan_s_max_;
-  } else if (pair) {  // long rows: CTA pairs, two candidate lists (column halves) per piece
-    tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_ / 2, tc_pair_block_points(), &n_cta, &work_per_cta, &s_max, &aligned, 2);
-    s_max *= 2;
+    s_max = pair ? 2 * plan_s_max_ : plan_s_max_;
   } else {
     tc_plan((int)nq, (int)n_dev_, (int)k, sm_count_, bn, &n_cta, &work_per_cta, &s_max, &aligned);
   }
@@ -777,7 +775,7 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
                    "tc_scan_ts");
     scan_end(stream);
     if (!s.ok()) return s;
-    stats_.kernel_launches += 2;
+    stats_.kernel_launches += 1;  // (the re-rank launches are counted where they are made)
   } else {
     if (!(s = check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)")).ok()) return s;
     s = check_cuda(launch_tc_prep_queries(static_cast<const float*>(dq), d_qa_.as<float>(), q_pad * (size_t)row_words_,
@@ -785,25 +783,36 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
                    "tc_prep_queries");
     if (!s.ok()) return s;
     scan_begin(stream);
-    s = check_cuda((pair ? launch_tc_scan_pair : launch_tc_scan)(
-                       d_qa_.as<float>(), q_pad, dbB, n_pad, mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr,
-                       d_ones_.as<float>(), (int)n_dev_, (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta,
-                       s_max, aligned, kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
-                       d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream),
+    const float* nbp = mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr;
+    s = check_cuda(pair ? launch_tc_scan_pair(d_qa_.as<float>(), q_pad, dbB, n_pad, nbp, d_ones_.as<float>(), (int)n_dev_,
+                                              (int)nq, row_words_, (int)k, pos_base_, n_cta, d_plan_.as<int>(), s_max,
+                                              kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                                              d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream)
+                        : launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad, nbp, d_ones_.as<float>(), (int)n_dev_,
+                                         (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
+                                         kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
+                                         d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream),
                    pair ? "tc_scan_pair" : "tc_scan");
     scan_end(stream);
     if (!s.ok()) return s;
-    stats_.kernel_launches += 3;
+    stats_.kernel_launches += 2;
   }
-  s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
-                                  mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)n_dev_, (int)nq, row_words_,
-                                  (int)k, s_max, space_ == SPACE_ANGULAR ? SCAN_ANGULAR : mode, pos_base_,
-                                  d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
-                                  d_cand_thr_.as<float>(), approx_ok_ ? 0.f : x_max_, d_flags_.as<int>(), out_keys,
-                                  d_cert_.as<int>(),
-                                  stream),
-                 "tc_rerank");
-  if (!s.ok()) return s;
+  // whole-wave query blocks are scanned as one piece: their re-rank only has lists_per_piece lists to read (a small
+  // sort buffer, many blocks per SM); the blocks behind them were cut into up to s_max lists
+  const size_t q_single = (ts || pair) ? std::min(nq, (size_t)plan_single_ * qb) : 0;
+  for (int part = 0; part < 2; ++part) {
+    const size_t qb0 = part == 0 ? 0 : q_single, qc = part == 0 ? q_single : nq - q_single;
+    if (qc == 0) continue;
+    s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
+                                    mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)n_dev_, (int)nq, row_words_,
+                                    (int)k, s_max, space_ == SPACE_ANGULAR ? SCAN_ANGULAR : mode, pos_base_,
+                                    d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(),
+                                    approx_ok_ ? 0.f : x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(), stream,
+                                    (int)qb0, (int)qc, part == 0 ? (pair ? 2 : 1) : s_max),
+                   "tc_rerank");
+    if (!s.ok()) return s;
+    ++stats_.kernel_launches;
+  }
   // certificates back to the host; re-run the (normally empty) set of uncertified queries exactly
   s = check_cuda(cudaMemcpyAsync(h_cert_.p, d_cert_.p, nq * 4, cudaMemcpyDeviceToHost, stream), "D2H(cert)");
   if (!s.ok()) return s;

@@ -217,7 +217,7 @@ class Engine {
   DevBuf d_plan_;                       // piece table of the TS scan (tc_ts_plan), cached per (nq, n, k)
   std::vector<int> h_plan_;
   size_t plan_key_[3] = {0, 0, 0};
-  int plan_n_cta_ = 0, plan_s_max_ = 0;
+  int plan_n_cta_ = 0, plan_s_max_ = 0, plan_single_ = 0;
   DevBuf d_bias_, d_db_unit_, d_flags_, d_qa_, d_cand_, d_cand_cnt_, d_cand_thr_, d_tc_keys_, d_cert_, d_fb_idx_,
       d_fb_q_, d_fb_keys_, d_nblock_, d_ones_;
   PinBuf h_cert_;

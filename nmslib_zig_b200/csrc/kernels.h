@@ -59,20 +59,23 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
 // bn = database rows per tile of the kernel that will run (tc_block_points() or tc_ts_block_points())
 void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned,
              int lists_per_piece = 1);
-// long rows on CTA pairs (cta_group::2 MMAs, M256 x N256): plan with tc_plan(nq, n, k, sm_count / 2,
-// tc_pair_block_points(), &n_pairs, &work_per_pair, &pieces, &aligned, 2) and pass s_max = 2 * pieces
+// long rows on CTA pairs (cta_group::2 MMAs, M256 x N256): plan with tc_ts_plan(nq, n, k, sm_count / 2, &table,
+// &n_pairs, &slots, tc_pair_block_points(), 2), upload the table and pass s_max = 2 * slots
 bool tc_pair_enabled();   // NB200_TC_PAIR=0 switches back to the single-CTA kernel (A/B runs)
 int tc_pair_block_points();
 cudaError_t launch_tc_scan_pair(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
                                 const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_pairs,
-                                int work_per_pair, int s_max, int aligned, int kprime, uint64_t* cand, int* cand_cnt,
+                                const int* d_pieces, int s_max, int kprime, uint64_t* cand, int* cand_cnt,
                                 float* cand_thr, uint32_t* gthr, cudaStream_t stream);
 // rows of at most 128 floats: the prepared queries live in tensor memory (tc_scan_ts_kernel); q = the ORIGINAL
 // queries [q_pad][row_words], scaled on the fly; sets *inexact_flag when a valid query row is not TF32-exact
 bool tc_ts_supported(int row_words);
 int tc_ts_block_points();
 // table: n_cta * 8 pieces of {query block, first tile, end tile, candidate slot} (query block -1 ends a CTA's list)
-void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int* n_cta, int* s_max);
+// bn: rows per tile (0 = the TS kernel's); lists_per_piece: candidate lists a piece fills (2 for the pair kernel)
+// single_blocks: number of leading query blocks scanned as one piece (their re-rank reads lists_per_piece lists)
+void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int* n_cta, int* s_max, int bn = 0,
+                int lists_per_piece = 1, int* single_blocks = nullptr);
 // kprime: survivors of a compaction (k + margin; the certificate needs the margin); gthr: [q_pad] uint32, filled
 // with 0xFF by the caller before every launch (best threshold published per query, shared by all CTAs)
 cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, const float* nblock, const float* ones,
@@ -90,7 +93,9 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
 cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int n, int nq,
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
-                             uint64_t* out_keys, int* out_cert, cudaStream_t stream);  // mode may be SCAN_ANGULAR
+                             uint64_t* out_keys, int* out_cert, cudaStream_t stream,  // mode may be SCAN_ANGULAR
+                             int q_begin = 0, int q_count = -1, int n_lists = -1);  // a query range whose blocks use
+                                                                                    // only the first n_lists lists
 
 // ---- range_scan.cu (one query, every row within the radius, in position order) ----------
 // dist_tmp: [n] scratch; out_ids / out_dists: [capacity] device buffers; *out_count <= capacity

@@ -369,6 +369,7 @@ struct TcParams {
   int use_nb;              // 1: an extra K=8 step adds |x|^2 (three TF32 pieces x 1.0) inside the MMA (l2)
   int aligned;             // 1: CTA = (segment, query block) with common tile boundaries; 0: equal linear ranges
   int debug;               // NB200_TC_DEBUG bit 0: epilogue drains TMEM without selecting (timing experiments only)
+  const int4* pieces;      // pair kernel: [pairs][TS_MAXP] {query block, first tile, end tile, slot} (tc_ts_plan)
 };
 
 // Work decomposition: the (query block, database tile) grid is cut into `gridDim.x` equal linear
@@ -674,6 +675,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // The epilogue is the one of tc_scan_kernel: thread = query row, warps 2-5 select over columns 0-127 and warps
 // 6-9 over columns 128-255 of the tile, each (row, column half) with its own candidate list.
 constexpr int TP_BN = 256;  // database rows per pair tile
+constexpr int TS_MAXP = 8;  // pieces per CTA (or CTA pair) in a plan table (tc_ts_plan)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -739,8 +741,8 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
       : "memory");
 }
 
-// TcParams as for tc_scan_kernel with: n_tiles = 256-row tiles, work_per_cta / total_work / aligned = the plan over
-// PAIRS (blockIdx.x / 2), s_max = candidate lists per query block = 2 x the pairs that may share a block.
+// TcParams as for tc_scan_kernel with: pieces = the host-made table of (query block, 256-row tile range, slot) per
+// PAIR (blockIdx.x / 2; tc_ts_plan over sm_count / 2 units), s_max = candidate lists per query block = 2 x slots.
 template <int KPL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -764,15 +766,7 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  long w_begin, w_end;
-  if (p.aligned) {
-    const int qb_a = pair % p.q_blocks, seg = pair / p.q_blocks;
-    w_begin = (long)qb_a * p.n_tiles + min((long)seg * p.work_per_cta, (long)p.n_tiles);
-    w_end = (long)qb_a * p.n_tiles + min((long)(seg + 1) * p.work_per_cta, (long)p.n_tiles);
-  } else {
-    w_begin = (long)pair * p.work_per_cta;
-    w_end = min(w_begin + (long)p.work_per_cta, (long)p.total_work);
-  }
+  const int4* my_pieces = p.pieces + (size_t)pair * TS_MAXP;  // host-made table: every pair gets the same number of tiles
   const int n_kb_all = p.n_kb + p.use_nb;
 
   if (tid == 0) {
@@ -812,13 +806,13 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; completion bytes go to the leader's full barrier) ==========
-    if (w_begin < w_end) {
+    {
       int s = 0;
       uint32_t ph = 0;
-      for (long w = w_begin; w < w_end;) {
-        const int qb = (int)(w / p.n_tiles);
-        const int t_begin = (int)(w - (long)qb * p.n_tiles);
-        const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
+      for (int pi = 0; pi < TS_MAXP; ++pi) {
+        const int4 pc = my_pieces[pi];
+        if (pc.x < 0) break;
+        const int qb = pc.x, t_begin = pc.y, t_end = pc.z;
         const int q0 = qb * TC_QB + (int)rank * TC_BM;
         for (int t = t_begin; t < t_end; ++t) {
           const int r0 = t * TP_BN + (int)rank * TC_BM;
@@ -843,22 +837,21 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        w += t_end - t_begin;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && w_begin < w_end) {
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_tf32(2 * TC_BM, TP_BN);
       const uint32_t st_base = smem_u32(smem_st);
       const uint64_t d_ones = make_smem_desc(smem_u32(smem_ones));
       int s = 0;
       uint32_t ph = 0;
       int ti = 0;
-      for (long w = w_begin; w < w_end;) {
-        const int qb = (int)(w / p.n_tiles);
-        const int t_begin = (int)(w - (long)qb * p.n_tiles);
-        const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
+      for (int pi = 0; pi < TS_MAXP; ++pi) {
+        const int4 pc = my_pieces[pi];
+        if (pc.x < 0) break;
+        const int t_begin = pc.y, t_end = pc.z;
         for (int t = t_begin; t < t_end; ++t, ++ti) {
           const int b = ti & 1;
           mbar_wait_cluster(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
@@ -901,7 +894,6 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (elect_one()) tc_commit_2sm(&tfull_bar[b], 3);  // accumulators of this tile are complete, in both CTAs
           __syncwarp();
         }
-        w += t_end - t_begin;
       }
     }
   } else {
@@ -917,12 +909,11 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     unsigned ctr[4] = {0, 0, 0, 0};
 
     int ti = 0;
-    for (long w = w_begin; w < w_end;) {
-      const int qb = (int)(w / p.n_tiles);
-      const int t_begin = (int)(w - (long)qb * p.n_tiles);
-      const int t_end = (int)min((long)p.n_tiles, t_begin + (w_end - w));
-      const int first_pair = (int)(((long)qb * p.n_tiles) / p.work_per_cta);
-      const size_t unit = (size_t)qb * p.s_max + 2 * (p.aligned ? pair / p.q_blocks : pair - first_pair) + ch;
+    for (int pi = 0; pi < TS_MAXP; ++pi) {
+      const int4 pc = my_pieces[pi];
+      if (pc.x < 0) break;
+      const int qb = pc.x, t_begin = pc.y, t_end = pc.z;
+      const size_t unit = (size_t)qb * p.s_max + 2 * pc.w + ch;
       const bool row_valid = qb * TC_QB + row_in_block < p.nq;
       uint64_t* buf = p.cand + (unit * TC_QB + row_in_block) * (size_t)p.cap;
       uint32_t* gthr = p.gthr + (qb * TC_QB + row_in_block);
@@ -966,7 +957,6 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const size_t slot = unit * TC_QB + row_in_block;
       p.cand_cnt[slot] = row_valid ? cnt : 0;
       p.cand_thr[slot] = thr;
-      w += t_end - t_begin;
     }
   }
 
@@ -994,7 +984,6 @@ constexpr int TS_BN = 64;                 // database rows per tile
 constexpr int TS_CHUNK = TS_BN * 128;     // 8 KB: 64 rows x one 128-byte k-block
 constexpr int TS_ACC0 = 256;              // first accumulator column
 
-constexpr int TS_MAXP = 8;                // pieces per CTA in the plan table
 
 struct TsParams {
   int n, nq, n_kb;
@@ -1316,6 +1305,7 @@ struct RerankParams {
   const float* queries;    // [q_pad][row_words] ORIGINAL queries
   const float* db_norm2;   // [n_pad] |x|^2 (cosine) or NULL
   int nq, row_words, k, n_split, cap, mode;  // mode: SCAN_L2 / SCAN_COSINE / SCAN_NEGDOT
+  int q_begin, n_lists;    // this launch serves queries q_begin + blockIdx.x; only the first n_lists slots can be in use
   uint32_t pos_base;
   const uint64_t* cand;
   const int* cand_cnt;
@@ -1343,7 +1333,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   __shared__ int s_red[4];
   __shared__ int s_live;
   __shared__ float s_wmin[2], s_qn2;
-  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = p.q_begin + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qb = q / TC_QB, row = q % TC_QB;
   const float* qv = p.queries + (size_t)q * p.row_words;
 
@@ -1351,7 +1341,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   if (tid < 64) {
     float mt = __int_as_float(0x7F800000);
     int c = 0;
-    if (tid < p.n_split) {
+    if (tid < p.n_lists) {
       const size_t slot = ((size_t)qb * p.n_split + tid) * TC_QB + row;
       c = p.cand_cnt[slot];   // -1: slot unused (the host fills the array with 0xFF)
       if (c >= 0) mt = p.cand_thr[slot];  // +inf when the piece never dropped anything
@@ -1376,7 +1366,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   // the certificate below holds, every true neighbour has pass-1 rank < minthr, and if it does not
   // hold the query is re-run anyway.  With shared thresholds this is ~k' keys out of the few hundred appended.
   // One warp per slot (round robin), so the slots' lists are read concurrently.
-  for (int s = warp; s < p.n_split; s += 4) {
+  for (int s = warp; s < p.n_lists; s += 4) {
     const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
     const uint64_t* cb = p.cand + slot * (size_t)p.cap;
     const int c = s_cnt[s];
@@ -1796,6 +1786,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
     const char* dbg = getenv("NB200_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  p.pieces = nullptr;
   p.a_resident = (2 * p.n_kb * CHUNK_BYTES <= 128 * 1024) ? 1 : 0;
   const int a_bytes = p.a_resident ? 2 * p.n_kb * CHUNK_BYTES : 0;
   const int ones_bytes = use_nb ? CHUNK_BYTES : 0;
@@ -1832,11 +1823,11 @@ bool tc_pair_enabled() {
 }
 int tc_pair_block_points() { return TP_BN; }
 
-// CTA-pair kernel for long rows: n_pairs / work_per_pair / aligned from tc_plan(.., sm_count / 2, TP_BN, .., 2);
-// s_max = candidate lists per query block = 2 x the plan's pieces per block
+// CTA-pair kernel for long rows: d_pieces / n_pairs from tc_ts_plan(nq, n, k, sm_count / 2, .., TP_BN, 2);
+// s_max = candidate lists per query block = 2 x the plan's slots per block
 cudaError_t launch_tc_scan_pair(const float* qa, size_t q_pad, const float* dbB, size_t n_pad, const float* nblock,
                                 const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_pairs,
-                                int work_per_pair, int s_max, int aligned, int kprime, uint64_t* cand, int* cand_cnt,
+                                const int* d_pieces, int s_max, int kprime, uint64_t* cand, int* cand_cnt,
                                 float* cand_thr, uint32_t* gthr, cudaStream_t stream) {
   if (n <= 0 || nq <= 0) return cudaSuccess;
   if (row_words % TC_KB) return cudaErrorInvalidValue;
@@ -1855,10 +1846,11 @@ cudaError_t launch_tc_scan_pair(const float* qa, size_t q_pad, const float* dbB,
   p.n_kb = row_words / TC_KB;
   p.n_tiles = (n + TP_BN - 1) / TP_BN;
   p.q_blocks = (nq + TC_QB - 1) / TC_QB;
-  p.work_per_cta = work_per_pair;
+  p.work_per_cta = 0;
   p.total_work = p.q_blocks * p.n_tiles;
   p.s_max = s_max;
-  p.aligned = aligned;
+  p.aligned = 0;
+  p.pieces = reinterpret_cast<const int4*>(d_pieces);
   p.pos_base = pos_base;
   p.cand = cand;
   p.cand_cnt = cand_cnt;
@@ -1914,15 +1906,18 @@ int tc_ts_block_points() { return TS_BN; }
 //  * the remaining B' < sm_count blocks: g = floor(S / B') aligned segments per block (CTAs of a segment are
 //    neighbours and share tiles in L2) covering the first g*B'/S of the tiles, and the R = S - g*B' CTAs left
 //    over split what remains of every block in equal linear ranges -- every SM gets the same number of tiles.
-void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int* n_cta, int* s_max) {
+void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int* n_cta, int* s_max, int bn,
+                int lists_per_piece, int* single_blocks) {
   int kprime, cap;
   tc_candidate_shape(k, &kprime, &cap);
+  if (bn <= 0) bn = TS_BN;
   const int B = (nq + TC_QB - 1) / TC_QB;
-  const int T = (n + TS_BN - 1) / TS_BN;
+  const int T = (n + bn - 1) / bn;
   const int S = std::max(1, sm_count);
   // pieces per query block: bounded by the re-rank (64 lists) and by k' -- every piece ends with its own k' best
   // below a threshold that is only as tight as the piece is long, and the re-rank sorts at most 8192 live keys
-  const int max_pieces = std::min(std::min(64, std::max(4, 16384 / cap)), std::max(4, 3072 / kprime));
+  const int max_pieces =
+      std::max(4, std::min(std::min(64, std::max(4, 16384 / cap)), std::max(4, 3072 / kprime)) / std::max(1, lists_per_piece));
   std::vector<std::vector<int4>> ctas;
   std::vector<int> slots(B, 0);
   auto add_piece = [&](std::vector<int4>& c, int qb, int t0, int t1) {
@@ -1980,6 +1975,7 @@ void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int
     }
   *n_cta = (int)ctas.size();
   *s_max = smax;
+  if (single_blocks) *single_blocks = full;  // the leading query blocks that are scanned as ONE piece (whole waves)
 }
 
 cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, const float* nblock, const float* ones,
@@ -2088,9 +2084,15 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
 cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int n, int nq,
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
-                             uint64_t* out_keys, int* out_cert, cudaStream_t stream) {
+                             uint64_t* out_keys, int* out_cert, cudaStream_t stream, int q_begin, int q_count,
+                             int n_lists) {
   if (nq <= 0) return cudaSuccess;
+  if (q_count < 0) q_count = nq - q_begin;
+  if (q_count <= 0) return cudaSuccess;
+  if (n_lists <= 0 || n_lists > n_split) n_lists = n_split;
   RerankParams p;
+  p.q_begin = q_begin;
+  p.n_lists = n_lists;
   p.db = db;
   p.queries = queries;
   p.db_norm2 = db_norm2;
@@ -2118,7 +2120,7 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
   if (n_split > 64) return cudaErrorInvalidValue;
   // sort buffer: the live keys (pass-1 rank below the final threshold) are a few times k'; a query with more
   // than this many is left uncertified and re-run exactly
-  int items = std::min(n_split * p.cap, std::max(std::max(2048, 4 * k), std::min(n, 8192)));  // (small shards: all rows)
+  int items = std::min(n_lists * p.cap, std::max(std::max(2048, 4 * k), std::min(n, 8192)));  // (small shards: all rows)
   int p2 = 1;
   while (p2 < items || p2 < k) p2 <<= 1;
   const size_t smem = (size_t)p2 * 12 + 16;
@@ -2128,7 +2130,7 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
     fprintf(stderr, "nmslib_b200: tc_rerank cudaFuncSetAttribute(%zu) failed: %s\n", smem, cudaGetErrorString(e));
     return e;
   }
-  tc_rerank_kernel<<<nq, 128, smem, stream>>>(p, p2);
+  tc_rerank_kernel<<<q_count, 128, smem, stream>>>(p, p2);
   e = cudaGetLastError();
   if (e != cudaSuccess)
     fprintf(stderr, "nmslib_b200: tc_rerank launch (grid %d, smem %zu, items %d) failed: %s\n", nq, smem, p2,

@@ -1,5 +1,5 @@
 """Three config-2 query batches (the ncu target: `-k regex:tc_scan -s 1 -c 1` captures a warm launch).
-usage: tc_prof.py [dim] [n] [nq] [k]"""
+usage: tc_prof.py [dim] [n] [nq] [k] [space]   (space negdotprod: the embedding-shaped rows of config 5)"""
 import sys
 from pathlib import Path
 
@@ -11,8 +11,12 @@ dim = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 nq = int(sys.argv[3]) if len(sys.argv) > 3 else 10_000
 k = int(sys.argv[4]) if len(sys.argv) > 4 else 10
-data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
-idx = nb.Index("l2sqr", None, "seq_search")
+space = sys.argv[5] if len(sys.argv) > 5 else "l2sqr"
+if space == "negdotprod":
+    data, q = synth.embedding_like(n, dim, 9), synth.embedding_like(nq, dim, 10)
+else:
+    data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
+idx = nb.Index(space, None, "seq_search")
 idx.addDenseBatch(data)
 idx.buildIndex()
 for _ in range(3):
