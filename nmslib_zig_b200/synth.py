@@ -49,16 +49,20 @@ def gist_like(n: int, dim: int, seed: int, clusters: int = 64, centroid_seed: in
     return np.ascontiguousarray(x, np.float32)
 
 
-def embedding_like(n: int, dim: int, seed: int, chunk: int = 1 << 17) -> np.ndarray:
-    """C5: N(0,1) rows, L2-normalised, scaled by lognormal(0, 0.1)."""
-    rng = _rng(seed)
-    out = np.empty((n, dim), np.float32)
-    for s in range(0, n, chunk):
-        e = min(n, s + chunk)
+def embedding_like(n: int, dim: int, seed: int, chunk: int = 1 << 17, rows=None) -> np.ndarray:
+    """C5: N(0,1) rows, L2-normalised, scaled by lognormal(0, 0.1).  Every chunk of 131 072 rows has its own
+    counter-based stream (Philox key (seed, chunk)), so `rows=(lo, hi)` regenerates just those rows of the same
+    n-row data set -- a rank of the 8-way sharded 10 M x 768 run makes its 3.8 GB shard, not the 30.7 GB whole."""
+    lo, hi = rows if rows is not None else (0, n)
+    out = np.empty((hi - lo, dim), np.float32)
+    for c in range(lo // chunk, (hi + chunk - 1) // chunk):
+        s, e = c * chunk, min(n, (c + 1) * chunk)
+        rng = _rng(seed) if c == 0 else np.random.Generator(np.random.Philox(key=[seed, c]))
         x = rng.standard_normal((e - s, dim), dtype=np.float32)
         x /= np.linalg.norm(x, axis=1, keepdims=True)
         x *= rng.lognormal(0.0, 0.1, size=(e - s, 1)).astype(np.float32)
-        out[s:e] = x
+        a, b = max(lo, s), min(hi, e)
+        out[a - lo:b - lo] = x[a - s:b - s]
     return out
 
 
@@ -72,11 +76,17 @@ CONFIGS = {
 }
 
 
-def make(config: str, n: int | None = None, nq: int | None = None):
-    """(database, queries) of a BASELINE config, optionally at a reduced row / query count."""
+def make(config: str, n: int | None = None, nq: int | None = None, rows=None):
+    """(database, queries) of a BASELINE config, optionally at a reduced row / query count.  rows=(lo, hi): only
+    that shard of the database (generated without the rest where the generator allows it: c5)."""
     space, method, dtype, dist, n0, dim, nq0, k, s_db, s_q = CONFIGS[config]
     n = n or n0
     nq = nq or nq0
+    if rows is not None:
+        if config == "c5":
+            return embedding_like(n, dim, s_db, rows=rows), embedding_like(nq, dim, s_q)
+        data, queries = make(config, n, nq)
+        return np.ascontiguousarray(data[rows[0]:rows[1]]), queries
     if config == "c1":
         return uniform(n, dim, s_db), uniform(nq, dim, s_q)
     if config == "c2":
