@@ -226,6 +226,45 @@ def test_config2_full_size_properties():
     idx.deinit()
 
 
+@pytest.mark.parametrize("space,n,dim,nq,k", [("l2sqr", 60_000, 256, 20_000, 10), ("negdotprod", 40_000, 768, 20_000, 100),
+                                              ("cosinesimil", 30_000, 960, 19_200, 10)])
+def test_long_rows_many_query_blocks_pair_kernel(space, n, dim, nq, k):
+    """Rows of more than 128 floats run on CTA pairs (tc_scan_pair_kernel, cta_group::2).  >= 74 query blocks make
+    the piece table use whole waves of blocks AND the aligned-segments + left-over tail, and the re-rank is launched
+    once per list count.  Size-independent properties + the oracle on a query sample spread over all blocks."""
+    if space == "negdotprod":
+        data, q = synth.embedding_like(n, dim, 9), synth.embedding_like(nq, dim, 10)
+    elif space == "cosinesimil":
+        data, q = synth.gist_like(n, dim, 5), synth.gist_like(nq, dim, 6)
+    else:
+        data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
+    planted = np.arange(0, nq, 997)
+    q[planted] = data[(planted * 7) % n]
+    idx = make_index(space, data)
+    r = idx.knnQueryBatch(q, k)
+    assert np.all(r.sizes == k)
+    assert np.all(np.diff(r.distances, axis=1) >= 0)
+    if space != "negdotprod":                                   # a row is its own nearest neighbour (distance ~ 0)
+        hit = [(planted[i] * 7) % n in r.ids[planted[i], :3] for i in range(len(planted))]
+        assert np.mean(hit) == 1.0
+    for row in r.ids[::211]:
+        assert len(set(row.tolist())) == k
+    sample = np.concatenate([np.arange(0, nq, 389), np.arange(nq - 40, nq)])   # every block range incl. the tail blocks
+    oi, od, oc = O.seq_knn(space, data, q[sample], k)
+    dist_of = lambda qi, i: O.pair_distance(space, data[i], q[sample[qi]])
+    assert_knn_matches(r.ids[sample], r.distances[sample], r.sizes[sample], oi, od, oc, dist_of=dist_of,
+                       atol=ATOL_COSINE if space == "cosinesimil" else ATOL, what=f"pair kernel {space}")
+    perm = np.random.default_rng(1).permutation(nq)[:4096]      # the same queries in another batch shape
+    r2 = idx.knnQueryBatch(q[perm], k)
+    same = np.mean(r2.ids == r.ids[perm])
+    # (cosine on clustered 960-D rows: neighbours closer than fp32 resolves swap places when a query is certified in
+    # one batch and re-run by the exact kernel -- another summation order -- in the other; both pass the oracle check)
+    assert same >= (0.995 if space == "cosinesimil" else 0.9999), f"batch-shape dependence: {same}"
+    assert np.allclose(r2.distances, r.distances[perm], rtol=RTOL, atol=ATOL_COSINE)
+    assert idx.stats()["fallback_queries"] <= 0.02 * (nq + 4096)
+    idx.deinit()
+
+
 def test_tensor_core_path_is_the_one_that_runs_and_certifies():
     """Float seq_search goes through the tcgen05 candidate pass + exact re-rank; the certificate
     must hold for (nearly) every query on ordinary data, i.e. the exact-scan re-run stays idle."""
