@@ -97,6 +97,11 @@ def workload(name: str, n: int | None, nq: int | None, rank: int = 0, world: int
                 queries=queries, n=n, nq=queries.shape[0], lo=lo, hi=hi)
 
 
+def synth_method(name: str) -> str:
+    from nmslib_zig_b200 import synth
+    return synth.CONFIGS[name][1]
+
+
 def ref_space(space):  # l2sqr is not a registered reference space: same ranking as l2
     return "l2" if space == "l2sqr" else space
 
@@ -124,6 +129,123 @@ def time_reference(w, sample: int, steps: int, warmup: int):
                       + (" (space l2: l2sqr is not registered in the reference; same ranking + one sqrtf)"
                          if w["space"] == "l2sqr" else ""),
             "ms_per_step": dt * 1e3}
+
+
+def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
+    """Config 3: HNSW beam search (K3).  One graph does not shard without changing its answers: every
+    rank holds a replica of the index -- built on the device by csrc/hnsw_build_gpu.cu -- and takes 1/N of the
+    queries; there is no data-path collective.  efSearch = the smallest of the sweep that reaches recall@10 >= 0.95
+    against the exact scan on a query sample (the metric's condition), else the largest."""
+    import torch
+    import nmslib_zig_b200 as nb
+    if dist_on:
+        import torch.distributed as dist
+    n, nq, dim, k = w["n"], w["nq"], w["dim"], w["k"]
+    data, queries = w["data"], w["queries"]
+    t0 = time.perf_counter()
+    idx = nb.Index(w["space"], None, "hnsw")
+    idx.addDenseBatch(data)
+    idx.buildIndex(nb.Params({"M": 16, "efConstruction": 200, "b200_build": "device"}))
+    idx.prepare()
+    build_s = time.perf_counter() - t0
+    build = {k_: v for k_, v in idx.stats().items() if k_.startswith("build_")}
+    # ground truth for the recall condition: the exact scan (itself parity-tested) on a query sample
+    sample = queries[:: max(1, nq // 1000)][:1000]
+    ex = nb.Index(w["space"], None, "seq_search")
+    ex.addDenseBatch(data)
+    ex.buildIndex()
+    exact_ids = ex.knnQueryBatch(sample, k).ids
+    ex.deinit()
+    sweep, ef, rec = [], None, 0.0
+    for cand in (50, 100, 200, 400, 800):
+        idx.setQueryTimeParams(nb.Params({"efSearch": cand}))
+        got = idx.knnQueryBatch(sample, k).ids
+        r = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(got, exact_ids)]))
+        sweep.append({"efSearch": cand, "recall": r})
+        ef, rec = cand, r
+        if r >= 0.95:
+            break
+    idx.setQueryTimeParams(nb.Params({"efSearch": ef}))
+    q_lo, q_hi = (nq * rank) // world, (nq * (rank + 1)) // world
+    my_nq = q_hi - q_lo
+    q_host = torch.from_numpy(np.ascontiguousarray(queries[q_lo:q_hi])).pin_memory()
+    d_q = q_host.to(dev)
+    d_ids = torch.empty((my_nq, k), dtype=torch.int32, device=dev)
+    d_dists = torch.empty((my_nq, k), dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+
+    def step_device():
+        idx.knnDevice(d_q.data_ptr(), my_nq, dim, k, d_ids.data_ptr(), d_dists.data_ptr(), 0, stream.cuda_stream)
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    st0 = idx.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    st1 = idx.stats()
+    q_np = q_host.numpy()
+    for _ in range(2):
+        idx.knnQueryBatch(q_np, k)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        idx.knnQueryBatch(q_np, k)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if dist_on:
+        t = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0].item()), float(t[1].item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peaks = load_peaks()
+        ms_per_step = ms / args.steps
+        steps = max(1, args.steps)
+        evals = (st1["distance_evals"] - st0["distance_evals"]) / steps
+        exps = (st1["hnsw_expansions"] - st0["hnsw_expansions"]) / steps
+        kern_ms = (st1["scan_ms_sum"] - st0["scan_ms_sum"]) / max(1, st1["scan_count"] - st0["scan_count"])
+        launches_per_step = (st1["scan_count"] - st0["scan_count"]) / steps
+        gbytes = (evals * 4.0 * dim + exps * 4.0 * 32) / 1e9          # SURVEY 8d: rows gathered + adjacency lists read
+        achieved = gbytes / max(1e-9, kern_ms * launches_per_step * 1e-3)
+        cpu = None
+        line = {
+            "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{w['name']}: hnsw {w['space']} {n}x{dim}, M=16 efConstruction=200 (graph built on the "
+                                   f"device), efSearch={ef}, {nq} queries, k={k}", "space": w["space"], "k": k,
+                       "efSearch": ef, "recall_at_k": rec, "recall_sweep": sweep,
+                       "parallelism": f"index replicated x{world}, queries split {world} ways (no collective)",
+                       "l2_policy": f"random gathers over {n * dim * 4 / 1e6:.0f} MB of rows (L2 is 126 MB)",
+                       "build_s_incl_upload": build_s, **build},
+            "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(nq * dim * 4), "d2h_bytes_per_step": int(nq * k * 8 + nq * 4)},
+            "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "hnsw_search",
+                         "kernel_ms": kern_ms * launches_per_step,
+                         "bytes_per_query": gbytes * 1e9 / max(1, my_nq),
+                         "peak_src": f"{peaks['src']} HBM copy bandwidth"},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    idx.deinit()
 
 
 def main():
@@ -177,6 +299,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
+    if synth_method(args.workload) == "hnsw":          # config 3: replicas, queries split (no row shards)
+        w = workload(args.workload, args.n, args.nq)
+        run_hnsw(args, w, rank, world, local_rank, dev, dist_on)
+        if dist_on:
+            dist.destroy_process_group()
+        return
     w = workload(args.workload, args.n, args.nq, rank, world)
     n, nq, dim, k = w["n"], w["nq"], w["dim"], w["k"]
     u8 = w["dtype"] == "DenseUInt8Vector"

@@ -278,6 +278,7 @@ typedef struct {
   double build_link_ms;      /* back links: sort + append / re-prune */
   uint64_t build_batches;    /* insertion batches over all levels */
   uint64_t build_prunes;     /* neighbour lists re-pruned because they overflowed */
+  uint64_t split_queries;    /* queries re-run by the 3xTF32 (split operand) scan after a failed certificate */
 } nmslib_b200_stats_t;
 nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_stats_t* out);
 

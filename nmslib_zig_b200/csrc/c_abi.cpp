@@ -763,6 +763,7 @@ nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_st
   out->build_link_ms = bi.link_ms;
   out->build_batches = (uint64_t)bi.batches;
   out->build_prunes = bi.prunes;
+  out->split_queries = s.split_queries;
   return NMSLIB_SUCCESS;
 }
 

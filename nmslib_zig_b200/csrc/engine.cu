@@ -101,7 +101,8 @@ Engine::~Engine() {
   for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
                     &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
                     &d_out_counts_, &d_bias_, &d_db_unit_, &d_flags_, &d_qa_, &d_cand_, &d_cand_cnt_, &d_cand_thr_,
-                    &d_tc_keys_, &d_cert_, &d_plan_, &d_gthr_, &d_u8tmp_, &d_range_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_})
+                    &d_tc_keys_, &d_cert_, &d_plan_, &d_gthr_, &d_u8tmp_, &d_range_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_,
+                    &d_db_split_, &d_q_split_, &d_sp_idx_, &d_sp_q_, &d_sp_keys_})
     b->release();
   for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_}) b->release();
   for (auto& e : ev_)
@@ -316,6 +317,13 @@ Stats Engine::stats() {
     }
     scan_pending_[i] = false;
   }
+  if (method_ == METHOD_HNSW && d_counters_.p) {  // cumulative device counters (also after device-resident calls)
+    unsigned long long c[2] = {0, 0};
+    if (cudaSetDevice(device_) == cudaSuccess && cudaMemcpy(c, d_counters_.p, 16, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      stats_.distance_evals = c[0];
+      stats_.hnsw_expansions = c[1];
+    }
+  }
   cudaGetLastError();
   return stats_;
 }
@@ -436,6 +444,8 @@ Status Engine::upload_data() {
     ++stats_.kernel_launches;
   }
   x_max_ = 0.f;
+  tc_split_ = false;
+  d_db_split_.release();
   if (!dev_u8 && method_ == METHOD_SEQ && space_ != SPACE_L1 && space_ != SPACE_LINF) {
     // operands of the tensor-core scan: bias (|x|^2 or 0, +inf on padding rows), the unit-norm copy
     // for cosine, max operand-row norm and the "is TF32-exact" flag (both feed the certificate)
@@ -716,8 +726,38 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
 }
 
 // Tensor-core candidates + exact fp32 re-rank + certificate; uncertified queries go to run_seq_exact.
-Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream) {
+// Split mode (3xTF32): when a batch mostly fails its certificates on data that is not TF32-exact -- neighbours
+// closer together than the 2^-9 |q||x| error band of truncated operands, e.g. cosine over concentrated 960-D
+// clusters -- the operands are split into TF32-exact halves, q = q_hi + q_lo, x = x_hi + x_lo, and the scan runs on
+// rows of three times the length, [q_hi | q_hi | q_lo] . [x_hi | x_lo | x_hi] = q_hi.x_hi + q_hi.x_lo + q_lo.x_hi:
+// the same kernels, three times the MMA work, and an error band of D 2^-22 + 3 2^-20 (accumulation + the dropped
+// q_lo.x_lo term) instead of 2^-9.  The failed queries of that batch and every later batch use it.
+Status Engine::enable_split(cudaStream_t stream) {
+  if (tc_split_) return Status::OK();
+  if (const char* e = getenv("NB200_TC_SPLIT"))
+    if (e[0] == '0') return Status::Err(kErrQuery, "split mode disabled");
+  const size_t n_pad = round_up(n_dev_ < n_ ? n_ : n_dev_, (size_t)tc_block_points());
+  const size_t bytes = n_pad * 3 * (size_t)row_words_ * 4;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes + (2ull << 30) > free_b)
+    return Status::Err(kErrOOM, "no room for the split operand copy");
+  Status s = check_cuda(d_db_split_.ensure(bytes), "cudaMalloc(split rows)");
+  if (!s.ok()) return s;
+  const bool cos_family = space_ == SPACE_COSINE || space_ == SPACE_ANGULAR;
+  s = check_cuda(launch_tc_split_rows(cos_family ? d_db_unit_.as<float>() : d_db_.as<float>(), n_pad, row_words_, 1.0f, 0,
+                                      d_db_split_.as<float>(), stream),
+                 "tc_split_rows");
+  if (!s.ok()) return s;
+  ++stats_.kernel_launches;
+  tc_split_ = true;
+  return Status::OK();
+}
+
+Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream,
+                          bool allow_split_retry) {
   Status s;
+  const bool split = tc_split_;
+  const int rw = split ? 3 * row_words_ : row_words_;  // operand row length the scan kernels see
   const int mode = (space_ == SPACE_COSINE || space_ == SPACE_ANGULAR) ? SCAN_COSINE
                    : space_ == SPACE_NEGDOT                             ? SCAN_NEGDOT
                                                                         : SCAN_L2;
@@ -726,11 +766,11 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   const size_t n_pad = round_up(n_dev_, bn);
   const int q_blocks = (int)(q_pad / qb);
   // equal linear ranges of the (query block x tile) grid, one CTA per SM (scan_tc.cu tc_plan)
-  const bool ts = tc_ts_supported(row_words_);  // rows <= 128 floats: queries live in tensor memory
+  const bool ts = tc_ts_supported(rw);  // rows <= 128 floats: queries live in tensor memory
   const bool pair = !ts && tc_pair_enabled() && sm_count_ >= 2;
   int n_cta, work_per_cta = 0, s_max, aligned = 0;
   if (ts || pair) {  // host-made piece table (pair: units are CTA pairs over 256-row tiles, two lists per piece)
-    if (plan_key_[0] != nq || plan_key_[1] != n_dev_ || plan_key_[2] != k) {
+    if (plan_key_[0] != nq || plan_key_[1] != n_dev_ || plan_key_[2] != k || plan_key_[3] != (size_t)rw) {
       if (ts) tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &h_plan_, &plan_n_cta_, &plan_s_max_, 0, 1, &plan_single_);
       else tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_ / 2, &h_plan_, &plan_n_cta_, &plan_s_max_, tc_pair_block_points(), 2, &plan_single_);
       if (!(s = check_cuda(d_plan_.ensure(h_plan_.size() * 4), "cudaMalloc(plan)")).ok()) return s;
@@ -740,6 +780,7 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
       plan_key_[0] = nq;
       plan_key_[1] = n_dev_;
       plan_key_[2] = k;
+      plan_key_[3] = (size_t)rw;
     }
     n_cta = plan_n_cta_;
     s_max = pair ? 2 * plan_s_max_ : plan_s_max_;
@@ -757,18 +798,27 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   if (!(s = check_cuda(h_cert_.ensure(nq * 4), "cudaMallocHost(cert)")).ok()) return s;
   if (!(s = check_cuda(cudaMemsetAsync(d_flags_.as<int>() + 1, 0, 4, stream), "memset(qflag)")).ok()) return s;
   const float scale = mode == SCAN_L2 ? -2.f : -1.f;
-  const float* dbB = mode == SCAN_COSINE ? d_db_unit_.as<float>() : d_db_.as<float>();
+  const float* dbB = split ? d_db_split_.as<float>() : mode == SCAN_COSINE ? d_db_unit_.as<float>() : d_db_.as<float>();
+  if (split) stats_.split_queries += nq;
+  if (split) {  // prepared A operand [q_hi | q_hi | q_lo], already scaled
+    if (!(s = check_cuda(d_q_split_.ensure(q_pad * (size_t)rw * 4), "cudaMalloc(split queries)")).ok()) return s;
+    s = check_cuda(launch_tc_split_rows(static_cast<const float*>(dq), q_pad, row_words_, scale, 1,
+                                        d_q_split_.as<float>(), stream),
+                   "tc_split_rows(queries)");
+    if (!s.ok()) return s;
+    ++stats_.kernel_launches;
+  }
   if (!(s = check_cuda(d_gthr_.ensure(q_pad * 4), "cudaMalloc(gthr)")).ok()) return s;
   if (!(s = check_cuda(cudaMemsetAsync(d_gthr_.p, 0xFF, q_pad * 4, stream), "memset(gthr)")).ok()) return s;
   // survivors per compaction: k + margin.  Data that is not TF32-exact carries a pass-1 error of ~2^-9 |q||x|,
   // which at k = 100 spans tens of ranks: start with half of k there (the margin doubles when certificates fail)
   // (approx_ok_: graph construction takes the tensor-core ranking as it is -- small margin, no error band in the re-rank)
-  const int kprime_req = (int)k + (db_inexact_ && !approx_ok_ ? std::max(tc_margin_, (int)k / 2) : tc_margin_);
+  const int kprime_req = (int)k + (db_inexact_ && !approx_ok_ && !split ? std::max(tc_margin_, (int)k / 2) : tc_margin_);
   if (ts) {
     scan_begin(stream);
-    s = check_cuda(launch_tc_scan_ts(static_cast<const float*>(dq), dbB, n_pad,
+    s = check_cuda(launch_tc_scan_ts(split ? d_q_split_.as<float>() : static_cast<const float*>(dq), dbB, n_pad,
                                      mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(),
-                                     (int)n_dev_, (int)nq, row_words_, (int)k, kprime_req, scale, pos_base_,
+                                     (int)n_dev_, (int)nq, rw, (int)k, kprime_req, split ? 1.0f : scale, pos_base_,
                                      n_cta, s_max, d_plan_.as<int>(), d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
                                      d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), d_flags_.as<int>() + 1,
                                      stream),
@@ -777,19 +827,23 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     if (!s.ok()) return s;
     stats_.kernel_launches += 1;  // (the re-rank launches are counted where they are made)
   } else {
-    if (!(s = check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)")).ok()) return s;
-    s = check_cuda(launch_tc_prep_queries(static_cast<const float*>(dq), d_qa_.as<float>(), q_pad * (size_t)row_words_,
-                                          scale, d_flags_.as<int>() + 1, stream),
-                   "tc_prep_queries");
-    if (!s.ok()) return s;
+    const float* qa = d_q_split_.as<float>();
+    if (!split) {
+      if (!(s = check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)")).ok()) return s;
+      s = check_cuda(launch_tc_prep_queries(static_cast<const float*>(dq), d_qa_.as<float>(), q_pad * (size_t)row_words_,
+                                            scale, d_flags_.as<int>() + 1, stream),
+                     "tc_prep_queries");
+      if (!s.ok()) return s;
+      qa = d_qa_.as<float>();
+    }
     scan_begin(stream);
     const float* nbp = mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr;
-    s = check_cuda(pair ? launch_tc_scan_pair(d_qa_.as<float>(), q_pad, dbB, n_pad, nbp, d_ones_.as<float>(), (int)n_dev_,
-                                              (int)nq, row_words_, (int)k, pos_base_, n_cta, d_plan_.as<int>(), s_max,
+    s = check_cuda(pair ? launch_tc_scan_pair(qa, q_pad, dbB, n_pad, nbp, d_ones_.as<float>(), (int)n_dev_,
+                                              (int)nq, rw, (int)k, pos_base_, n_cta, d_plan_.as<int>(), s_max,
                                               kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
                                               d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream)
-                        : launch_tc_scan(d_qa_.as<float>(), q_pad, dbB, n_pad, nbp, d_ones_.as<float>(), (int)n_dev_,
-                                         (int)nq, row_words_, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
+                        : launch_tc_scan(qa, q_pad, dbB, n_pad, nbp, d_ones_.as<float>(), (int)n_dev_,
+                                         (int)nq, rw, (int)k, pos_base_, n_cta, work_per_cta, s_max, aligned,
                                          kprime_req, d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(),
                                          d_cand_thr_.as<float>(), d_gthr_.as<uint32_t>(), stream),
                    pair ? "tc_scan_pair" : "tc_scan");
@@ -808,7 +862,10 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
                                     (int)k, s_max, space_ == SPACE_ANGULAR ? SCAN_ANGULAR : mode, pos_base_,
                                     d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(),
                                     approx_ok_ ? 0.f : x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(), stream,
-                                    (int)qb0, (int)qc, part == 0 ? (pair ? 2 : 1) : s_max),
+                                    (int)qb0, (int)qc, part == 0 ? (pair ? 2 : 1) : s_max,
+                                    // split operands: accumulation error + the dropped q_lo.x_lo / re-truncated terms
+                                    split ? (float)row_words_ * 2.384185791015625e-07f * 1.01f + 3.0f * 9.5367431640625e-07f + 1e-6f
+                                          : 0.f),
                    "tc_rerank");
     if (!s.ok()) return s;
     ++stats_.kernel_launches;
@@ -823,8 +880,34 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   for (size_t i = 0; i < nq; ++i)
     if (!cert[i]) fb.push_back((int)i);
   if (fb.empty()) return Status::OK();
+  if (approx_ok_) {  // (graph construction: the re-ranked candidates are good enough)
+    stats_.fallback_queries += fb.size();
+    return Status::OK();
+  }
+  if (!split && allow_split_retry && db_inexact_ && fb.size() * 4 > nq && enable_split(stream).ok()) {
+    // most of the batch sits inside the TF32 error band: give the failed queries the split (3xTF32) scan now
+    const size_t nsp = fb.size(), sp_pad = round_up(nsp, (size_t)tc_block_queries());
+    if (!(s = check_cuda(d_sp_idx_.ensure(nsp * 4), "cudaMalloc(split idx)")).ok()) return s;
+    if (!(s = check_cuda(d_sp_q_.ensure(sp_pad * (size_t)row_words_ * 4), "cudaMalloc(split q)")).ok()) return s;
+    if (!(s = check_cuda(d_sp_keys_.ensure(nsp * k * 8), "cudaMalloc(split keys)")).ok()) return s;
+    if (!(s = check_cuda(cudaMemsetAsync(d_sp_q_.p, 0, sp_pad * (size_t)row_words_ * 4, stream), "memset(split q)")).ok())
+      return s;
+    s = check_cuda(cudaMemcpyAsync(d_sp_idx_.p, fb.data(), nsp * 4, cudaMemcpyHostToDevice, stream), "H2D(split idx)");
+    if (!s.ok()) return s;
+    s = check_cuda(launch_gather_rows(static_cast<const uint32_t*>(dq), d_sp_idx_.as<int>(), (int)nsp, row_words_,
+                                      d_sp_q_.as<uint32_t>(), stream),
+                   "gather");
+    if (!s.ok()) return s;
+    if (!(s = check_cuda(cudaStreamSynchronize(stream), "split gather")).ok()) return s;  // (fb is reused below)
+    s = run_seq_tc(d_sp_q_.p, nsp, k, d_sp_keys_.as<uint64_t>(), stream, false);
+    if (!s.ok()) return s;
+    s = check_cuda(launch_scatter_keys(d_sp_keys_.as<uint64_t>(), d_sp_idx_.as<int>(), (int)nsp, (int)k, out_keys, stream),
+                   "scatter");
+    if (!s.ok()) return s;
+    stats_.kernel_launches += 2;
+    return check_cuda(cudaStreamSynchronize(stream), "split scan");
+  }
   stats_.fallback_queries += fb.size();
-  if (approx_ok_) return Status::OK();  // (graph construction: the re-ranked candidates are good enough)
   // the thresholds sat too close to the k-th answer for this data's pass-1 error bound: keep more survivors per
   // compaction from the next batch on (costs candidates, buys certificate margin)
   if (fb.size() * 64 > nq && tc_margin_ < 128) tc_margin_ *= 2;

@@ -97,7 +97,7 @@ struct Stats {
   uint64_t queries = 0, kernel_launches = 0, distance_evals = 0, hnsw_expansions = 0;
   double last_kernel_ms = 0, last_total_ms = 0, last_scan_ms = 0, scan_ms_sum = 0;
   uint64_t scan_count = 0;
-  uint64_t fallback_queries = 0, device_bytes = 0;
+  uint64_t fallback_queries = 0, device_bytes = 0, split_queries = 0;
 };
 
 class Engine {
@@ -166,7 +166,9 @@ class Engine {
   Status upload_data();
   Status upload_graph();
   Status run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream);
-  Status run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream);
+  Status run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream,
+                    bool allow_split_retry = true);
+  Status enable_split(cudaStream_t stream);
   Status run(const void* d_queries_padded, size_t nq, size_t k, int32_t* d_ids, float* d_dists,
              uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream);
   Status stage_queries_device(const void* src, bool src_on_device, size_t nq, size_t elem_count,
@@ -216,7 +218,9 @@ class Engine {
   int tc_margin_ = 6;                   // survivors per compaction = k + margin (doubles when certificates fail)
   DevBuf d_plan_;                       // piece table of the TS scan (tc_ts_plan), cached per (nq, n, k)
   std::vector<int> h_plan_;
-  size_t plan_key_[3] = {0, 0, 0};
+  size_t plan_key_[4] = {0, 0, 0, 0};
+  bool tc_split_ = false;               // 3xTF32: operands split into TF32-exact halves (see run_seq_tc)
+  DevBuf d_db_split_, d_q_split_, d_sp_idx_, d_sp_q_, d_sp_keys_;
   int plan_n_cta_ = 0, plan_s_max_ = 0, plan_single_ = 0;
   DevBuf d_bias_, d_db_unit_, d_flags_, d_qa_, d_cand_, d_cand_cnt_, d_cand_thr_, d_tc_keys_, d_cert_, d_fb_idx_,
       d_fb_q_, d_fb_keys_, d_nblock_, d_ones_;

@@ -94,8 +94,12 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
                              uint64_t* out_keys, int* out_cert, cudaStream_t stream,  // mode may be SCAN_ANGULAR
-                             int q_begin = 0, int q_count = -1, int n_lists = -1);  // a query range whose blocks use
-                                                                                    // only the first n_lists lists
+                             int q_begin = 0, int q_count = -1, int n_lists = -1,  // a query range whose blocks use
+                             float eps_override = 0.f);  // only the first n_lists lists; eps: error band of split operands
+// 3xTF32 operand split: dst[r] = [hi | lo | hi] (layout 0, database) or [hi | hi | lo] (layout 1, queries) of
+// scale * src[r], hi = the TF32-exact part, lo = the TF32-exact part of the rest; dst rows are 3 * row_words long
+cudaError_t launch_tc_split_rows(const float* src, size_t rows, int row_words, float scale, int layout, float* dst,
+                                 cudaStream_t stream);
 
 // ---- range_scan.cu (one query, every row within the radius, in position order) ----------
 // dist_tmp: [n] scratch; out_ids / out_dists: [capacity] device buffers; *out_count <= capacity

@@ -1570,6 +1570,23 @@ __global__ void tc_prep_queries_kernel(const float* __restrict__ q, float* __res
   if ((threadIdx.x & 31) == 0 && bad) atomicOr(inexact_flag, 1);
 }
 
+__global__ void tc_split_rows_kernel(const float* __restrict__ src, size_t rows, int rw, float scale, int layout,
+                                     float* __restrict__ dst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, total = rows * (size_t)rw;
+  for (; i < total; i += stride) {
+    const size_t r = i / (size_t)rw;
+    const int c = (int)(i - r * (size_t)rw);
+    const float v = src[i] * scale;
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // what the tensor core would keep of v
+    const float lo = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
+    float* d = dst + r * 3 * (size_t)rw;
+    d[c] = hi;
+    d[rw + c] = layout ? hi : lo;
+    d[2 * rw + c] = layout ? lo : hi;
+  }
+}
+
 // database side: bias[row] (|x|^2 for l2, 0 otherwise; +inf on padding rows), optional normalised copy,
 // max operand-row norm, TF32-exactness flag.  One warp per row.
 __global__ void tc_prep_db_kernel(const float* __restrict__ db, int n, int n_pad, int row_words, int mode,
@@ -1724,6 +1741,15 @@ void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_p
       return;
     }
   }
+}
+
+cudaError_t launch_tc_split_rows(const float* src, size_t rows, int row_words, float scale, int layout, float* dst,
+                                 cudaStream_t stream) {
+  const size_t total = rows * (size_t)row_words;
+  if (total == 0) return cudaSuccess;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  tc_split_rows_kernel<<<blocks, 256, 0, stream>>>(src, rows, row_words, scale, layout, dst);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_tc_prep_queries(const float* q, float* out, size_t words, float scale, int* inexact_flag,
@@ -2085,7 +2111,7 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
                              uint64_t* out_keys, int* out_cert, cudaStream_t stream, int q_begin, int q_count,
-                             int n_lists) {
+                             int n_lists, float eps_override) {
   if (nq <= 0) return cudaSuccess;
   if (q_count < 0) q_count = nq - q_begin;
   if (q_count <= 0) return cudaSuccess;
@@ -2112,6 +2138,7 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
   const float dterms = (float)row_words;
   p.eps_exact = dterms * 2.384185791015625e-07f;                    // D * 2^-22  (accumulation only)
   p.eps_inexact = 2.0f * 0.0009765625f * 1.01f + p.eps_exact;       // 2 * 2^-10 + accumulation
+  if (eps_override > 0.f) p.eps_exact = p.eps_inexact = eps_override;  // (split operands: see Engine::enable_split)
   p.x_max = x_max;
   p.inexact_flags = inexact_flags;
   p.out_keys = out_keys;

@@ -261,7 +261,12 @@ def test_long_rows_many_query_blocks_pair_kernel(space, n, dim, nq, k):
     # one batch and re-run by the exact kernel -- another summation order -- in the other; both pass the oracle check)
     assert same >= (0.995 if space == "cosinesimil" else 0.9999), f"batch-shape dependence: {same}"
     assert np.allclose(r2.distances, r.distances[perm], rtol=RTOL, atol=ATOL_COSINE)
-    assert idx.stats()["fallback_queries"] <= 0.02 * (nq + 4096)
+    st = idx.stats()
+    # concentrated 960-D clusters sit inside the error band of truncated TF32 operands: the first batch fails its
+    # certificates, the engine switches to split (3xTF32) operands and certifies (nearly) all of them
+    assert st["fallback_queries"] <= 0.02 * (nq + 4096), f"{st['fallback_queries']} queries re-run by the exact scan"
+    if space == "cosinesimil":
+        assert st["split_queries"] >= nq // 2
     idx.deinit()
 
 

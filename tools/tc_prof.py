@@ -14,6 +14,8 @@ k = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 space = sys.argv[5] if len(sys.argv) > 5 else "l2sqr"
 if space == "negdotprod":
     data, q = synth.embedding_like(n, dim, 9), synth.embedding_like(nq, dim, 10)
+elif space == "cosinesimil":
+    data, q = synth.gist_like(n, dim, 5), synth.gist_like(nq, dim, 6)
 else:
     data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
 idx = nb.Index(space, None, "seq_search")
@@ -21,5 +23,7 @@ idx.addDenseBatch(data)
 idx.buildIndex()
 for _ in range(3):
     idx.knnQueryBatch(q, k)
-    print("scan_ms", idx.stats()["last_scan_ms"], "fallback", idx.stats()["fallback_queries"], flush=True)
+    st = idx.stats()
+    print("scan_ms", st["last_scan_ms"], "total_ms", st["last_total_ms"], "fallback", st["fallback_queries"], "split",
+          st["split_queries"], flush=True)
 idx.deinit()
