@@ -290,6 +290,11 @@ nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_st
 size_t nmslib_b200_scan_plan(size_t query_count, size_t n, size_t k, int sm_count, int32_t* pieces,
                              size_t capacity, int* n_cta, int* s_max);
 
+/* The same for rows of more than 128 floats, which run on CTA pairs (cta_group::2 MMAs): units are sm_count / 2
+ * pairs, tiles are 256 rows, every piece fills two candidate lists (*s_max counts lists). */
+size_t nmslib_b200_scan_plan_pairs(size_t query_count, size_t n, size_t k, int sm_count, int32_t* pieces,
+                                   size_t capacity, int* n_pairs, int* s_max);
+
 /* Library build / arch string, e.g. "nmslib_b200 0.1 sm_100a". Static storage. */
 const char* nmslib_b200_version(void);
 

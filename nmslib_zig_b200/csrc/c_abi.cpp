@@ -767,11 +767,28 @@ nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_st
   return NMSLIB_SUCCESS;
 }
 
+static size_t scan_plan_impl(size_t query_count, size_t n, size_t k, int units, int tile_rows, int lists_per_piece,
+                             int32_t* pieces, size_t capacity, int* n_cta, int* s_max);
+
 size_t nmslib_b200_scan_plan(size_t query_count, size_t n, size_t k, int sm_count, int32_t* pieces, size_t capacity,
                              int* n_cta, int* s_max) {
+  return scan_plan_impl(query_count, n, k, sm_count, 0, 1, pieces, capacity, n_cta, s_max);
+}
+
+size_t nmslib_b200_scan_plan_pairs(size_t query_count, size_t n, size_t k, int sm_count, int32_t* pieces,
+                                   size_t capacity, int* n_pairs, int* s_max) {
+  int slots = 0;
+  const size_t m = scan_plan_impl(query_count, n, k, sm_count / 2, nb200::tc_pair_block_points(), 2, pieces, capacity,
+                                  n_pairs, &slots);
+  if (s_max) *s_max = 2 * slots;  // two candidate lists (column halves of the 256-row tile) per piece
+  return m;
+}
+
+static size_t scan_plan_impl(size_t query_count, size_t n, size_t k, int units, int tile_rows, int lists_per_piece,
+                             int32_t* pieces, size_t capacity, int* n_cta, int* s_max) {
   std::vector<int> table;
   int nc = 0, sm = 0;
-  nb200::tc_ts_plan((int)query_count, (int)n, (int)k, sm_count, &table, &nc, &sm);
+  nb200::tc_ts_plan((int)query_count, (int)n, (int)k, units, &table, &nc, &sm, tile_rows, lists_per_piece);
   if (n_cta) *n_cta = nc;
   if (s_max) *s_max = sm;
   size_t out = 0;

@@ -84,7 +84,7 @@ ABI_SYMBOLS = [
 EXT_SYMBOLS = [
     "nmslib_b200_set_device", "nmslib_b200_device_available", "nmslib_b200_set_shard", "nmslib_b200_import_hnsw",
     "nmslib_b200_prepare", "nmslib_b200_knn_device", "nmslib_b200_merge_topk", "nmslib_b200_get_stats",
-    "nmslib_b200_version", "nmslib_b200_scan_plan",
+    "nmslib_b200_version", "nmslib_b200_scan_plan", "nmslib_b200_scan_plan_pairs",
 ]
 
 _lib = None
@@ -175,6 +175,7 @@ def lib() -> C.CDLL:
         "nmslib_b200_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "nmslib_b200_version": (C.c_char_p, []),
         "nmslib_b200_scan_plan": (sz, [sz, sz, sz, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "nmslib_b200_scan_plan_pairs": (sz, [sz, sz, sz, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here == a symbol the header promises is not exported
@@ -501,6 +502,16 @@ def scan_plan(nq: int, n: int, k: int, sm_count: int = 148):
     m = L.nmslib_b200_scan_plan(nq, n, k, sm_count, None, 0, C.byref(nc), C.byref(sm))
     out = np.zeros((m, 5), np.int32)
     L.nmslib_b200_scan_plan(nq, n, k, sm_count, out.ctypes.data, m, C.byref(nc), C.byref(sm))
+    return out, nc.value, sm.value
+
+
+def scan_plan_pairs(nq: int, n: int, k: int, sm_count: int = 148):
+    """The same for long rows (CTA pairs, 256-row tiles): (pieces[m,5], n_pairs, lists per query block)."""
+    L = lib()
+    nc, sm = C.c_int(0), C.c_int(0)
+    m = L.nmslib_b200_scan_plan_pairs(nq, n, k, sm_count, None, 0, C.byref(nc), C.byref(sm))
+    out = np.zeros((m, 5), np.int32)
+    L.nmslib_b200_scan_plan_pairs(nq, n, k, sm_count, out.ctypes.data, m, C.byref(nc), C.byref(sm))
     return out, nc.value, sm.value
 
 

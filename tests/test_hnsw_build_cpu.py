@@ -81,3 +81,17 @@ def test_reference_loads_and_searches_our_file(tmp_path):
         assert r.size == 5 and np.array_equal(ids, pi[i]) and np.allclose(d, pd[i], rtol=1e-5, atol=1e-6)
     L.nmslib_index_destroy(h)
     port.close()
+
+
+def test_b200_build_parameter_is_accepted_and_host_is_honoured(tmp_path):
+    """`b200_build` (where the graph is built) is an index-time parameter of this library next to the reference's own
+    (hnsw.cc:185-205); `host` must work without a GPU, an unknown name still fails like AnyParamManager::CheckUnused."""
+    data = synth.gist_like(2000, 16, 43, clusters=8)
+    path = tmp_path / "h.hnsw"
+    _build("l2", data, {"M": 8, "efConstruction": 60, "b200_build": "host"}, path)
+    assert path.stat().st_size > 2000 * 16 * 4
+    idx = nb.Index("l2", None, "hnsw")
+    idx.addDenseBatch(data)
+    with pytest.raises(nb.NmslibError):
+        idx.buildIndex(nb.Params({"M": 8, "b200_where": "host"}))
+    idx.deinit()
