@@ -771,8 +771,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   int n_cta, work_per_cta = 0, s_max, aligned = 0;
   if (ts || pair) {  // host-made piece table (pair: units are CTA pairs over 256-row tiles, two lists per piece)
     if (plan_key_[0] != nq || plan_key_[1] != n_dev_ || plan_key_[2] != k || plan_key_[3] != (size_t)rw) {
-      if (ts) tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &h_plan_, &plan_n_cta_, &plan_s_max_, 0, 1, &plan_single_);
-      else tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_ / 2, &h_plan_, &plan_n_cta_, &plan_s_max_, tc_pair_block_points(), 2, &plan_single_);
+      if (ts) tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_, &h_plan_, &plan_n_cta_, &plan_s_max_, 0, 1, &plan_block_slots_);
+      else tc_ts_plan((int)nq, (int)n_dev_, (int)k, sm_count_ / 2, &h_plan_, &plan_n_cta_, &plan_s_max_, tc_pair_block_points(), 2, &plan_block_slots_);
       if (!(s = check_cuda(d_plan_.ensure(h_plan_.size() * 4), "cudaMalloc(plan)")).ok()) return s;
       s = check_cuda(cudaMemcpyAsync(d_plan_.p, h_plan_.data(), h_plan_.size() * 4, cudaMemcpyHostToDevice, stream),
                      "H2D(plan)");
@@ -851,24 +851,37 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     if (!s.ok()) return s;
     stats_.kernel_launches += 2;
   }
-  // whole-wave query blocks are scanned as one piece: their re-rank only has lists_per_piece lists to read (a small
-  // sort buffer, many blocks per SM); the blocks behind them were cut into up to s_max lists
-  const size_t q_single = (ts || pair) ? std::min(nq, (size_t)plan_single_ * qb) : 0;
-  for (int part = 0; part < 2; ++part) {
-    const size_t qb0 = part == 0 ? 0 : q_single, qc = part == 0 ? q_single : nq - q_single;
-    if (qc == 0) continue;
-    s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
-                                    mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)n_dev_, (int)nq, row_words_,
-                                    (int)k, s_max, space_ == SPACE_ANGULAR ? SCAN_ANGULAR : mode, pos_base_,
-                                    d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(),
-                                    approx_ok_ ? 0.f : x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(), stream,
-                                    (int)qb0, (int)qc, part == 0 ? (pair ? 2 : 1) : s_max,
-                                    // split operands: accumulation error + the dropped q_lo.x_lo / re-truncated terms
-                                    split ? (float)row_words_ * 2.384185791015625e-07f * 1.01f + 3.0f * 9.5367431640625e-07f + 1e-6f
-                                          : 0.f),
-                   "tc_rerank");
-    if (!s.ok()) return s;
-    ++stats_.kernel_launches;
+  // The re-rank's sort buffer (and with it how many of its blocks fit an SM) follows the number of candidate lists
+  // it may have to read: one launch per run of query blocks with the same number of pieces (whole-wave blocks were
+  // scanned as one piece, the blocks behind them in up to s_max).
+  {
+    const int lpp = pair ? 2 : 1;
+    int b0 = 0;
+    while (b0 < q_blocks) {
+      int lists = s_max, b1 = q_blocks;
+      if ((ts || pair) && (int)plan_block_slots_.size() == q_blocks) {
+        lists = std::max(1, plan_block_slots_[b0]) * lpp;
+        b1 = b0 + 1;
+        while (b1 < q_blocks && std::max(1, plan_block_slots_[b1]) * lpp == lists) ++b1;
+      }
+      const size_t q0 = (size_t)b0 * qb, q1 = std::min(nq, (size_t)b1 * qb);
+      if (q1 > q0) {
+        s = check_cuda(launch_tc_rerank(d_db_.as<float>(), static_cast<const float*>(dq),
+                                        mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, (int)n_dev_, (int)nq, row_words_,
+                                        (int)k, s_max, space_ == SPACE_ANGULAR ? SCAN_ANGULAR : mode, pos_base_,
+                                        d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(),
+                                        approx_ok_ ? 0.f : x_max_, d_flags_.as<int>(), out_keys, d_cert_.as<int>(), stream,
+                                        (int)q0, (int)(q1 - q0), std::min(lists, s_max),
+                                        // split operands: accumulation error + the dropped q_lo.x_lo / re-truncated terms
+                                        split ? (float)row_words_ * 2.384185791015625e-07f * 1.01f +
+                                                    3.0f * 9.5367431640625e-07f + 1e-6f
+                                              : 0.f),
+                       "tc_rerank");
+        if (!s.ok()) return s;
+        ++stats_.kernel_launches;
+      }
+      b0 = b1;
+    }
   }
   // certificates back to the host; re-run the (normally empty) set of uncertified queries exactly
   s = check_cuda(cudaMemcpyAsync(h_cert_.p, d_cert_.p, nq * 4, cudaMemcpyDeviceToHost, stream), "D2H(cert)");

@@ -221,7 +221,8 @@ class Engine {
   size_t plan_key_[4] = {0, 0, 0, 0};
   bool tc_split_ = false;               // 3xTF32: operands split into TF32-exact halves (see run_seq_tc)
   DevBuf d_db_split_, d_q_split_, d_sp_idx_, d_sp_q_, d_sp_keys_;
-  int plan_n_cta_ = 0, plan_s_max_ = 0, plan_single_ = 0;
+  int plan_n_cta_ = 0, plan_s_max_ = 0;
+  std::vector<int> plan_block_slots_;   // pieces per query block of the cached plan
   DevBuf d_bias_, d_db_unit_, d_flags_, d_qa_, d_cand_, d_cand_cnt_, d_cand_thr_, d_tc_keys_, d_cert_, d_fb_idx_,
       d_fb_q_, d_fb_keys_, d_nblock_, d_ones_;
   PinBuf h_cert_;

@@ -73,9 +73,9 @@ bool tc_ts_supported(int row_words);
 int tc_ts_block_points();
 // table: n_cta * 8 pieces of {query block, first tile, end tile, candidate slot} (query block -1 ends a CTA's list)
 // bn: rows per tile (0 = the TS kernel's); lists_per_piece: candidate lists a piece fills (2 for the pair kernel)
-// single_blocks: number of leading query blocks scanned as one piece (their re-rank reads lists_per_piece lists)
+// block_slots: pieces of every query block (its re-rank reads that many x lists_per_piece lists)
 void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int* n_cta, int* s_max, int bn = 0,
-                int lists_per_piece = 1, int* single_blocks = nullptr);
+                int lists_per_piece = 1, std::vector<int>* block_slots = nullptr);
 // kprime: survivors of a compaction (k + margin; the certificate needs the margin); gthr: [q_pad] uint32, filled
 // with 0xFF by the caller before every launch (best threshold published per query, shared by all CTAs)
 cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, const float* nblock, const float* ones,

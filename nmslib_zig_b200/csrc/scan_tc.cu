@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -1930,10 +1931,12 @@ int tc_ts_block_points() { return TS_BN; }
 //  * whole waves of query blocks (>= sm_count of them): one CTA = one block over the whole shard; CTAs of a wave
 //    sweep the same tiles together, so the L2 serves all but one of them;
 //  * the remaining B' < sm_count blocks: g = floor(S / B') aligned segments per block (CTAs of a segment are
-//    neighbours and share tiles in L2) covering the first g*B'/S of the tiles, and the R = S - g*B' CTAs left
-//    over split what remains of every block in equal linear ranges -- every SM gets the same number of tiles.
+//    neighbours and share tiles in L2) covering the first part of the tiles, and the R = S - g*B' CTAs left
+//    over take what remains of every block: whole tails first, unit j those of blocks j, R + j, ... (so all
+//    left-over units sweep the same tile range at the same time, too), then chunks of the B' mod R tails that
+//    remain, cut at common boundaries; the segment length is chosen so that all units finish together.
 void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int* n_cta, int* s_max, int bn,
-                int lists_per_piece, int* single_blocks) {
+                int lists_per_piece, std::vector<int>* block_slots) {
   int kprime, cap;
   tc_candidate_shape(k, &kprime, &cap);
   if (bn <= 0) bn = TS_BN;
@@ -1961,10 +1964,21 @@ void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int
     // (and a piece should be long enough to pay for its start-up: >= 16 tiles unless the shard is tiny)
     int g = std::max(1, std::min(std::min(S / Bp, full > 0 ? 4 : max_pieces - 3), std::max(1, T / 16)));
     int R = (g == S / Bp) ? S - g * Bp : 0;
-    if (R > 0 && (Bp + R - 1) / R + 1 > TS_MAXP - 2) R = 0;   // too many blocks per left-over CTA
-    long Wa = R > 0 ? ((long)T * Bp) / S : (T + g - 1) / g;
+    // Left-over units take WHOLE tails first (unit j: blocks j, R + j, ...: all units sweep the same tile range of
+    // different blocks at the same time, so the L2 serves all but one of them, like the aligned segments), then the
+    // Bp mod R tails that remain are cut into c chunks at common boundaries.  f = tails per left-over unit.
+    const int whole = R > 0 ? Bp / R : 0, rem = R > 0 ? Bp % R : 0;
+    if (R > 0 && whole + (rem > 0 ? 1 : 0) > TS_MAXP - 2) R = 0;   // too many blocks per left-over unit
+    int c = (R > 0 && rem > 0) ? std::max(1, std::min(R / rem, std::max(1, max_pieces - g))) : 0;
+    const double f = R > 0 ? (double)whole + (c > 0 ? 1.0 / c : 0.0) : 0.0;
+    // every unit finishes at the same time: Wa = f * (T - g * Wa)
+    long Wa = R > 0 ? (long)std::ceil(f * T / (1.0 + f * g)) : (T + g - 1) / g;
     if (Wa < 1) { Wa = 1; R = 0; }
-    if (R == 0) g = (int)((T + Wa - 1) / Wa);
+    if (R > 0 && (long)g * Wa >= T) R = 0;
+    if (R == 0) {
+      Wa = std::max<long>(1, (T + g - 1) / g);
+      g = (int)((T + Wa - 1) / Wa);
+    }
     const long Ta = std::min<long>((long)g * Wa, T);
     // aligned part: CTA index = seg * Bp + block, so the CTAs of a segment are launched together
     for (int seg = 0; seg < g; ++seg)
@@ -1975,16 +1989,17 @@ void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int
         add_piece(ctas.back(), full + b, (int)t0, (int)t1);
       }
     if (R > 0) {
-      const long r = T - Ta, total = (long)Bp * r, Wr = (total + R - 1) / R;
+      const long r = T - Ta;
+      const long ce = c > 0 ? (r + c - 1) / c : 0;
       for (int j = 0; j < R; ++j) {
-        const long u0 = (long)j * Wr, u1 = std::min(u0 + Wr, total);
-        if (u1 <= u0) break;
-        ctas.emplace_back();
-        for (long u = u0; u < u1;) {
-          const long b = u / r, off = u - b * r, len = std::min(r - off, u1 - u);
-          add_piece(ctas.back(), full + (int)b, (int)(Ta + off), (int)(Ta + off + len));
-          u += len;
+        std::vector<int4> u;
+        for (int p = 0; p < whole; ++p) add_piece(u, full + p * R + j, (int)Ta, (int)T);
+        if (c > 0 && j < rem * c) {  // unit q * rem + b takes chunk q of the b-th remaining tail
+          const int q = j / rem, b = j % rem;
+          const long t0 = Ta + (long)q * ce, t1 = std::min<long>(t0 + ce, T);
+          add_piece(u, full + whole * R + b, (int)t0, (int)t1);
         }
+        if (!u.empty()) ctas.push_back(u);
       }
     }
   }
@@ -2001,7 +2016,7 @@ void tc_ts_plan(int nq, int n, int k, int sm_count, std::vector<int>* table, int
     }
   *n_cta = (int)ctas.size();
   *s_max = smax;
-  if (single_blocks) *single_blocks = full;  // the leading query blocks that are scanned as ONE piece (whole waves)
+  if (block_slots) *block_slots = slots;  // pieces (candidate slots in use) of every query block
 }
 
 cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, const float* nblock, const float* ones,
