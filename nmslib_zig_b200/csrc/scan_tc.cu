@@ -692,21 +692,12 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Remote arrival with the default semantics (.release at CTA scope), as CUTLASS' ClusterBarrier::arrive does: what
+// the barriers of this kernel hand over lives in tensor memory / the async proxy and is ordered by the tcgen05
+// fences and the TMA transaction counts.  (.release.cluster / .acquire.cluster made every arrival and every wait an
+// L1 invalidation -- CCTL.IVALL + ERRBAR were 45 % of all warp samples in the first version's ncu source page.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAITC_LOOP:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAITC_DONE;\n\t"
-      "bra WAITC_LOOP;\n\t"
-      "WAITC_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // this CTA's box into its own shared memory, completion bytes on the barrier at cluster address `bar_cluster`
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1) {
@@ -818,7 +809,7 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int t = t_begin; t < t_end; ++t) {
           const int r0 = t * TP_BN + (int)rank * TC_BM;
           for (int kb = 0; kb < n_kb_all; ++kb) {
-            mbar_wait_cluster(&empty_bar[s], ph ^ 1);
+            mbar_wait(&empty_bar[s], ph ^ 1);
             unsigned char* st = smem_st + (size_t)s * stage_bytes;
             const uint32_t fb = mapa_cluster(smem_u32(&full_bar[s]), 0);
             if (elect_one()) {
@@ -855,11 +846,11 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int t_begin = pc.y, t_end = pc.z;
         for (int t = t_begin; t < t_end; ++t, ++ti) {
           const int b = ti & 1;
-          mbar_wait_cluster(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
+          mbar_wait(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d0 = tmem_base + (uint32_t)(b * TP_BN);
           for (int kb = 0; kb < p.n_kb; ++kb) {
-            mbar_wait_cluster(&full_bar[s], ph);
+            mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
             const uint64_t db = make_smem_desc(sb);
@@ -879,7 +870,7 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (p.use_nb) {  // + 1.0 * (hi + mid + lo pieces of |x|^2)
-            mbar_wait_cluster(&full_bar[s], ph);
+            mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             const uint64_t db = make_smem_desc(st_base + (uint32_t)s * (uint32_t)stage_bytes);
             if (elect_one()) {
@@ -922,7 +913,7 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float thr = row_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
       for (int tile = t_begin; tile < t_end; ++tile, ++ti) {
         const int b = ti & 1;
-        mbar_wait_cluster(&tfull_bar[b], (ti >> 1) & 1);
+        mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
         tc_fence_after();
         const uint32_t tcol = trow + (uint32_t)(b * TP_BN + ch * TC_BN);
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TP_BN + ch * TC_BN);
