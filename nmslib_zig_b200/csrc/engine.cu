@@ -667,6 +667,7 @@ Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d
                       space_ != SPACE_LINF;  // (no dot-product form: exact CUDA-core scan)
   s = use_tc ? run_seq_tc(dq, nq, k, keys, stream) : run_seq_exact(dq, nq, k, keys, stream);
   if (!s.ok()) return s;
+  if (dry_run_ && use_tc) return Status::OK();
   // sorted (distance, position) keys -> external ids + float distances (extract_knn_results, nmslib_c.cpp:293-328)
   s = check_cuda(launch_merge_topk(keys, nullptr, 1, 0, k, (int)nq, (int)k, finalize_kind(), d_ids_.as<int32_t>(),
                                    pos_base_, d_keys, d_ids, d_dists, d_counts, stream),
@@ -810,6 +811,11 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   }
   if (!(s = check_cuda(d_gthr_.ensure(q_pad * 4), "cudaMalloc(gthr)")).ok()) return s;
   if (!(s = check_cuda(cudaMemsetAsync(d_gthr_.p, 0xFF, q_pad * 4, stream), "memset(gthr)")).ok()) return s;
+  if (dry_run_) {  // (hnsw_build_gpu.cu sizes the scratch buffers for its largest batch once, instead of regrowing
+                   //  them -- cudaFree + cudaMalloc of gigabytes -- every few batches)
+    if (!ts && !split) return check_cuda(d_qa_.ensure(q_pad * (size_t)row_words_ * 4), "cudaMalloc(qa)");
+    return Status::OK();
+  }
   // survivors per compaction: k + margin.  Data that is not TF32-exact carries a pass-1 error of ~2^-9 |q||x|,
   // which at k = 100 spans tens of ranks: start with half of k there (the margin doubles when certificates fail)
   // (approx_ok_: graph construction takes the tensor-core ranking as it is -- small margin, no error band in the re-rank)

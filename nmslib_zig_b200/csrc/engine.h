@@ -85,6 +85,7 @@ bool parse_hnsw_build_params(const std::vector<std::string>& params, HnswBuildPa
 std::vector<int> hnsw_assign_levels(size_t n, double mult);  // getRandomLevel (hnsw.h:476-480), seed 0 (init.cc:34)
 struct HnswBuildInfo {
   double scan_ms = 0, select_ms = 0, link_ms = 0, total_ms = 0;
+  double setup_ms = 0, reserve_ms = 0, download_ms = 0;  // host wall clock: scan engine set-up, scratch sizing, D2H
   int batches = 0, levels = 0;
   uint64_t reverse_edges = 0, prunes = 0;
 };
@@ -136,6 +137,7 @@ class Engine {
   Status adopt_device_rows(const float* d_rows, size_t n, int dim, int row_words);
   void set_scan_rows(size_t n) { n_dev_ = n < n_ ? n : n_; }  // scan only the first n rows (prefix kNN)
   void set_approx_ok(bool v) { approx_ok_ = v; }              // keep uncertified tensor-core answers (no exact re-run)
+  void set_dry_run(bool v) { dry_run_ = v; }                  // size every scratch buffer of a batch shape, launch nothing
 
   // ---- queries ----
   // host in / host out: ids/dists are [nq][k] staging arrays owned by the engine
@@ -228,7 +230,7 @@ class Engine {
   PinBuf h_cert_;
   float x_max_ = 0.f;
   bool force_exact_ = false;
-  bool approx_ok_ = false, rows_borrowed_ = false;
+  bool approx_ok_ = false, rows_borrowed_ = false, dry_run_ = false;
   HnswBuildInfo build_info_;
   size_t n_dev_ = 0;
   DevBuf d_links0_, d_links0_cnt_, d_upper_, d_upper_off_, d_visited_, d_epoch_, d_counters_;

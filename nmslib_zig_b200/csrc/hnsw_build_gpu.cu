@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cub/cub.cuh>
+#include <chrono>
 #include <memory>
 
 #include "engine.h"
@@ -37,6 +38,9 @@ namespace nb200 {
 namespace {
 
 constexpr unsigned FULLW = 0xffffffffu;
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 constexpr int HB_MAXC = 256;    // candidates per new point (<= the scan's max k)
 constexpr int HB_MAXKEEP = 64;  // M, maxM, maxM0 <= 64
 constexpr int HB_MAXIN = 32;    // back links taken per neighbour and batch (closest first)
@@ -298,6 +302,7 @@ Status build_level(const float* d_rows_l, size_t m, int dim, int row_words, int 
   int K = std::min(HB_MAXC, efc + efc / 8 + 8);
   if (const char* e = getenv("NB200_HNSW_BUILD_K")) K = std::max(M + 1, std::min(HB_MAXC, atoi(e)));  // (experiments)
   // scan engine over the members' rows, in place.  cosine rows are unit vectors: 1 - dot ranks like -dot.
+  const double t_setup = now_ms();
   Engine scan(kind == 0 ? SPACE_L2SQR : SPACE_NEGDOT, METHOD_SEQ, false, device);
   Status s = scan.adopt_device_rows(d_rows_l, m, dim, row_words);
   if (!s.ok()) return s;
@@ -345,6 +350,28 @@ Status build_level(const float* d_rows_l, size_t m, int dim, int row_words, int 
     }
   } evguard{ev};
 
+  info->setup_ms += now_ms() - t_setup;
+  const double t_reserve = now_ms();
+  // The batches grow up to max_batch points against up to m rows: size the scan's scratch once for every batch
+  // shape of the schedule (a dry run allocates, launches nothing) instead of regrowing it every few batches.
+  {
+    scan.set_dry_run(true);
+    size_t a2 = 0;
+    while (a2 < m) {
+      size_t step = std::min(std::max<size_t>(256, (a2 / 8) / 256 * 256), max_batch);
+      const size_t b2 = std::min(m, a2 + step);
+      if (b2 >= 2) {
+        scan.set_scan_rows(b2);
+        s = scan.knn_device(d_rows_l + a2 * (size_t)row_words, b2 - a2, dim, K, d_ids.as<int32_t>(), d_dists.as<float>(),
+                            d_keys.as<uint64_t>(), nullptr, stream, (size_t)row_words * 4);
+        if (!s.ok()) return s;
+      }
+      a2 = b2;
+    }
+    scan.set_dry_run(false);
+    HB_CUDA(cudaStreamSynchronize(stream), "reserve");
+  }
+  info->reserve_ms += now_ms() - t_reserve;
   size_t a = 0;
   while (a < m) {
     // batch [a, b): at most a/8 new points (whole 256-query blocks), the first one takes 256
@@ -408,11 +435,13 @@ Status build_level(const float* d_rows_l, size_t m, int dim, int row_words, int 
     a = b;
   }
   unsigned long long prunes = 0;
+  const double t_down = now_ms();
   HB_CUDA(cudaMemcpyAsync(out->links.data(), d_links.p, m * (size_t)cap * 4, cudaMemcpyDeviceToHost, stream), "D2H");
   HB_CUDA(cudaMemcpyAsync(out->cnt.data(), d_cnt.p, m * 4, cudaMemcpyDeviceToHost, stream), "D2H");
   HB_CUDA(cudaMemcpyAsync(&prunes, d_prunes.p, 8, cudaMemcpyDeviceToHost, stream), "D2H");
   HB_CUDA(cudaStreamSynchronize(stream), "level");
   info->prunes += prunes;
+  info->download_ms += now_ms() - t_down;
   return Status::OK();
 }
 
@@ -523,9 +552,10 @@ Status build_hnsw_device(const float* d_rows, size_t n, int dim, int row_words, 
   cudaEventDestroy(t1);
   if (getenv("NB200_HNSW_BUILD_VERBOSE"))
     fprintf(stderr,
-            "[nb200] hnsw device build: n=%zu dim=%d levels=%d batches=%d total %.1f ms (scan %.1f, select %.1f, link %.1f), "
-            "%llu back links, %llu prunes\n",
+            "[nb200] hnsw device build: n=%zu dim=%d levels=%d batches=%d total %.1f ms (scan %.1f, select %.1f, link %.1f; "
+            "host: set-up %.1f, scratch sizing %.1f, download %.1f), %llu back links, %llu prunes\n",
             n, dim, info->levels, info->batches, info->total_ms, info->scan_ms, info->select_ms, info->link_ms,
+            info->setup_ms, info->reserve_ms, info->download_ms,
             (unsigned long long)info->reverse_edges, (unsigned long long)info->prunes);
   *out = std::move(g);
   return Status::OK();
