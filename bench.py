@@ -255,7 +255,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--n", type=int, default=None, help="override database rows (debug)")
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=None,
+                    help="override database rows (debug; under torchrun use --rows: its parser claims --n)")
     ap.add_argument("--nq", type=int, default=None, help="override query count (debug)")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
