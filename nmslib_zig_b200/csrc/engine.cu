@@ -766,7 +766,8 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   const size_t q_pad = round_up(nq, qb);
   const size_t n_pad = round_up(n_dev_, bn);
   const int q_blocks = (int)(q_pad / qb);
-  // equal linear ranges of the (query block x tile) grid, one CTA per SM (scan_tc.cu tc_plan)
+  // work decomposition: the host-made piece table (tc_ts_plan) for the TS kernel (rows <= 128 floats, units = SMs,
+  // 64-row tiles) and the pair kernel (longer rows, units = CTA pairs, 256-row tiles); tc_plan for the A/B kernel
   const bool ts = tc_ts_supported(rw);  // rows <= 128 floats: queries live in tensor memory
   const bool pair = !ts && tc_pair_enabled() && sm_count_ >= 2;
   int n_cta, work_per_cta = 0, s_max, aligned = 0;

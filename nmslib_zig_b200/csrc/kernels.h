@@ -57,8 +57,8 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
                               int* inexact_flag, cudaStream_t stream);
 // balanced (query block x tile) decomposition: CTAs, work items per CTA, candidate pieces per query block
 // bn = database rows per tile of the kernel that will run (tc_block_points() or tc_ts_block_points())
-void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned,
-             int lists_per_piece = 1);
+// (the single-CTA long-row kernel, kept behind NB200_TC_PAIR=0 for A/B runs)
+void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned);
 // long rows on CTA pairs (cta_group::2 MMAs, M256 x N256): plan with tc_ts_plan(nq, n, k, sm_count / 2, &table,
 // &n_pairs, &slots, tc_pair_block_points(), 2), upload the table and pass s_max = 2 * slots
 bool tc_pair_enabled();   // NB200_TC_PAIR=0 switches back to the single-CTA kernel (A/B runs)

@@ -1686,16 +1686,14 @@ cudaError_t launch_tc_prep_db(const float* db, int n, int n_pad, int row_words, 
 //  * aligned: every query block is cut into the same `s` segments; q_blocks * s CTAs.  Chosen when some s
 //    fills >= 80 % of the last wave: co-scheduled CTAs then stream the same tiles and share them in L2.
 //  * linear (few query blocks): equal linear ranges, `sm_count` CTAs, a CTA may span two query blocks.
-void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned,
-             int lists_per_piece) {
+void tc_plan(int nq, int n, int k, int sm_count, int bn, int* n_cta, int* work_per_cta, int* s_max, int* aligned) {
   int kprime, cap;
   tc_candidate_shape(k, &kprime, &cap);
   const long q_blocks = (nq + TC_QB - 1) / TC_QB;
   const long n_tiles = (n + bn - 1) / bn;
   const long total = q_blocks * n_tiles;
   // the re-rank sorts s_max * cap keys per query in shared memory: bound the pieces per query block
-  long max_pieces = std::min<long>(std::min<long>(64, std::max<long>(2, 16384 / cap)), std::max<long>(4, 3072 / kprime));
-  max_pieces = std::max<long>(1, max_pieces / std::max(1, lists_per_piece));  // (pair kernel: two lists per piece)
+  const long max_pieces = std::min<long>(std::min<long>(64, std::max<long>(2, 16384 / cap)), std::max<long>(4, 3072 / kprime));
   if (q_blocks * 4 >= sm_count || q_blocks * n_tiles <= sm_count) {
     long best = 1;
     double best_eff = 0;
