@@ -122,3 +122,23 @@ def test_device_build_uint8_rows():
     r = dev.knnQueryBatch(q, 10)
     assert recall(r.ids, exact) >= 0.95
     dev.deinit()
+
+
+@pytest.mark.parametrize("n", [1, 3, 300, 2049])
+def test_device_build_tiny_indexes(n):
+    """Forced onto the device (b200_build=device) below the automatic threshold: single batch / single level /
+    fewer rows than candidates asked for.  Every point must find itself, and on 300+ points recall must be ~1."""
+    data = synth.gist_like(max(n, 1), 24, 61, clusters=4)[:n]
+    dev = _build("l2", data, "device", {"M": 8, "efConstruction": 40})
+    assert dev.stats()["build_total_ms"] > 0
+    k = min(5, n)
+    dev.setQueryTimeParams(nb.Params({"efSearch": 100}))
+    r = dev.knnQueryBatch(data, k)
+    assert np.all(r.sizes >= 1)
+    if n >= 300:
+        exact, _, _ = O.seq_knn("l2", data, data, k)
+        assert recall(r.ids, exact) >= 0.99
+        assert np.mean(r.ids[:, 0] == np.arange(n)) >= 0.99
+    else:
+        assert np.array_equal(r.ids[:, 0], np.arange(n))
+    dev.deinit()
