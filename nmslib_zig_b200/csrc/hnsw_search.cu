@@ -19,6 +19,7 @@
 // loads (lane c reads float4 c, c+32, ...), four neighbours in flight per warp; the
 // level-0 adjacency row (maxM0 ints) is one coalesced 128-byte read.  The kernel is
 // bound by HBM random-gather bandwidth, not FLOPs.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -361,6 +362,303 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
   }
 }
 
+// ---------------------------------------------------------------- small batches: a team of 2 or 4 warps per query
+// With fewer queries than resident warps (a 10 K batch split over 8 replicas leaves 1 250 per GPU for 3 552 warps)
+// the one-warp kernel is a chain of dependent gather rounds per query and most of the machine idles.  Here a team of
+// TW warps owns ONE query: the team's warp 0 runs exactly the control flow of hnsw_search_kernel (query staging,
+// greedy descent, adjacency + visited check, beam insertion -- so the expansions, their order and every comparison
+// are the same), and the distance evaluations of an expansion are dealt out to all TW warps, EVG rows each, through
+// shared memory.  A round of up to 4 TW neighbours replaces TW rounds of four.  The per-pair arithmetic is evalG's,
+// so the answers are bit-identical to the one-warp kernel's (tests/test_hnsw_gpu.py runs all of them on one graph).
+// A block holds WARPS / TW teams; a team synchronises on its own named barrier.
+template <int TW>
+__device__ __forceinline__ void team_sync(int team) {
+  if (TW == WARPS) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(TW * 32) : "memory");
+}
+
+template <int KIND, int EVG, int TW>
+__global__ void __launch_bounds__(WARPS * 32, 6)
+hnsw_search_team_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq, int k, int ef, int cap,
+                        int cap_r, uint8_t* __restrict__ visited, size_t visited_stride,
+                        int* __restrict__ slot_epoch, uint64_t* __restrict__ out_keys,
+                        unsigned long long* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int team = (threadIdx.x >> 5) / TW, warp = (threadIdx.x >> 5) % TW;  // warp: index inside the team
+  const int tthread = warp * 32 + lane;                                     // thread index inside the team
+  const size_t per_team = (size_t)g.row_words * 4 + (size_t)cap_r * 8 + 3 * 32 * 4 + 8 * 4;
+  float* qv = reinterpret_cast<float*>(smem_raw + per_team * team);  // row_words
+  float* wkey = qv + g.row_words;                                   // cap_r
+  int* wdat = reinterpret_cast<int*>(wkey + cap_r);                 // cap_r (bit 31 = used)
+  int* pbuf = wdat + cap_r;                                         // 32
+  int* s_nb = pbuf + 32;                                            // 32: neighbours of the current chunk
+  float* s_d = reinterpret_cast<float*>(s_nb + 32);                 // 32: their distances
+  int* s_ctl = reinterpret_cast<int*>(s_d + 32);                    // 8: qi, cur, n_w, fresh mask, more-chunks flag
+  const float4* q4 = reinterpret_cast<const float4*>(qv);
+
+  const int slot = blockIdx.x * (WARPS / TW) + team;
+  uint8_t* vis = visited + (size_t)slot * visited_stride;
+  unsigned long long n_eval = 0, n_exp = 0;
+
+  // evaluation service: every warp takes every fourth group of EVG fresh neighbours of the published chunk
+  auto team_eval = [&]() {
+    unsigned mask = (unsigned)s_ctl[3];
+    const int nb = s_nb[lane];
+    int grp = 0;
+    while (mask) {
+      int t[EVG], src[EVG], cnt = 0;
+#pragma unroll
+      for (int gq = 0; gq < EVG; ++gq) {
+        src[gq] = 0;
+        t[gq] = 0;
+        if (mask) {
+          src[gq] = __ffs(mask) - 1;
+          mask &= mask - 1;
+          ++cnt;
+        }
+      }
+      if ((grp++ % TW) != warp) continue;
+#pragma unroll
+      for (int gq = 0; gq < EVG; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
+      float d[EVG];
+      evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, cnt, lane, d);
+#pragma unroll
+      for (int gq = 0; gq < EVG; ++gq)
+        if (gq < cnt && lane == 0) s_d[src[gq]] = d[gq];
+    }
+  };
+
+  for (;;) {
+    if (tthread == 0) s_ctl[0] = (int)atomicAdd(&counters[2], 1ull);
+    team_sync<TW>(team);
+    const int qi = s_ctl[0];
+    if (qi >= nq) break;
+    // ---- visited epoch (VisitedList::reset, hnsw.h:575-582) ----
+    int epoch = slot_epoch[slot] + 1;
+    team_sync<TW>(team);
+    if (epoch > 255) {
+      uint4 z = make_uint4(0, 0, 0, 0);
+      for (size_t o = (size_t)tthread * 16; o < visited_stride; o += TW * 32 * 16)
+        *reinterpret_cast<uint4*>(vis + o) = z;
+      epoch = 1;
+    }
+    if (tthread == 0) slot_epoch[slot] = epoch;
+    const uint8_t ep = (uint8_t)epoch;
+    team_sync<TW>(team);
+
+    int n_w = 1, cur = 0;
+    if (warp == 0) {
+      // ---- stage the query (cosine: NormalizeVect, hnsw.h:486-497): the one-warp kernel's arithmetic ----
+      const float* qsrc = queries + (size_t)qi * g.row_words;
+      float ss = 0.f;
+      for (int c = lane; c < g.row_words; c += 32) {
+        const float v = qsrc[c];
+        qv[c] = v;
+        ss = fmaf(v, v, ss);
+      }
+      if constexpr (KIND == 1) {
+        ss = warp_sum(ss);
+        if (ss != 0.f) {
+          const float sc = 1.f / sqrtf(ss);
+          for (int c = lane; c < g.row_words; c += 32) qv[c] *= sc;
+        }
+      }
+      __syncwarp();
+      // ---- greedy descent through the upper layers (hnsw_distfunc_opt.cc:168-198), warp 0 alone ----
+      int cur_node = g.enterpoint;
+      float cur_dist;
+      {
+        int t[EVG] = {cur_node};
+        float d[EVG];
+        evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, 1, lane, d);
+        cur_dist = d[0];
+        ++n_eval;
+      }
+      for (int level = g.maxlevel; level > 0; --level) {
+        bool changed = true;
+        while (changed) {
+          changed = false;
+          const int32_t* lk = g.upper + g.upper_off[cur_node] + (size_t)(level - 1) * (g.maxM + 1);
+          const int size = lk[0];
+          for (int b0 = 0; b0 < size; b0 += 32) {
+            const int nb = (b0 + lane < size) ? lk[1 + b0 + lane] : -1;
+            unsigned mask = __ballot_sync(FULL, nb >= 0);
+            float my_d = __int_as_float(0x7F800000);
+            while (mask) {
+              int t[EVG], src[EVG], cnt = 0;
+#pragma unroll
+              for (int gq = 0; gq < EVG; ++gq) {
+                src[gq] = 0;
+                t[gq] = 0;
+                if (mask) {
+                  src[gq] = __ffs(mask) - 1;
+                  mask &= mask - 1;
+                  ++cnt;
+                }
+              }
+#pragma unroll
+              for (int gq = 0; gq < EVG; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
+              float d[EVG];
+              evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, cnt, lane, d);
+              n_eval += cnt;
+#pragma unroll
+              for (int gq = 0; gq < EVG; ++gq)
+                if (gq < cnt && lane == src[gq]) my_d = d[gq];
+            }
+            uint64_t best = ((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const uint64_t other = __shfl_xor_sync(FULL, best, o);
+              best = other < best ? other : best;
+            }
+            const int bl = (int)(best & 31u);
+            const float bd = __shfl_sync(FULL, my_d, bl);
+            const int bn = __shfl_sync(FULL, nb, bl);
+            if (bn >= 0 && bd < cur_dist) {
+              cur_dist = bd;
+              cur_node = bn;
+              changed = true;
+            }
+          }
+        }
+      }
+      if (lane == 0) {
+        wkey[0] = cur_dist;
+        wdat[0] = cur_node;
+        vis[cur_node] = ep;
+        s_ctl[1] = 0;  // cur
+        s_ctl[2] = 1;  // n_w
+      }
+    }
+    team_sync<TW>(team);
+
+    // ---- level-0 beam (hnsw_distfunc_opt.cc:200-274): warp 0 decides, everybody evaluates ----
+    for (;;) {
+      cur = s_ctl[1];
+      n_w = s_ctl[2];
+      if (!(cur < min(n_w, ef))) break;
+      int node = 0, size = 0;
+      float top_key = 0.f;
+      bool grow = false;
+      if (warp == 0) {
+        node = wdat[cur] & ~USED_BIT;
+        __syncwarp();
+        if (lane == 0) wdat[cur] |= USED_BIT;
+        ++cur;
+        ++n_exp;
+        top_key = wkey[n_w - 1];
+        grow = n_w < ef;
+        __syncwarp();
+        size = g.links0_cnt[node];
+      }
+      for (int b0 = 0;; b0 += 32) {
+        int nb = -1;
+        bool fresh = false;
+        if (warp == 0) {
+          nb = (b0 + lane < size) ? g.links0[(size_t)node * g.maxM0 + b0 + lane] : -1;
+          if (nb >= 0) {
+            fresh = vis[nb] != ep;
+            if (fresh) vis[nb] = ep;
+          }
+          const unsigned mask = __ballot_sync(FULL, fresh);
+          s_nb[lane] = nb;
+          if (lane == 0) {
+            s_ctl[3] = (int)mask;
+            s_ctl[4] = b0 < size ? 1 : 0;  // 0: no such chunk, the expansion is over
+          }
+          n_eval += __popc(mask);
+        }
+        team_sync<TW>(team);
+        if (!s_ctl[4]) break;
+        team_eval();
+        team_sync<TW>(team);
+        if (warp == 0) {
+          const float my_d = fresh ? s_d[lane] : __int_as_float(0x7F800000);
+          const bool accept = fresh && (my_d < top_key || grow);
+          const int m = __popc(__ballot_sync(FULL, accept));
+          if (m != 0) {
+            uint64_t item = accept ? (((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)nb) : KEY_MAX;
+            item = warp_sort64(item, lane);
+            const float d_i = f32_from_ordered((uint32_t)(item >> 32));
+            const int t_i = (int)(uint32_t)item;
+            int p_i = n_w;
+            if (lane < m) {
+              int lo = 0, hi = n_w;
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (wkey[mid] <= d_i) lo = mid + 1; else hi = mid;
+              }
+              p_i = lo;
+            }
+            pbuf[lane] = lane < m ? p_i : 0x7FFFFFFF;
+            __syncwarp();
+            const int p0 = pbuf[0];
+            if (p0 < n_w) {
+              for (int cb = ((n_w - 1) >> 5) << 5; cb >= ((p0 >> 5) << 5); cb -= 32) {
+                const int a = cb + lane;
+                const bool valid = a < n_w && a >= p0;
+                float ka = 0.f;
+                int da = 0, c = 0;
+                if (valid) {
+                  ka = wkey[a];
+                  da = wdat[a];
+                  for (int i = 0; i < m; ++i) c += (pbuf[i] <= a) ? 1 : 0;
+                }
+                __syncwarp();
+                if (valid && a + c < cap) {
+                  wkey[a + c] = ka;
+                  wdat[a + c] = da;
+                }
+                __syncwarp();
+              }
+            }
+            if (lane < m && p_i + lane < cap) {
+              wkey[p_i + lane] = d_i;
+              wdat[p_i + lane] = t_i;
+            }
+            n_w = min(cap, n_w + m);
+            if (p0 < cur) cur = p0;
+            __syncwarp();
+          }
+        }
+        // (the next chunk's publication overwrites s_nb / s_ctl[3..4]: everybody has read them before this barrier)
+        team_sync<TW>(team);
+      }
+      if (warp == 0) {
+        while (cur < n_w) {  // advance to the first unused item (hnsw_distfunc_opt.cc:272)
+          const int a = cur + lane;
+          const bool unused = a < n_w && !(wdat[a] & USED_BIT);
+          const unsigned um = __ballot_sync(FULL, unused);
+          if (um) {
+            cur += __ffs(um) - 1;
+            break;
+          }
+          cur += 32;
+        }
+        if (cur > n_w) cur = n_w;
+        if (lane == 0) {
+          s_ctl[1] = cur;
+          s_ctl[2] = n_w;
+        }
+      }
+      team_sync<TW>(team);
+    }
+
+    // ---- W[0..k) -> keys (hnsw_distfunc_opt.cc:276-281) ----
+    for (int e = tthread; e < k; e += TW * 32) {
+      uint64_t key = KEY_MAX;
+      if (e < n_w) key = make_key(f32_ordered(wkey[e]), (uint32_t)(wdat[e] & ~USED_BIT));
+      out_keys[(size_t)qi * k + e] = key;
+    }
+    team_sync<TW>(team);
+  }
+  if (tthread == 0) {
+    atomicAdd(&counters[0], n_eval);
+    atomicAdd(&counters[1], n_exp);
+  }
+}
+
 }  // namespace
 
 int hnsw_max_ef() { return MAX_EF; }
@@ -390,6 +688,52 @@ cudaError_t launch_hnsw_search(const HnswDeviceGraph& g, const float* queries, i
     return e2 ? atoi(e2) : 6;
   }();
   cudaMemsetAsync(counters + 2, 0, 8, stream);  // next query index
+  // few queries: a team of 4 or 2 warps per query (hnsw_search_team_kernel); the one-warp kernel keeps 4 x the
+  // resident blocks' worth of queries in flight, so it wins as soon as the batch fills that
+  static const int team_mode = [] {  // -1 auto, 0 never, 2 / 4 always that team size (A/B runs)
+    const char* e2 = getenv("NB200_HNSW_TEAM");
+    return e2 ? atoi(e2) : -1;
+  }();
+  {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int resident = 6 * sms;  // blocks of 4 warps per wave at the kernels' occupancy
+    int tw = 0;
+    if (team_mode == 2 || team_mode == 4) tw = team_mode;
+    else if (team_mode == 1) tw = 4;
+    else if (team_mode < 0) tw = nq <= resident * 3 / 2 ? 4 : nq <= resident * 3 ? 2 : 0;
+    if (tw) {
+      const size_t per_team = (size_t)g.row_words * 4 + (size_t)cap_r * 8 + 3 * 32 * 4 + 8 * 4;
+      const int teams = WARPS / tw;
+      const size_t tsmem = per_team * teams;
+#define NB_TEAM(KIND, TWV)                                                                                            \
+  {                                                                                                                   \
+    e = cudaFuncSetAttribute(hnsw_search_team_kernel<KIND, 4, TWV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                             (int)tsmem);                                                                             \
+    if (e != cudaSuccess) return e;                                                                                   \
+    int occ = 0;                                                                                                      \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hnsw_search_team_kernel<KIND, 4, TWV>, WARPS * 32, tsmem);    \
+    int tb = std::min(slots / teams, std::max(1, occ) * sms); /* one resident wave: a team owns its visited array */  \
+    if (tb > (nq + teams - 1) / teams) tb = (nq + teams - 1) / teams;                                                 \
+    hnsw_search_team_kernel<KIND, 4, TWV><<<tb, WARPS * 32, tsmem, stream>>>(g, queries, nq, k, ef, cap, cap_r,        \
+                                                                             visited, vstride, slot_epoch, out_keys,  \
+                                                                             counters);                               \
+  }
+#define NB_TEAM2(KIND)          \
+  if (tw == 4) NB_TEAM(KIND, 4) \
+  else NB_TEAM(KIND, 2)
+      switch (g.dist_kind) {
+        case 0: NB_TEAM2(0); break;
+        case 1: NB_TEAM2(1); break;
+        case 2: NB_TEAM2(2); break;
+        default: return cudaErrorInvalidValue;
+      }
+#undef NB_TEAM2
+#undef NB_TEAM
+      return cudaGetLastError();
+    }
+  }
 #define NB_HNSW3(KIND, G, MB)                                                                                   \
   {                                                                                                             \
     e = cudaFuncSetAttribute(hnsw_search_kernel<KIND, G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

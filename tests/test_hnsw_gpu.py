@@ -162,3 +162,30 @@ def test_same_graph_live_reference_ef_sweep(space, n, dim, params, tmp_path):
         assert rec_gpu >= rec_ref - 2e-3, f"{space} ef={ef}: recall {rec_gpu} < reference {rec_ref}"
         assert agreement(r.ids, ri) >= 0.99, f"{space} ef={ef}: agreement {agreement(r.ids, ri)}"
     idx.deinit()
+
+
+def test_team_kernel_answers_are_bit_identical_to_the_one_warp_kernel(tmp_path):
+    """Small batches run a team of 2 or 4 warps per query (hnsw_search_team_kernel): same expansions, same arithmetic
+    per pair, so the same keys.  The switch is read once per process, hence one child process per kernel."""
+    import subprocess
+    import sys
+    script = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {str(Path(__file__).resolve().parents[1])!r})\n"
+        "import nmslib_zig_b200 as nb\n"
+        "from nmslib_zig_b200 import synth\n"
+        "data, q = synth.gist_like(20000, 96, 5, clusters=16), synth.gist_like(700, 96, 6, clusters=16)\n"
+        "idx = nb.Index('cosinesimil', None, 'hnsw'); idx.addDenseBatch(data)\n"
+        "idx.buildIndex(nb.Params({'M': 16, 'efConstruction': 100, 'b200_build': 'host', 'indexThreadQty': 1}))\n"
+        "out = []\n"
+        "for ef in (10, 64, 300, 1000):\n"
+        "    idx.setQueryTimeParams(nb.Params({'efSearch': ef}))\n"
+        "    r = idx.knnQueryBatch(q, 10); out += [r.ids, r.distances.view(np.int32)]\n"
+        "np.save(sys.argv[1], np.stack(out))\n")
+    outs = []
+    for mode in ("0", "2", "4"):
+        path = tmp_path / f"team{mode}.npy"
+        env = dict(**__import__("os").environ, NB200_HNSW_TEAM=mode)
+        subprocess.run([sys.executable, "-c", script, str(path)], check=True, env=env, timeout=600)
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])

@@ -27,6 +27,8 @@ if sys.argv[1] == "build":
     print("built", n, dim, idx.stats()["build_total_ms"], "ms")
 else:
     q = np.load("/tmp/nb200_ab_q.npy")
+    if len(sys.argv) > 2:
+        q = q[:int(sys.argv[2])]
     idx = nb.Index("cosinesimil", None, "hnsw")
     idx.importHnsw(P)
     idx.prepare()
@@ -39,4 +41,4 @@ else:
         s1 = idx.stats()
         ms = s1["scan_ms_sum"] - s0["scan_ms_sum"]
         ev = s1["distance_evals"] - s0["distance_evals"]
-        print(tag, "ef", ef, "kernel_ms %.2f" % ms, "GB/s %.0f" % (ev * 4.0 * q.shape[1] / 1e6 / ms), "ids_sum", int(r.ids.sum()))
+        print(tag, "nq", len(q), "ef", ef, "kernel_ms %.2f" % ms, "GB/s %.0f" % (ev * 4.0 * q.shape[1] / 1e6 / ms), "ids_sum", int(r.ids.sum()))
