@@ -224,6 +224,29 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
         gbytes = (evals * 4.0 * dim + exps * 4.0 * 32) / 1e9          # rows gathered + adjacency lists read
         achieved = gbytes / max(1e-9, kern_ms * launches_per_step * 1e-3)
         cpu = None
+        if world == 1 and not args.no_cpu:
+            # the REFERENCE's own HNSW search (Index::LoadIndex + Search through oracle/_ref, OpenMP over queries on all
+            # host cores) on the SAME device-built graph, same efSearch, a bounded query sample
+            from oracle import oracle as O
+            if O.ref_available():
+                path = "/tmp/nb200_bench_c3.hnsw"
+                idx.save(path, False)
+                threads = os.cpu_count() or 1
+                ref = O.RefIndex(w["space"], "hnsw").load(path)
+                ref.set_query_params(f"efSearch={ef}")
+                ref.knn(sample[:64], k, threads=threads)
+                t0 = time.perf_counter()
+                ri, _, _ = ref.knn(sample, k, threads=threads)
+                dt = time.perf_counter() - t0
+                rec_ref = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(ri, exact_ids)]))
+                cpu = {"value": len(sample) / dt, "unit": "queries/s", "cores": threads, "kind": "reference",
+                       "sample": f"{len(sample)} of {nq} queries, the reference's Hnsw::Search on the same (device-built) "
+                                 f"graph at efSearch={ef}; its recall@{k} on that sample: {rec_ref:.4f} (ours: {rec:.4f})"}
+                ref.close()
+                try:
+                    os.remove(path)
+                except OSError:
+                    pass
         line = {
             "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -168,6 +168,8 @@ def harness():
         L.refh_knn_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                      _i32p, _f32p, _i32p, C.c_int]
         L.refh_save.argtypes = [C.c_void_p, C.c_char_p]
+        if hasattr(L, "refh_load"):
+            L.refh_load.argtypes = [C.c_void_p, C.c_char_p]
         L.refh_size.restype = C.c_size_t
         L.refh_size.argtypes = [C.c_void_p]
         L.refh_last_error.restype = C.c_char_p
@@ -223,6 +225,11 @@ class RefIndex:
 
     def save(self, path):
         self._chk(self.L.refh_save(self.h, str(path).encode()), "save")
+
+    def load(self, path):
+        """Index::LoadIndex of an optimized HNSW file (e.g. one written by nmslib_b200's nmslib_save_index)."""
+        self._chk(self.L.refh_load(self.h, str(path).encode()), "load")
+        return self
 
     def max_threads(self):
         return int(self.L.refh_max_threads())

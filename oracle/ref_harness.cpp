@@ -55,6 +55,7 @@ struct HarnessBase {
   virtual int knn(const void* q, size_t nq, size_t dim, size_t k, int32_t* ids, float* dists,
                   int32_t* counts, int threads) = 0;
   virtual int save(const char* path) = 0;
+  virtual int load(const char* path) = 0;
   virtual size_t size() const = 0;
   std::string err;
 };
@@ -155,6 +156,19 @@ struct Harness : HarnessBase {
       return -2;
     }
   }
+  // Index::LoadIndex on an empty data set, the way nmslib_load_index does it (nmslib_c.cpp:1428-1435): the
+  // optimized HNSW stream carries the vectors itself.  Used to let the REFERENCE search a graph this library built.
+  int load(const char* path) override {
+    try {
+      index.reset(MethodFactoryRegistry<dist_t>::Instance().CreateMethod(
+          false, method_name, space_name, *space, data));
+      index->LoadIndex(path);
+      return 0;
+    } catch (const std::exception& e) {
+      err = e.what();
+      return -2;
+    }
+  }
 };
 
 }  // namespace
@@ -200,6 +214,7 @@ int refh_knn_batch(void* h, const void* q, size_t nq, size_t dim, size_t k, int3
   return static_cast<HarnessBase*>(h)->knn(q, nq, dim, k, ids, dists, counts, threads);
 }
 int refh_save(void* h, const char* path) { return static_cast<HarnessBase*>(h)->save(path); }
+int refh_load(void* h, const char* path) { return static_cast<HarnessBase*>(h)->load(path); }
 size_t refh_size(void* h) { return static_cast<HarnessBase*>(h)->size(); }
 const char* refh_last_error(void* h) { return static_cast<HarnessBase*>(h)->err.c_str(); }
 int refh_max_threads(void) { return omp_get_max_threads(); }

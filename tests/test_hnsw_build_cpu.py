@@ -95,3 +95,22 @@ def test_b200_build_parameter_is_accepted_and_host_is_honoured(tmp_path):
     with pytest.raises(nb.NmslibError):
         idx.buildIndex(nb.Params({"M": 8, "b200_where": "host"}))
     idx.deinit()
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+def test_reference_searches_our_graph_through_its_cpp_api(tmp_path):
+    """The reference's own Index::LoadIndex + Search (ref_harness.cpp, efSearch settable -- its C ABI pins 200) on a
+    graph built here: the answers are those of the oracle's port of its search on the same file."""
+    data = synth.gist_like(4000, 24, 43, clusters=8)
+    q = synth.gist_like(64, 24, 44, clusters=8)
+    path = tmp_path / "ours.hnsw"
+    _build("cosinesimil", data, {"M": 10, "efConstruction": 80}, path)
+    ref = O.RefIndex("cosinesimil", "hnsw").load(path)
+    port = O.PortHnsw(path)
+    for ef in (10, 50, 300):
+        ref.set_query_params(f"efSearch={ef}")
+        ri, rd, rc = ref.knn(q, 10, threads=4)
+        pi, pd, pc, _ = port.knn(q, 10, ef)
+        assert np.array_equal(rc, pc) and np.mean(ri == pi) >= 0.995
+    port.close()
+    ref.close()
