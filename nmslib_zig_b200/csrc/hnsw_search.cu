@@ -118,6 +118,159 @@ __device__ __forceinline__ uint64_t warp_sort64(uint64_t v, int lane) {
   return v;
 }
 
+// ---- pieces shared by the one-warp kernel and the team kernel (one warp executes each of them) ----------------
+
+// stage the query in shared memory (cosine: NormalizeVect, hnsw.h:486-497)
+template <int KIND>
+__device__ __forceinline__ void stage_query(const float* __restrict__ qsrc, float* qv, int row_words, int lane) {
+  float ss = 0.f;
+  for (int c = lane; c < row_words; c += 32) {
+    const float v = qsrc[c];
+    qv[c] = v;
+    ss = fmaf(v, v, ss);
+  }
+  if constexpr (KIND == 1) {
+    ss = warp_sum(ss);
+    if (ss != 0.f) {
+      const float sc = 1.f / sqrtf(ss);
+      for (int c = lane; c < row_words; c += 32) qv[c] *= sc;
+    }
+  }
+  __syncwarp();
+}
+
+// greedy descent through the upper layers (hnsw_distfunc_opt.cc:168-198): ends at the level-0 entry node
+template <int KIND, int EVG>
+__device__ __forceinline__ void greedy_descent(const HnswDeviceGraph& g, const float4* q4, int lane, int& cur_node,
+                                               float& cur_dist, unsigned long long& n_eval) {
+  cur_node = g.enterpoint;
+  {
+    int t[EVG] = {cur_node};
+    float d[EVG];
+    evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, 1, lane, d);
+    cur_dist = d[0];
+    ++n_eval;
+  }
+  for (int level = g.maxlevel; level > 0; --level) {
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      const int32_t* lk = g.upper + g.upper_off[cur_node] + (size_t)(level - 1) * (g.maxM + 1);
+      const int size = lk[0];
+      for (int b0 = 0; b0 < size; b0 += 32) {
+        const int nb = (b0 + lane < size) ? lk[1 + b0 + lane] : -1;
+        unsigned mask = __ballot_sync(FULL, nb >= 0);
+        float my_d = __int_as_float(0x7F800000);
+        while (mask) {
+          int t[EVG], src[EVG], cnt = 0;
+#pragma unroll
+          for (int gq = 0; gq < EVG; ++gq) {
+            src[gq] = 0;
+            t[gq] = 0;
+            if (mask) {
+              src[gq] = __ffs(mask) - 1;
+              mask &= mask - 1;
+              ++cnt;
+            }
+          }
+#pragma unroll
+          for (int gq = 0; gq < EVG; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
+          float d[EVG];
+          evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, cnt, lane, d);
+          n_eval += cnt;
+#pragma unroll
+          for (int gq = 0; gq < EVG; ++gq)
+            if (gq < cnt && lane == src[gq]) my_d = d[gq];
+        }
+        // sequential "if (d < curdist)" over j == first minimum over the list
+        uint64_t best = ((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const uint64_t other = __shfl_xor_sync(FULL, best, o);
+          best = other < best ? other : best;
+        }
+        const int bl = (int)(best & 31u);
+        const float bd = __shfl_sync(FULL, my_d, bl);
+        const int bn = __shfl_sync(FULL, nb, bl);
+        if (bn >= 0 && bd < cur_dist) {
+          cur_dist = bd;
+          cur_node = bn;
+          changed = true;
+        }
+      }
+    }
+  }
+}
+
+// merge the accepted neighbours of one adjacency chunk (one per lane) into the beam W: SortArrBI's
+// merge_with_sorted_items (sort_arr_bi.h:159-199) -- new items go after equal old ones, the tail shifts up and is
+// truncated at the capacity, cur rewinds to the smallest insertion index
+__device__ __forceinline__ void beam_insert(bool accept, float my_d, int nb, float* wkey, int* wdat, int* pbuf, int cap,
+                                            int lane, int& n_w, int& cur) {
+  const int m = __popc(__ballot_sync(FULL, accept));
+  if (m == 0) return;
+  // sort the accepted candidates; lane i < m ends with the i-th smallest
+  uint64_t item = accept ? (((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)nb) : KEY_MAX;
+  item = warp_sort64(item, lane);
+  const float d_i = f32_from_ordered((uint32_t)(item >> 32));
+  const int t_i = (int)(uint32_t)item;
+  // p_i = number of beam items with key <= d_i (new items go after equal old ones)
+  int p_i = n_w;
+  if (lane < m) {
+    int lo = 0, hi = n_w;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (wkey[mid] <= d_i) lo = mid + 1; else hi = mid;
+    }
+    p_i = lo;
+  }
+  pbuf[lane] = lane < m ? p_i : 0x7FFFFFFF;
+  __syncwarp();
+  const int p0 = pbuf[0];
+  // shift the tail of the beam, highest chunk first
+  if (p0 < n_w) {
+    for (int cb = ((n_w - 1) >> 5) << 5; cb >= ((p0 >> 5) << 5); cb -= 32) {
+      const int a = cb + lane;
+      const bool valid = a < n_w && a >= p0;
+      float ka = 0.f;
+      int da = 0, c = 0;
+      if (valid) {
+        ka = wkey[a];
+        da = wdat[a];
+        for (int i = 0; i < m; ++i) c += (pbuf[i] <= a) ? 1 : 0;
+      }
+      __syncwarp();
+      if (valid && a + c < cap) {
+        wkey[a + c] = ka;
+        wdat[a + c] = da;
+      }
+      __syncwarp();
+    }
+  }
+  if (lane < m && p_i + lane < cap) {
+    wkey[p_i + lane] = d_i;
+    wdat[p_i + lane] = t_i;
+  }
+  n_w = min(cap, n_w + m);
+  if (p0 < cur) cur = p0;  // p_0 + 0 is the smallest insertion index (sort_arr_bi.h:159-199)
+  __syncwarp();
+}
+
+// advance to the first unused item of the beam (hnsw_distfunc_opt.cc:272)
+__device__ __forceinline__ void beam_advance(const int* wdat, int n_w, int lane, int& cur) {
+  while (cur < n_w) {
+    const int a = cur + lane;
+    const bool unused = a < n_w && !(wdat[a] & USED_BIT);
+    const unsigned um = __ballot_sync(FULL, unused);
+    if (um) {
+      cur += __ffs(um) - 1;
+      break;
+    }
+    cur += 32;
+  }
+  if (cur > n_w) cur = n_w;
+}
+
 template <int KIND, int EVG, int MINB>  // EVG: neighbour vectors gathered at once per warp
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq, int k, int ef, int cap,
@@ -157,82 +310,10 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
     const uint8_t ep = (uint8_t)epoch;
     __syncwarp();
 
-    // ---- stage the query (cosine: NormalizeVect, hnsw.h:486-497) ----
-    const float* qsrc = queries + (size_t)qi * g.row_words;
-    float ss = 0.f;
-    for (int c = lane; c < g.row_words; c += 32) {
-      const float v = qsrc[c];
-      qv[c] = v;
-      ss = fmaf(v, v, ss);
-    }
-    if constexpr (KIND == 1) {
-      ss = warp_sum(ss);
-      if (ss != 0.f) {
-        const float sc = 1.f / sqrtf(ss);
-        for (int c = lane; c < g.row_words; c += 32) qv[c] *= sc;
-      }
-    }
-    __syncwarp();
-
-    // ---- greedy descent through the upper layers (hnsw_distfunc_opt.cc:168-198) ----
-    int cur_node = g.enterpoint;
+    stage_query<KIND>(queries + (size_t)qi * g.row_words, qv, g.row_words, lane);
+    int cur_node;
     float cur_dist;
-    {
-      int t[EVG] = {cur_node};
-      float d[EVG];
-      evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, 1, lane, d);
-      cur_dist = d[0];
-      ++n_eval;
-    }
-    for (int level = g.maxlevel; level > 0; --level) {
-      bool changed = true;
-      while (changed) {
-        changed = false;
-        const int32_t* lk = g.upper + g.upper_off[cur_node] + (size_t)(level - 1) * (g.maxM + 1);
-        const int size = lk[0];
-        for (int b0 = 0; b0 < size; b0 += 32) {
-          const int nb = (b0 + lane < size) ? lk[1 + b0 + lane] : -1;
-          unsigned mask = __ballot_sync(FULL, nb >= 0);
-          float my_d = __int_as_float(0x7F800000);
-          while (mask) {
-            int t[EVG], src[EVG], cnt = 0;
-#pragma unroll
-            for (int gq = 0; gq < EVG; ++gq) {
-              src[gq] = 0;
-              t[gq] = 0;
-              if (mask) {
-                src[gq] = __ffs(mask) - 1;
-                mask &= mask - 1;
-                ++cnt;
-              }
-            }
-#pragma unroll
-            for (int gq = 0; gq < EVG; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
-            float d[EVG];
-            evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, cnt, lane, d);
-            n_eval += cnt;
-#pragma unroll
-            for (int gq = 0; gq < EVG; ++gq)
-              if (gq < cnt && lane == src[gq]) my_d = d[gq];
-          }
-          // sequential "if (d < curdist)" over j == first minimum over the list
-          uint64_t best = ((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)lane;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const uint64_t other = __shfl_xor_sync(FULL, best, o);
-            best = other < best ? other : best;
-          }
-          const int bl = (int)(best & 31u);
-          const float bd = __shfl_sync(FULL, my_d, bl);
-          const int bn = __shfl_sync(FULL, nb, bl);
-          if (bn >= 0 && bd < cur_dist) {
-            cur_dist = bd;
-            cur_node = bn;
-            changed = true;
-          }
-        }
-      }
-    }
+    greedy_descent<KIND, EVG>(g, q4, lane, cur_node, cur_dist, n_eval);
 
     // ---- level-0 beam (hnsw_distfunc_opt.cc:200-274) ----
     int n_w = 1, cur = 0;
@@ -283,68 +364,9 @@ hnsw_search_kernel(HnswDeviceGraph g, const float* __restrict__ queries, int nq,
           for (int gq = 0; gq < EVG; ++gq)
             if (gq < cnt && lane == src[gq]) my_d = d[gq];
         }
-        const bool accept = fresh && (my_d < top_key || grow);
-        const int m = __popc(__ballot_sync(FULL, accept));
-        if (m == 0) continue;
-
-        // sort the accepted candidates; lane i < m ends with the i-th smallest
-        uint64_t item = accept ? (((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)nb) : KEY_MAX;
-        item = warp_sort64(item, lane);
-        const float d_i = f32_from_ordered((uint32_t)(item >> 32));
-        const int t_i = (int)(uint32_t)item;
-        // p_i = number of beam items with key <= d_i (new items go after equal old ones)
-        int p_i = n_w;
-        if (lane < m) {
-          int lo = 0, hi = n_w;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (wkey[mid] <= d_i) lo = mid + 1; else hi = mid;
-          }
-          p_i = lo;
-        }
-        pbuf[lane] = lane < m ? p_i : 0x7FFFFFFF;
-        __syncwarp();
-        const int p0 = pbuf[0];
-        // shift the tail of the beam, highest chunk first
-        if (p0 < n_w) {
-          for (int cb = ((n_w - 1) >> 5) << 5; cb >= ((p0 >> 5) << 5); cb -= 32) {
-            const int a = cb + lane;
-            const bool valid = a < n_w && a >= p0;
-            float ka = 0.f;
-            int da = 0, c = 0;
-            if (valid) {
-              ka = wkey[a];
-              da = wdat[a];
-              for (int i = 0; i < m; ++i) c += (pbuf[i] <= a) ? 1 : 0;
-            }
-            __syncwarp();
-            if (valid && a + c < cap) {
-              wkey[a + c] = ka;
-              wdat[a + c] = da;
-            }
-            __syncwarp();
-          }
-        }
-        if (lane < m && p_i + lane < cap) {
-          wkey[p_i + lane] = d_i;
-          wdat[p_i + lane] = t_i;
-        }
-        n_w = min(cap, n_w + m);
-        if (p0 < cur) cur = p0;  // p_0 + 0 is the smallest insertion index (sort_arr_bi.h:159-199)
-        __syncwarp();
+        beam_insert(fresh && (my_d < top_key || grow), my_d, nb, wkey, wdat, pbuf, cap, lane, n_w, cur);
       }
-      // advance to the first unused item (hnsw_distfunc_opt.cc:272)
-      while (cur < n_w) {
-        const int a = cur + lane;
-        const bool unused = a < n_w && !(wdat[a] & USED_BIT);
-        const unsigned um = __ballot_sync(FULL, unused);
-        if (um) {
-          cur += __ffs(um) - 1;
-          break;
-        }
-        cur += 32;
-      }
-      if (cur > n_w) cur = n_w;
+      beam_advance(wdat, n_w, lane, cur);
     }
 
     // ---- W[0..k) -> keys (hnsw_distfunc_opt.cc:276-281) ----
@@ -449,80 +471,11 @@ hnsw_search_team_kernel(HnswDeviceGraph g, const float* __restrict__ queries, in
 
     int n_w = 1, cur = 0;
     if (warp == 0) {
-      // ---- stage the query (cosine: NormalizeVect, hnsw.h:486-497): the one-warp kernel's arithmetic ----
-      const float* qsrc = queries + (size_t)qi * g.row_words;
-      float ss = 0.f;
-      for (int c = lane; c < g.row_words; c += 32) {
-        const float v = qsrc[c];
-        qv[c] = v;
-        ss = fmaf(v, v, ss);
-      }
-      if constexpr (KIND == 1) {
-        ss = warp_sum(ss);
-        if (ss != 0.f) {
-          const float sc = 1.f / sqrtf(ss);
-          for (int c = lane; c < g.row_words; c += 32) qv[c] *= sc;
-        }
-      }
-      __syncwarp();
-      // ---- greedy descent through the upper layers (hnsw_distfunc_opt.cc:168-198), warp 0 alone ----
-      int cur_node = g.enterpoint;
+      // query staging and greedy descent by the team's warp 0 alone: the one-warp kernel's arithmetic
+      stage_query<KIND>(queries + (size_t)qi * g.row_words, qv, g.row_words, lane);
+      int cur_node;
       float cur_dist;
-      {
-        int t[EVG] = {cur_node};
-        float d[EVG];
-        evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, 1, lane, d);
-        cur_dist = d[0];
-        ++n_eval;
-      }
-      for (int level = g.maxlevel; level > 0; --level) {
-        bool changed = true;
-        while (changed) {
-          changed = false;
-          const int32_t* lk = g.upper + g.upper_off[cur_node] + (size_t)(level - 1) * (g.maxM + 1);
-          const int size = lk[0];
-          for (int b0 = 0; b0 < size; b0 += 32) {
-            const int nb = (b0 + lane < size) ? lk[1 + b0 + lane] : -1;
-            unsigned mask = __ballot_sync(FULL, nb >= 0);
-            float my_d = __int_as_float(0x7F800000);
-            while (mask) {
-              int t[EVG], src[EVG], cnt = 0;
-#pragma unroll
-              for (int gq = 0; gq < EVG; ++gq) {
-                src[gq] = 0;
-                t[gq] = 0;
-                if (mask) {
-                  src[gq] = __ffs(mask) - 1;
-                  mask &= mask - 1;
-                  ++cnt;
-                }
-              }
-#pragma unroll
-              for (int gq = 0; gq < EVG; ++gq) t[gq] = __shfl_sync(FULL, nb, src[gq]);
-              float d[EVG];
-              evalG<KIND, EVG>(g.vectors, g.row_words, q4, t, cnt, lane, d);
-              n_eval += cnt;
-#pragma unroll
-              for (int gq = 0; gq < EVG; ++gq)
-                if (gq < cnt && lane == src[gq]) my_d = d[gq];
-            }
-            uint64_t best = ((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const uint64_t other = __shfl_xor_sync(FULL, best, o);
-              best = other < best ? other : best;
-            }
-            const int bl = (int)(best & 31u);
-            const float bd = __shfl_sync(FULL, my_d, bl);
-            const int bn = __shfl_sync(FULL, nb, bl);
-            if (bn >= 0 && bd < cur_dist) {
-              cur_dist = bd;
-              cur_node = bn;
-              changed = true;
-            }
-          }
-        }
-      }
+      greedy_descent<KIND, EVG>(g, q4, lane, cur_node, cur_dist, n_eval);
       if (lane == 0) {
         wkey[0] = cur_dist;
         wdat[0] = cur_node;
@@ -575,68 +528,13 @@ hnsw_search_team_kernel(HnswDeviceGraph g, const float* __restrict__ queries, in
         team_sync<TW>(team);
         if (warp == 0) {
           const float my_d = fresh ? s_d[lane] : __int_as_float(0x7F800000);
-          const bool accept = fresh && (my_d < top_key || grow);
-          const int m = __popc(__ballot_sync(FULL, accept));
-          if (m != 0) {
-            uint64_t item = accept ? (((uint64_t)f32_ordered(my_d) << 32) | (uint32_t)nb) : KEY_MAX;
-            item = warp_sort64(item, lane);
-            const float d_i = f32_from_ordered((uint32_t)(item >> 32));
-            const int t_i = (int)(uint32_t)item;
-            int p_i = n_w;
-            if (lane < m) {
-              int lo = 0, hi = n_w;
-              while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (wkey[mid] <= d_i) lo = mid + 1; else hi = mid;
-              }
-              p_i = lo;
-            }
-            pbuf[lane] = lane < m ? p_i : 0x7FFFFFFF;
-            __syncwarp();
-            const int p0 = pbuf[0];
-            if (p0 < n_w) {
-              for (int cb = ((n_w - 1) >> 5) << 5; cb >= ((p0 >> 5) << 5); cb -= 32) {
-                const int a = cb + lane;
-                const bool valid = a < n_w && a >= p0;
-                float ka = 0.f;
-                int da = 0, c = 0;
-                if (valid) {
-                  ka = wkey[a];
-                  da = wdat[a];
-                  for (int i = 0; i < m; ++i) c += (pbuf[i] <= a) ? 1 : 0;
-                }
-                __syncwarp();
-                if (valid && a + c < cap) {
-                  wkey[a + c] = ka;
-                  wdat[a + c] = da;
-                }
-                __syncwarp();
-              }
-            }
-            if (lane < m && p_i + lane < cap) {
-              wkey[p_i + lane] = d_i;
-              wdat[p_i + lane] = t_i;
-            }
-            n_w = min(cap, n_w + m);
-            if (p0 < cur) cur = p0;
-            __syncwarp();
-          }
+          beam_insert(fresh && (my_d < top_key || grow), my_d, nb, wkey, wdat, pbuf, cap, lane, n_w, cur);
         }
         // (the next chunk's publication overwrites s_nb / s_ctl[3..4]: everybody has read them before this barrier)
         team_sync<TW>(team);
       }
       if (warp == 0) {
-        while (cur < n_w) {  // advance to the first unused item (hnsw_distfunc_opt.cc:272)
-          const int a = cur + lane;
-          const bool unused = a < n_w && !(wdat[a] & USED_BIT);
-          const unsigned um = __ballot_sync(FULL, unused);
-          if (um) {
-            cur += __ffs(um) - 1;
-            break;
-          }
-          cur += 32;
-        }
-        if (cur > n_w) cur = n_w;
+        beam_advance(wdat, n_w, lane, cur);
         if (lane == 0) {
           s_ctl[1] = cur;
           s_ctl[2] = n_w;
