@@ -124,7 +124,14 @@ def time_reference(w, sample: int, steps: int, warmup: int):
     for _ in range(steps):
         run()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": sample / dt, "unit": "queries/s", "cores": threads, "kind": kind,
+    # the path as shipped -- lib.zig calls nmslib_knn_query_fill in a serial loop, one core
+    one = None
+    if kind == "reference":
+        q1 = q[:min(32, sample)]
+        t1 = time.perf_counter()
+        ref.knn(q1, w["k"], threads=1)
+        one = len(q1) / (time.perf_counter() - t1)
+    return {"value": sample / dt, "unit": "queries/s", "cores": threads, "kind": kind, "as_shipped_1core": one,
             "sample": f"{sample} of {w['nq']} queries x all {w['n']} rows per step, {steps} steps"
                       + (" (space l2: l2sqr is not registered in the reference; same ranking + one sqrtf)"
                          if w["space"] == "l2sqr" else ""),
@@ -303,7 +310,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"{w['name']}: seq_search {w['space']} {w['n']}x{w['dim']}, "
                                        f"{w['nq']} queries, k={w['k']}", "space": w["space"], "k": w["k"]},
-                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "as_shipped_1core")},
                 "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -437,7 +444,7 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu:
             base = time_reference(w, min(args.cpu_sample, nq), 3, 1)
-            cpu = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+            cpu = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample", "as_shipped_1core")}
         traffic = None
         try:  # DRAM bytes per launch from the committed ncu capture of this workload (full-size, one GPU only)
             tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
