@@ -361,3 +361,33 @@ def test_range_query_errors_like_the_reference():
         idx.rangeQuery(data[0, :8], 1.0)
     assert e.value.code == 9                      # length mismatch -> QUERY_EXECUTION_FAILED
     idx.deinit()
+
+
+def test_pair_kernel_and_single_cta_kernel_agree(tmp_path):
+    """NB200_TC_PAIR=0 keeps the single-CTA long-row kernel (tc_scan_kernel) for A/B runs: on the same data both
+    nominate candidates for the same exact re-rank, so ids and distances are equal.  The switch is read once per
+    process, hence two child processes."""
+    import os
+    import subprocess
+    import sys
+    script = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {str(Path(__file__).resolve().parents[1])!r})\n"
+        "import nmslib_zig_b200 as nb\n"
+        "from nmslib_zig_b200 import synth\n"
+        "out = []\n"
+        "for space, dim, k in (('negdotprod', 768, 100), ('l2', 200, 10)):\n"
+        "    data = synth.embedding_like(30000, dim, 9) if space == 'negdotprod' else synth.uniform(30000, dim, 1)\n"
+        "    q = synth.embedding_like(3000, dim, 10) if space == 'negdotprod' else synth.uniform(3000, dim, 2)\n"
+        "    idx = nb.Index(space, None, 'seq_search'); idx.addDenseBatch(data); idx.buildIndex()\n"
+        "    r = idx.knnQueryBatch(q, k)\n"
+        "    out += [r.ids[:, :10].copy(), r.distances[:, :10].view(np.int32).copy()]\n"
+        "    idx.deinit()\n"
+        "np.save(sys.argv[1], np.stack(out))\n")
+    outs = []
+    for mode in ("1", "0"):
+        path = tmp_path / f"pair{mode}.npy"
+        env = dict(os.environ, NB200_TC_PAIR=mode)
+        subprocess.run([sys.executable, "-c", script, str(path)], check=True, env=env, timeout=600)
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1])
