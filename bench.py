@@ -230,6 +230,13 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
         launches_per_step = (st1["scan_count"] - st0["scan_count"]) / steps
         gbytes = (evals * 4.0 * dim + exps * 4.0 * 32) / 1e9          # rows gathered + adjacency lists read
         achieved = gbytes / max(1e-9, kern_ms * launches_per_step * 1e-3)
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu capture (full-size config, one GPU, efSearch 400 only)
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
+            if world == 1 and args.n is None and args.nq is None and ef == 400 and w["name"] in tj:
+                traffic = tj[w["name"]]["bytes"]
+        except Exception:
+            traffic = None
         cpu = None
         if world == 1 and not args.no_cpu:
             # the REFERENCE's own HNSW search (Index::LoadIndex + Search through oracle/_ref, OpenMP over queries on all
@@ -268,7 +275,7 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
                     "h2d_bytes_per_step": int(nq * dim * 4), "d2h_bytes_per_step": int(nq * k * 8 + nq * 4)},
             "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "hnsw_search",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "kernel": "hnsw_search",
                          "kernel_ms": kern_ms * launches_per_step,
                          "bytes_per_query": gbytes * 1e9 / max(1, my_nq),
                          "peak_src": f"{peaks['src']} HBM copy bandwidth"},
