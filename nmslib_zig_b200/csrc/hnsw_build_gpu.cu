@@ -297,7 +297,7 @@ Status build_level(const float* d_rows_l, size_t m, int dim, int row_words, int 
   out->links.assign(m * (size_t)cap, -1);
   out->cnt.assign(m, 0);
   if (m < 2) return Status::OK();
-  const int M = bp.M;
+  const int M = std::min(bp.M, cap);  // (a level whose capacity is below M keeps at most its capacity)
   const int efc = std::min(bp.efConstruction, HB_MAXC - 24);  // room for the slack below inside the scan's max k
   int K = std::min(HB_MAXC, efc + efc / 8 + 8);
   if (const char* e = getenv("NB200_HNSW_BUILD_K")) K = std::max(M + 1, std::min(HB_MAXC, atoi(e)));  // (experiments)
