@@ -253,7 +253,8 @@ nmslib_error_t nmslib_b200_knn_device(nmslib_index_handle_t index, const void* d
  * all-gather lays them out) into [q][k]: the cross-shard step of SURVEY 8e.
  * Ordering is by key (distance, then global position); the index handle supplies
  * the space's final distance transform (sqrt for l2, int->float for l2sqr_sift).
- * All pointers are device pointers (peer-mapped pointers are fine). */
+ * All pointers are device pointers (peer-mapped pointers are fine).  d_ids may be NULL when the external ids are
+ * the global positions themselves (the low word of every key): the id lists then need not be exchanged at all. */
 nmslib_error_t nmslib_b200_merge_topk(nmslib_index_handle_t index, const uint64_t* d_keys,
                                       const int32_t* d_ids, size_t lists, size_t query_count,
                                       size_t k, int32_t* d_out_ids, float* d_out_distances,

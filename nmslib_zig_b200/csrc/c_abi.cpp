@@ -732,7 +732,9 @@ nmslib_error_t nmslib_b200_knn_device(nmslib_index_handle_t index, const void* d
 nmslib_error_t nmslib_b200_merge_topk(nmslib_index_handle_t index, const uint64_t* d_keys, const int32_t* d_ids,
                                       size_t lists, size_t query_count, size_t k, int32_t* d_out_ids,
                                       float* d_out_distances, void* stream) {
-  if (!index || !d_keys || !d_ids || lists == 0 || query_count == 0 || k == 0)
+  // d_ids == NULL: the ids ARE the global positions the keys carry (default ids of lib.zig's addDenseBatch; what a
+  // sharded caller gets when every rank numbers its rows by global position) -- one all-gather per step instead of two
+  if (!index || !d_keys || lists == 0 || query_count == 0 || k == 0)
     return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid merge inputs");
   if (lists * k > (size_t)nb200::merge_topk_max_items()) return NB_ERR(NMSLIB_ERROR_QUERY_TOO_LARGE, "lists * k too large");
   cudaError_t e = nb200::launch_merge_topk(d_keys, d_ids, (int)lists, query_count * k, k, (int)query_count, (int)k,

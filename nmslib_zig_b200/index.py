@@ -482,7 +482,8 @@ class Index:
 
     def mergeTopk(self, d_keys_ptr: int, d_ids_ptr: int, lists: int, nq: int, k: int, d_out_ids_ptr: int,
                   d_out_dists_ptr: int, stream: int = 0):
-        _check(lib().nmslib_b200_merge_topk(self.handle, d_keys_ptr, d_ids_ptr, lists, nq, k, d_out_ids_ptr,
+        """d_ids_ptr = 0: the external ids are the global positions in the keys (no id lists to exchange)."""
+        _check(lib().nmslib_b200_merge_topk(self.handle, d_keys_ptr, d_ids_ptr or None, lists, nq, k, d_out_ids_ptr,
                                             d_out_dists_ptr, stream or None))
 
 

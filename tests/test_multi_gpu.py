@@ -59,7 +59,12 @@ def _worker(rank, world, port, space, n, dim, nq, k, out_path):
     o_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
     idx.mergeTopk(g_keys.data_ptr(), g_ids.data_ptr(), world, nq, k, o_ids.data_ptr(), o_d.data_ptr(),
                   stream.cuda_stream)
+    # without id lists the merge reports the global POSITION in the key: ids here are 2 * position + 1
+    p_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    p_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    idx.mergeTopk(g_keys.data_ptr(), 0, world, nq, k, p_ids.data_ptr(), p_d.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize(dev)
+    assert torch.equal(p_ids * 2 + 1, o_ids) and torch.equal(p_d, o_d)
     if rank == 0:
         np.savez(out_path, ids=o_ids.cpu().numpy(), dists=o_d.cpu().numpy())
     idx.deinit()
