@@ -296,6 +296,16 @@ size_t nmslib_b200_scan_plan(size_t query_count, size_t n, size_t k, int sm_coun
 size_t nmslib_b200_scan_plan_pairs(size_t query_count, size_t n, size_t k, int sm_count, int32_t* pieces,
                                    size_t capacity, int* n_pairs, int* s_max);
 
+/* Process-wide variant selectors (every variant returns the same answers; used for A/B comparisons):
+ *   "tc_pair"     1 (default) rows of more than 128 floats on CTA pairs / 0 the single-CTA long-row kernel
+ *   "hnsw_team"   -1 (default) auto / 0 one warp per query / 2, 4 teams of that many warps per query
+ *   "force_exact" 0 (default) / 1 CUDA-core exact scan only (read when an index is created)
+ *   "tc_split"    1 (default) / 0 never switch to split (3xTF32) operands
+ *   "u8_imma"     1 (default) uint8 rows on the integer tensor pipe / 0 rows widened to TF32 operands
+ * Unknown names are INVALID_ARGUMENT.  The NB200_* timing / debugging environment variables of the tools exist only
+ * in -DNB200_EXPERIMENTS builds of the library; the release build never reads the environment for them. */
+nmslib_error_t nmslib_b200_set_option(const char* name, int value);
+
 /* Library build / arch string, e.g. "nmslib_b200 0.1 sm_100a". Static storage. */
 const char* nmslib_b200_version(void);
 

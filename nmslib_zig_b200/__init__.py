@@ -5,4 +5,4 @@ CUDA kernels behind the reference's own C ABI (include/nmslib_b200.h), plus a ho
 mirror of lib.zig's `Index` (nmslib_zig_b200.index).  See DESIGN.md.
 """
 from .index import (BatchResult, Index, NmslibError, Params, QueryResult, device_available, lib,  # noqa: F401
-                    live_allocations, scan_plan, scan_plan_pairs, set_device, version)
+                    live_allocations, scan_plan, scan_plan_pairs, set_device, set_option, version)

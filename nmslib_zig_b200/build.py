@@ -1,6 +1,10 @@
 """Build libnmslib_b200.so in-tree with nvcc for sm_100a (no JIT cache, no torch dependency).
 
-    python -m nmslib_zig_b200.build [--force] [--verbose]
+    python -m nmslib_zig_b200.build [--force] [--verbose] [--experiments]
+
+--experiments builds a second library, lib/libnmslib_b200_exp.so, with -DNB200_EXPERIMENTS: the NB200_* timing /
+debugging environment switches and the kernels' cycle counters exist only there (tools/ load it through
+NB200_LIB=...; the release library never reads them).
 
 The shared library links cudart statically, so it dlopen()s on a machine without a GPU
 (the CPU-side tests check that it loads and exports every symbol of include/nmslib_b200.h).
@@ -37,8 +41,9 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def _digest() -> str:
+def _digest(extra: str = "") -> str:
     h = hashlib.sha256()
+    h.update(extra.encode())
     for f in sorted(CSRC.iterdir()) + [PKG.parent / "include" / "nmslib_b200.h", Path(__file__)]:
         if f.is_file():
             h.update(f.name.encode())
@@ -47,11 +52,14 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
-    digest = _digest()
-    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text() == digest:
-        return LIB
+    lib = LIBDIR / "libnmslib_b200_exp.so" if experiments else LIB
+    stamp = LIBDIR / ".build_stamp_exp" if experiments else STAMP
+    flags = NVCC_FLAGS + (["-DNB200_EXPERIMENTS"] if experiments else [])
+    digest = _digest("exp" if experiments else "")
+    if not force and lib.exists() and stamp.exists() and stamp.read_text() == digest:
+        return lib
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -59,9 +67,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     env.pop("CXX", None)  # the image's CXX wrapper is not a host compiler nvcc can use
     env.pop("CC", None)
     for src in SOURCES:
-        obj = LIBDIR / (src.rsplit(".", 1)[0] + ".o")
+        obj = LIBDIR / (("exp_" if experiments else "") + src.rsplit(".", 1)[0] + ".o")
         objs.append(str(obj))
-        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *flags, "-x", "cu", "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
             print(" ".join(cmd), flush=True)
@@ -76,13 +84,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *objs,
             "-cudart", "static", "-Xcompiler", "-fPIC"]
     subprocess.run(link, check=True, env=env)
-    STAMP.write_text(digest)
-    return LIB
+    stamp.write_text(digest)
+    return lib
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, experiments="--experiments" in sys.argv)
     print(p)

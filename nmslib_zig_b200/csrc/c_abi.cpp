@@ -320,6 +320,7 @@ size_t nmslib_data_qty(nmslib_index_handle_t index) {
     NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid index");
     return 0;
   }
+  std::lock_guard<std::mutex> lock(index->engine->mutex());
   return index->engine->size();
 }
 // ref :1546-1565: sum of object buffers (16-byte header + payload) + n * dim * 4
@@ -497,6 +498,9 @@ nmslib_error_t nmslib_borrow_data_sparse(nmslib_index_handle_t index, size_t, vo
 nmslib_error_t nmslib_get_distance(nmslib_index_handle_t index, size_t pos1, size_t pos2, float* distance) {
   if (!index || !distance || pos1 >= index->engine->size() || pos2 >= index->engine->size())
     return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid distance inputs");
+  std::lock_guard<std::mutex> lock(index->engine->mutex());
+  if (pos1 >= index->engine->size() || pos2 >= index->engine->size())
+    return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid distance inputs");
   *distance = index->engine->host_distance(pos1, pos2);
   return NB_OK("Distance computed");
 }
@@ -511,7 +515,9 @@ nmslib_error_t nmslib_get_data_point_size(nmslib_index_handle_t index, size_t po
 nmslib_error_t nmslib_get_data_point_fill(nmslib_index_handle_t index, size_t position, void* data, size_t size) {
   if (!index || !data || position >= index->engine->size())
     return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid data point request");
-  const Engine* e = index->engine;
+  Engine* e = index->engine;
+  std::lock_guard<std::mutex> lock(e->mutex());  // (a concurrent add_rows may reallocate the host rows)
+  if (position >= e->size()) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid data point request");
   if (size < (size_t)e->dim()) return NB_ERR(NMSLIB_ERROR_BUFFER_TOO_SMALL, "Buffer too small for data point");
   if (e->is_u8()) memcpy(data, e->row_u8(position), (size_t)e->dim());
   else memcpy(data, e->row_f32(position), (size_t)e->dim() * sizeof(float));
@@ -540,7 +546,9 @@ nmslib_error_t nmslib_borrow_data_dense(nmslib_index_handle_t index, size_t posi
                                         void (**free_fn)(void*)) {
   if (!index || !data || !size || !free_fn || position >= index->engine->size())
     return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid dense borrow inputs");
-  const Engine* e = index->engine;
+  Engine* e = index->engine;
+  std::lock_guard<std::mutex> lock(e->mutex());
+  if (position >= e->size()) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid dense borrow inputs");
   if (e->is_u8()) return NB_ERR(NMSLIB_ERROR_SPACE_INCOMPATIBLE, "Not dense vector");
   const size_t bytes = (size_t)e->dim() * sizeof(float);
   nmslib_allocator_t a = index->allocator;
@@ -643,6 +651,10 @@ nmslib_error_t nmslib_load_index(const char* path, nmslib_data_type_t data_type,
               int32_t id;
               memcpy(&id, buf.data(), 4);
               const size_t payload = buflen - 16;
+              uint64_t datalen = 0;  // Object header: id, label, datalength (object.h); must describe this record
+              memcpy(&datalen, buf.data() + 8, 8);
+              ok = datalen == payload && (h->engine->is_u8() ? payload > 4 : (payload >= 4 && payload % 4 == 0));
+              if (!ok) break;
               const size_t elems = h->engine->is_u8() ? payload - 4 : payload / 4;
               ok = h->engine->add_rows(buf.data() + 16, 1, elems, &id).ok();
             }
@@ -685,6 +697,7 @@ int nmslib_b200_device_available(void) { return nb200::device_available() ? 1 : 
 
 nmslib_error_t nmslib_b200_set_shard(nmslib_index_handle_t index, uint32_t pos_base) {
   if (!index) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid index");
+  std::lock_guard<std::mutex> lock(index->engine->mutex());
   index->engine->set_pos_base(pos_base);
   return NB_OK("Shard base set");
 }
@@ -737,7 +750,9 @@ nmslib_error_t nmslib_b200_merge_topk(nmslib_index_handle_t index, const uint64_
   if (!index || !d_keys || lists == 0 || query_count == 0 || k == 0)
     return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid merge inputs");
   if (lists * k > (size_t)nb200::merge_topk_max_items()) return NB_ERR(NMSLIB_ERROR_QUERY_TOO_LARGE, "lists * k too large");
-  cudaError_t e = nb200::launch_merge_topk(d_keys, d_ids, (int)lists, query_count * k, k, (int)query_count, (int)k,
+  std::lock_guard<std::mutex> lock(index->engine->mutex());
+  cudaError_t e = cudaSetDevice(index->engine->device());  // launch where the index lives, whatever is current
+  if (e == cudaSuccess) e = nb200::launch_merge_topk(d_keys, d_ids, (int)lists, query_count * k, k, (int)query_count, (int)k,
                                            index->engine->finalize_kind(), nullptr, 0, nullptr, d_out_ids,
                                            d_out_distances, nullptr, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return NB_ERR(NMSLIB_ERROR_QUERY_EXECUTION_FAILED, std::string("merge failed: ") + cudaGetErrorString(e));
@@ -746,6 +761,7 @@ nmslib_error_t nmslib_b200_merge_topk(nmslib_index_handle_t index, const uint64_
 
 nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_stats_t* out) {
   if (!index || !out) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid stats request");
+  std::lock_guard<std::mutex> lock(index->engine->mutex());
   const nb200::Stats s = index->engine->stats();
   out->queries = s.queries;
   out->kernel_launches = s.kernel_launches;
@@ -805,6 +821,17 @@ static size_t scan_plan_impl(size_t query_count, size_t n, size_t k, int units, 
       ++out;
     }
   return out;
+}
+
+nmslib_error_t nmslib_b200_set_option(const char* name, int value) {
+  static const char* const known[] = {"tc_pair", "hnsw_team", "force_exact", "tc_split", "u8_imma"};
+  if (!name) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid option name");
+  for (const char* k : known)
+    if (strcmp(k, name) == 0) {
+      nb200::nb200_set_option(name, value);
+      return NB_OK("Option set");
+    }
+  return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, std::string("unknown option '") + name + "'");
 }
 
 const char* nmslib_b200_version(void) { return "nmslib_b200 0.1 sm_100a"; }

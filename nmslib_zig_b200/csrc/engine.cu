@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
+#include <map>
 #include <sstream>
 
 namespace nb200 {
@@ -12,7 +14,34 @@ namespace nb200 {
 namespace {
 constexpr int kErrInvalid = 2, kErrOOM = 3, kErrIncompat = 5, kErrTooLarge = 6, kErrBuild = 8, kErrQuery = 9;
 thread_local int g_default_device = -1;
+std::mutex g_opt_mu;
+std::map<std::string, int>& option_table() {
+  static std::map<std::string, int> t;
+  return t;
+}
 }  // namespace
+
+// Variant selectors (kernels.h).  -DNB200_EXPERIMENTS builds also accept NB200_<NAME> from the environment.
+int nb200_option(const char* name, int dflt) {
+  {
+    std::lock_guard<std::mutex> g(g_opt_mu);
+    auto it = option_table().find(name);
+    if (it != option_table().end()) return it->second;
+  }
+#ifdef NB200_EXPERIMENTS
+  std::string env = "NB200_";
+  for (const char* c = name; *c; ++c) env.push_back((char)toupper(*c));
+  if (const char* e = getenv(env.c_str())) return atoi(e);
+#endif
+  return dflt;
+}
+void nb200_set_option(const char* name, int value) {
+  std::lock_guard<std::mutex> g(g_opt_mu);
+  option_table()[name] = value;
+}
+#ifdef NB200_EXPERIMENTS
+const char* nb200_env(const char* name) { return getenv(name); }
+#endif
 
 int default_device() {
   if (g_default_device >= 0) return g_default_device;
@@ -91,9 +120,8 @@ void PinBuf::release() {
 
 Engine::Engine(Space space, Method method, bool is_u8, int device)
     : space_(space), method_(method), is_u8_(is_u8), device_(device) {
-  const char* fe = getenv("NB200_FORCE_EXACT");  // debugging / A-B switch: CUDA-core exact scan only
-  force_exact_ = fe && fe[0] == '1';
-  if (const char* e = getenv("NB200_TC_MARGIN")) tc_margin_ = std::max(1, atoi(e));
+  force_exact_ = nb200_option("force_exact", 0) != 0;  // A/B switch: CUDA-core exact scan only
+  if (const char* e = nb200_env("NB200_TC_MARGIN")) tc_margin_ = std::max(1, atoi(e));
 }
 
 Engine::~Engine() {
@@ -175,6 +203,7 @@ void Engine::reset() {
   n_dev_ = 0;
   rows_normalized_ = false;
   h_hnsw_rows_.clear();
+  d_q_dim_ = -1;  // the staged-query buffer is re-zeroed before its next use (stale padding columns)
 }
 
 float Engine::host_distance(size_t a, size_t b) const {
@@ -567,24 +596,28 @@ Status Engine::upload_graph() {
   if (!s.ok()) return s;
   s = check_cuda(d_upper_off_.ensure((size_t)g.total * 8), "cudaMalloc(upper_off)");
   if (!s.ok()) return s;
-  cudaMemcpyAsync(d_links0_.p, g.links0.data(), g.links0.size() * 4, cudaMemcpyHostToDevice, stream_);
-  cudaMemcpyAsync(d_links0_cnt_.p, g.links0_cnt.data(), (size_t)g.total * 4, cudaMemcpyHostToDevice, stream_);
-  if (!g.upper.empty())
-    cudaMemcpyAsync(d_upper_.p, g.upper.data(), g.upper.size() * 4, cudaMemcpyHostToDevice, stream_);
-  cudaMemcpyAsync(d_upper_off_.p, g.upper_off.data(), (size_t)g.total * 8, cudaMemcpyHostToDevice, stream_);
+  if (!(s = check_cuda(cudaMemcpyAsync(d_links0_.p, g.links0.data(), g.links0.size() * 4, cudaMemcpyHostToDevice, stream_),
+                       "H2D(links0)")).ok()) return s;
+  if (!(s = check_cuda(cudaMemcpyAsync(d_links0_cnt_.p, g.links0_cnt.data(), (size_t)g.total * 4, cudaMemcpyHostToDevice,
+                                       stream_), "H2D(links0_cnt)")).ok()) return s;
+  if (!g.upper.empty() &&
+      !(s = check_cuda(cudaMemcpyAsync(d_upper_.p, g.upper.data(), g.upper.size() * 4, cudaMemcpyHostToDevice, stream_),
+                       "H2D(upper)")).ok()) return s;
+  if (!(s = check_cuda(cudaMemcpyAsync(d_upper_off_.p, g.upper_off.data(), (size_t)g.total * 8, cudaMemcpyHostToDevice,
+                                       stream_), "H2D(upper_off)")).ok()) return s;
   // visited epoch arrays: one per resident warp slot (VisitedListPool, hnsw.h:598-639)
   hnsw_slots_ = sm_count_ * 32;  // upper bound of warps per SM in flight (the launch uses one resident wave)
-  if (const char* e = getenv("NB200_HNSW_SLOTS")) hnsw_slots_ = sm_count_ * std::max(4, std::min(64, atoi(e)));
+  if (const char* e = nb200_env("NB200_HNSW_SLOTS")) hnsw_slots_ = sm_count_ * std::max(4, std::min(64, atoi(e)));
   const size_t vstride = round_up((size_t)g.total, 16);
   s = check_cuda(d_visited_.ensure(vstride * hnsw_slots_), "cudaMalloc(visited)");
   if (!s.ok()) return s;
-  cudaMemsetAsync(d_visited_.p, 0, vstride * hnsw_slots_, stream_);
+  if (!(s = check_cuda(cudaMemsetAsync(d_visited_.p, 0, vstride * hnsw_slots_, stream_), "memset(visited)")).ok()) return s;
   s = check_cuda(d_epoch_.ensure((size_t)hnsw_slots_ * 4), "cudaMalloc(epoch)");
   if (!s.ok()) return s;
-  cudaMemsetAsync(d_epoch_.p, 0, (size_t)hnsw_slots_ * 4, stream_);
+  if (!(s = check_cuda(cudaMemsetAsync(d_epoch_.p, 0, (size_t)hnsw_slots_ * 4, stream_), "memset(epoch)")).ok()) return s;
   s = check_cuda(d_counters_.ensure(32), "cudaMalloc(counters)");
   if (!s.ok()) return s;
-  cudaMemsetAsync(d_counters_.p, 0, 32, stream_);
+  if (!(s = check_cuda(cudaMemsetAsync(d_counters_.p, 0, 32, stream_), "memset(counters)")).ok()) return s;
   s = check_cuda(cudaStreamSynchronize(stream_), "graph upload sync");
   if (!s.ok()) return s;
   graph_dirty_ = false;
@@ -602,9 +635,12 @@ Status Engine::stage_queries_device(const void* src, bool src_on_device, size_t 
   const size_t old_cap = d_q_.cap;
   Status s = check_cuda(d_q_.ensure(q_pad * row_bytes), "cudaMalloc(queries)");
   if (!s.ok()) return s;
-  if (d_q_.cap != old_cap) {  // new buffer: zero it once so that the padding columns stay zero
+  if (d_q_.cap != old_cap || d_q_dim_ != dim_) {
+    // new buffer, or the index was reset and re-filled with rows of another length that pad to the same row_words:
+    // zero it so that the padding columns [dim, row_words) hold no values of earlier queries
     s = check_cuda(cudaMemsetAsync(d_q_.p, 0, d_q_.cap, stream), "memset(queries)");
     if (!s.ok()) return s;
+    d_q_dim_ = dim_;
   }
   if (u8_widened()) {  // uint8 queries: bytes to a staging buffer, widened into the padded fp32 rows
     s = check_cuda(d_u8tmp_.ensure(std::max<size_t>(nq * elem_count, d_u8tmp_.cap)), "cudaMalloc(u8 staging)");
@@ -735,8 +771,7 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
 // q_lo.x_lo term) instead of 2^-9.  The failed queries of that batch and every later batch use it.
 Status Engine::enable_split(cudaStream_t stream) {
   if (tc_split_) return Status::OK();
-  if (const char* e = getenv("NB200_TC_SPLIT"))
-    if (e[0] == '0') return Status::Err(kErrQuery, "split mode disabled");
+  if (nb200_option("tc_split", 1) == 0) return Status::Err(kErrQuery, "split mode disabled");
   const size_t n_pad = round_up(n_dev_ < n_ ? n_ : n_dev_, (size_t)tc_block_points());
   const size_t bytes = n_pad * 3 * (size_t)row_words_ * 4;
   size_t free_b = 0, total_b = 0;
@@ -1023,11 +1058,13 @@ Status Engine::range_host(const void* query, size_t elem_count, double radius, s
   if (!s.ok()) return s;
   stats_.kernel_launches += 2;
   int found = 0;
-  cudaMemcpyAsync(&found, d_cnt, 4, cudaMemcpyDeviceToHost, stream_);
+  if (!(s = check_cuda(cudaMemcpyAsync(&found, d_cnt, 4, cudaMemcpyDeviceToHost, stream_), "D2H(range count)")).ok()) return s;
   if (!(s = check_cuda(cudaStreamSynchronize(stream_), "range query")).ok()) return s;
   if (found > 0) {
-    cudaMemcpyAsync(ids, d_ids, (size_t)found * 4, cudaMemcpyDeviceToHost, stream_);
-    cudaMemcpyAsync(dists, d_d, (size_t)found * 4, cudaMemcpyDeviceToHost, stream_);
+    if (!(s = check_cuda(cudaMemcpyAsync(ids, d_ids, (size_t)found * 4, cudaMemcpyDeviceToHost, stream_), "D2H(range ids)")).ok())
+      return s;
+    if (!(s = check_cuda(cudaMemcpyAsync(dists, d_d, (size_t)found * 4, cudaMemcpyDeviceToHost, stream_), "D2H(range dists)")).ok())
+      return s;
     if (!(s = check_cuda(cudaStreamSynchronize(stream_), "range query")).ok()) return s;
   }
   *size = (size_t)found;
@@ -1075,8 +1112,10 @@ Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_
     const size_t row_bytes = (size_t)row_words_ * 4, src_row = elem_count * 4;
     const size_t old_cap = d_q_.cap;
     if (!(s = check_cuda(d_q_.ensure(round_up(nq, bq) * row_bytes), "cudaMalloc(queries)")).ok()) return s;
-    if (d_q_.cap != old_cap && !(s = check_cuda(cudaMemsetAsync(d_q_.p, 0, d_q_.cap, stream_), "memset(queries)")).ok())
-      return s;
+    if (d_q_.cap != old_cap || d_q_dim_ != dim_) {
+      if (!(s = check_cuda(cudaMemsetAsync(d_q_.p, 0, d_q_.cap, stream_), "memset(queries)")).ok()) return s;
+      d_q_dim_ = dim_;
+    }
     if (!copy_stream_) {
       if (!(s = check_cuda(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate")).ok()) return s;
       for (auto& e : copy_ev_)
@@ -1114,9 +1153,12 @@ Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_
     if (!s.ok()) return s;
   }
   cudaEventRecord(ev_[2], stream_);
-  cudaMemcpyAsync(h_out_ids_.p, d_out_ids_.p, out_n * 4, cudaMemcpyDeviceToHost, stream_);
-  cudaMemcpyAsync(h_out_dists_.p, d_out_dists_.p, out_n * 4, cudaMemcpyDeviceToHost, stream_);
-  cudaMemcpyAsync(h_out_counts_.p, d_out_counts_.p, nq * 4, cudaMemcpyDeviceToHost, stream_);
+  if (!(s = check_cuda(cudaMemcpyAsync(h_out_ids_.p, d_out_ids_.p, out_n * 4, cudaMemcpyDeviceToHost, stream_), "D2H(ids)")).ok())
+    return s;
+  if (!(s = check_cuda(cudaMemcpyAsync(h_out_dists_.p, d_out_dists_.p, out_n * 4, cudaMemcpyDeviceToHost, stream_), "D2H(dists)")).ok())
+    return s;
+  if (!(s = check_cuda(cudaMemcpyAsync(h_out_counts_.p, d_out_counts_.p, nq * 4, cudaMemcpyDeviceToHost, stream_), "D2H(counts)")).ok())
+    return s;
   cudaEventRecord(ev_[3], stream_);
   s = check_cuda(cudaStreamSynchronize(stream_), "query batch");
   if (!s.ok()) return s;

@@ -182,6 +182,7 @@ class Engine {
   bool is_u8_;
   int device_;
   int dim_ = 0;        // elements per vector
+  int d_q_dim_ = -1;   // dim_ the staged-query buffer d_q_ was last zeroed for
   int row_words_ = 0;  // padded 32-bit words per device row
   uint32_t pos_base_ = 0;
   size_t n_ = 0;

@@ -53,7 +53,7 @@ bool parse_hnsw_build_params(const std::vector<std::string>& params, HnswBuildPa
     else if (name == "indexThreadQty") bp->threads = (int)v;
     else if (name == "b200_build") bp->where = val == "device" || val == "gpu" ? 1 : val == "host" || val == "cpu" ? 0 : -1;
   }
-  if (const char* e = getenv("NB200_HNSW_BUILD")) {  // A/B switch for the tools
+  if (const char* e = nb200_env("NB200_HNSW_BUILD")) {  // A/B switch for the tools
     const std::string v(e);
     if (v == "device" || v == "gpu") bp->where = 1;
     else if (v == "host" || v == "cpu") bp->where = 0;

@@ -300,7 +300,7 @@ Status build_level(const float* d_rows_l, size_t m, int dim, int row_words, int 
   const int M = std::min(bp.M, cap);  // (a level whose capacity is below M keeps at most its capacity)
   const int efc = std::min(bp.efConstruction, HB_MAXC - 24);  // room for the slack below inside the scan's max k
   int K = std::min(HB_MAXC, efc + efc / 8 + 8);
-  if (const char* e = getenv("NB200_HNSW_BUILD_K")) K = std::max(M + 1, std::min(HB_MAXC, atoi(e)));  // (experiments)
+  if (const char* e = nb200_env("NB200_HNSW_BUILD_K")) K = std::max(M + 1, std::min(HB_MAXC, atoi(e)));  // (experiments)
   // scan engine over the members' rows, in place.  cosine rows are unit vectors: 1 - dot ranks like -dot.
   const double t_setup = now_ms();
   Engine scan(kind == 0 ? SPACE_L2SQR : SPACE_NEGDOT, METHOD_SEQ, false, device);
@@ -550,7 +550,7 @@ Status build_hnsw_device(const float* d_rows, size_t n, int dim, int row_words, 
   info->total_ms = ms;
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
-  if (getenv("NB200_HNSW_BUILD_VERBOSE"))
+  if (nb200_env("NB200_HNSW_BUILD_VERBOSE"))
     fprintf(stderr,
             "[nb200] hnsw device build: n=%zu dim=%d levels=%d batches=%d total %.1f ms (scan %.1f, select %.1f, link %.1f; "
             "host: set-up %.1f, scratch sizing %.1f, download %.1f), %llu back links, %llu prunes\n",

@@ -108,9 +108,31 @@ Status read_hnsw_file(const std::string& path, HnswGraph* out) {
         if ((uint32_t)lk[j] >= total) return Status::Err(kErrIO, "HNSW upper-level neighbour out of range");
     }
   }
-  if (total > 0 && maxlevel > 0) {
-    const int64_t off = g.upper_off[enterpoint];
-    if (off < 0) return Status::Err(kErrIO, "HNSW enterpoint has no upper-level lists");
+  // Level consistency: the greedy descent (hnsw_search.cu) reads the level-l list of every node it reaches at
+  // level l without asking how many levels that node has -- the enterpoint at every level up to maxlevel, and each
+  // neighbour named in a level-l list at level l.  A truncated or hostile file must not turn into device reads
+  // outside the upper-level block.
+  if (maxlevel < 0) return Status::Err(kErrIO, "negative HNSW maxlevel");
+  {
+    std::vector<int32_t> levels(total, 0);
+    // (the blocks were appended in node order: a node's block ends where the next non-empty one starts)
+    int64_t prev = -1;
+    uint32_t prev_i = 0;
+    for (uint32_t i = 0; i < total; ++i) {
+      if (g.upper_off[i] < 0) continue;
+      if (prev >= 0) levels[prev_i] = (int32_t)((g.upper_off[i] - prev) / (int64_t)(maxM + 1));
+      prev = g.upper_off[i];
+      prev_i = i;
+    }
+    if (prev >= 0) levels[prev_i] = (int32_t)(((int64_t)g.upper.size() - prev) / (int64_t)(maxM + 1));
+    if (total > 0 && levels[enterpoint] < maxlevel)
+      return Status::Err(kErrIO, "HNSW enterpoint has fewer levels than maxlevel");
+    for (uint32_t i = 0; i < total; ++i)
+      for (int32_t l = 1; l <= levels[i]; ++l) {
+        const int32_t* lk = &g.upper[g.upper_off[i] + (size_t)(l - 1) * (maxM + 1)];
+        for (int j = 1; j <= lk[0]; ++j)
+          if (levels[lk[j]] < l) return Status::Err(kErrIO, "HNSW upper-level neighbour does not reach that level");
+      }
   }
   *out = std::move(g);
   return Status::OK();

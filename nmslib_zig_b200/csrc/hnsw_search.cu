@@ -13,7 +13,7 @@
 // capacity); cur rewinds to the smallest insertion index; the answer is W[0..k).
 // For ef >= 1000 the reference switches to SearchOld (hnsw.cc:724); for k <= ef that
 // algorithm keeps the same ef-closest set and stops at the same point, so this kernel
-// serves both (tests/test_hnsw_parity.py checks ef = 1000 against the reference).
+// serves both (tests/test_hnsw_gpu.py checks ef = 1000 against the live reference).
 //
 // Memory behaviour: per evaluated neighbour the warp gathers one vector with 128-bit
 // loads (lane c reads float4 c, c+32, ...), four neighbours in flight per warp; the
@@ -578,20 +578,17 @@ cudaError_t launch_hnsw_search(const HnswDeviceGraph& g, const float* queries, i
   const size_t vstride = round_up((size_t)g.n, 16);
   cudaError_t e;
   static const int evg = [] {
-    const char* e2 = getenv("NB200_HNSW_G");
+    const char* e2 = nb200_env("NB200_HNSW_G");
     return e2 ? atoi(e2) : 4;
   }();
   static const int minb = [] {
-    const char* e2 = getenv("NB200_HNSW_MINB");
+    const char* e2 = nb200_env("NB200_HNSW_MINB");
     return e2 ? atoi(e2) : 6;
   }();
   cudaMemsetAsync(counters + 2, 0, 8, stream);  // next query index
   // few queries: a team of 4 or 2 warps per query (hnsw_search_team_kernel); the one-warp kernel keeps 4 x the
   // resident blocks' worth of queries in flight, so it wins as soon as the batch fills that
-  static const int team_mode = [] {  // -1 auto, 0 never, 2 / 4 always that team size (A/B runs)
-    const char* e2 = getenv("NB200_HNSW_TEAM");
-    return e2 ? atoi(e2) : -1;
-  }();
+  const int team_mode = nb200_option("hnsw_team", -1);  // -1 auto, 0 never, 2 / 4 always that team size (A/B runs)
   {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);

@@ -6,6 +6,27 @@
 
 namespace nb200 {
 
+// ---- options --------------------------------------------------------------------------
+// Documented variant selectors, set per process through nmslib_b200_set_option (every variant returns the same
+// answers; the tests use them for A/B comparisons):
+//   "tc_pair"     1 (default) long rows on CTA pairs / 0 the single-CTA long-row kernel
+//   "hnsw_team"   -1 (default) auto / 0 one warp per query / 2, 4 teams of that many warps
+//   "force_exact" 0 (default) / 1 CUDA-core exact scan only (read when an index is created)
+//   "tc_split"    1 (default) / 0 never switch to split (3xTF32) operands
+//   "u8_imma"     1 (default) uint8 rows on the integer tensor pipe / 0 rows widened to TF32 operands
+int nb200_option(const char* name, int dflt);
+void nb200_set_option(const char* name, int value);
+// Timing / debugging knobs (NB200_* environment variables) exist only in -DNB200_EXPERIMENTS builds (the tools);
+// the release library never reads them: nb200_env() is then a constant nullptr and the kernels' debug branches
+// are compiled out.
+#ifdef NB200_EXPERIMENTS
+const char* nb200_env(const char* name);
+#define NB200_DBG(flags, bit) ((flags) & (bit))
+#else
+inline const char* nb200_env(const char*) { return nullptr; }
+#define NB200_DBG(flags, bit) (false)
+#endif
+
 // accumulate/epilogue flavours of the exact scan kernel
 enum ScanMode : int { SCAN_L2 = 0, SCAN_NEGDOT = 1, SCAN_COSINE = 2, SCAN_SIFT = 3, SCAN_L1 = 4, SCAN_LINF = 5,
                       SCAN_ANGULAR = 6 };  // L1 / LINF: exact CUDA-core scan only; ANGULAR: cosine ranking, acos at the end

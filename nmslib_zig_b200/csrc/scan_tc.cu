@@ -272,6 +272,20 @@ __device__ __forceinline__ void compact_lane(int src, uint64_t* buf, int& cnt, f
   }
 }
 
+// cycle accounting of the warp roles (experiments builds only: NB200_TC_COUNT=1 prints the sums of the previous launch)
+#ifdef NB200_EXPERIMENTS
+#define NB_T0(var) long long var = clock64()
+#define NB_TACC(acc, var)                  \
+  do {                                     \
+    const long long now_ = clock64();      \
+    acc += (unsigned long long)(now_ - var); \
+    var = now_;                            \
+  } while (0)
+#else
+#define NB_T0(var) do {} while (0)
+#define NB_TACC(acc, var) do {} while (0)
+#endif
+
 constexpr int TS_RK = 16;  // register mode: ranks of a row's 16 best candidates, sorted, in registers
 
 // REG (kprime <= 16, i.e. k <= 10 with the default margin): the row's threshold is the exact 16th best rank seen,
@@ -477,7 +491,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty_bar[s], ph ^ 1);
             unsigned char* st = smem_st + (size_t)s * stage_bytes;
             if (elect_one()) {
-              if (p.debug & 2) {  // timing experiment: no database traffic, the MMAs read stale shared memory
+              if (NB200_DBG(p.debug, 2)) {  // timing experiment: no database traffic, the MMAs read stale shared memory
                 mbar_arrive(&full_bar[s]);
               } else if (kb < p.n_kb) {
                 mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
@@ -536,7 +550,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 make_smem_desc(a_res ? a_base + (uint32_t)(p.n_kb + kb) * CHUNK_BYTES : sb + 2 * CHUNK_BYTES);
             const uint32_t acc = kb != 0;
             if (elect_one()) {
-              if (!(p.debug & 4)) {  // (bit 2 set: timing experiment without the MMAs, TMA traffic only)
+              if (!NB200_DBG(p.debug, 4)) {  // (bit 2 set: timing experiment without the MMAs, TMA traffic only)
                 // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (address >> 4) field
                 umma_tf32(tmem_d0, da0, db, idesc, acc);
                 umma_tf32(tmem_d0, da0 + 2, db + 2, idesc, 1);
@@ -615,7 +629,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TC_BN);
         const int vtile = p.n - tile * TC_BN;  // >= 128 except in the last tile
         uint32_t v0[32], v1[32];
-        if (p.debug & 1) {  // timing experiment: touch the accumulators, select nothing
+        if (NB200_DBG(p.debug, 1)) {  // timing experiment: touch the accumulators, select nothing
           tmem_ld32(tcol, v0);
           tmem_ld_wait();
           if (__uint_as_float(v0[0]) == 1.2345e-30f) thr = 0.f;
@@ -919,7 +933,7 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TP_BN + ch * TC_BN);
         const int vtile = p.n - tile * TP_BN - ch * TC_BN;  // >= 128 except at the end of the shard
         uint32_t v0[32], v1[32];
-        if (p.debug & 1) {  // timing experiment: touch the accumulators, select nothing
+        if (NB200_DBG(p.debug, 1)) {  // timing experiment: touch the accumulators, select nothing
           tmem_ld32(tcol, v0);
           tmem_ld_wait();
           if (__uint_as_float(v0[0]) == 1.2345e-30f) thr = 0.f;
@@ -941,7 +955,7 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(b ? te_addr1 : te_addr0);  // this warp is done with the buffer (one arrival per warp)
-        if (!(p.debug & 1)) {
+        if (!NB200_DBG(p.debug, 1)) {
           const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);
           if (pend) compact_lane<KPL>(__ffs(pend) - 1, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
         }
@@ -1066,6 +1080,8 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       __syncwarp();
       int s = 0;
       uint32_t ph = 0;
+      [[maybe_unused]] unsigned long long c_wait = 0, c_all = 0;
+      NB_T0(tp);
       for (int pi = 0; pi < TS_MAXP; ++pi) {
         const int4 pc = __ldg(my_pieces + pi);
         if (pc.x < 0) break;
@@ -1073,10 +1089,12 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         const int wa = ts_warm_tiles(p.warm_max, len);
         for (int idx = -wa; idx < len; ++idx) {
           const int t = t_begin + (idx < 0 ? idx + wa : idx);
+          NB_TACC(c_all, tp);
           mbar_wait(&empty_bar[s], ph ^ 1);
+          NB_TACC(c_wait, tp);
           unsigned char* st = smem_st + (size_t)s * stage_bytes;
           if (elect_one()) {
-            if (p.debug & 2) {  // timing experiment: no database traffic
+            if (NB200_DBG(p.debug, 2)) {  // timing experiment: no database traffic
               mbar_arrive(&full_bar[s]);
             } else {
               mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
@@ -1092,6 +1110,12 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
           }
         }
       }
+#ifdef NB200_EXPERIMENTS
+      if (p.counters && lane == 0) {
+        atomicAdd(p.counters + 8, c_wait);
+        atomicAdd(p.counters + 9, c_all + c_wait);
+      }
+#endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -1103,22 +1127,29 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       int ti = 0;
+      [[maybe_unused]] unsigned long long c_afull = 0, c_tempty = 0, c_full = 0, c_issue = 0;
+      NB_T0(tm);
       for (int pi = 0; pi < TS_MAXP; ++pi) {
         const int4 pc = __ldg(my_pieces + pi);
         if (pc.x < 0) break;
         const int n_iter = (pc.z - pc.y) + ts_warm_tiles(p.warm_max, pc.z - pc.y);
+        NB_TACC(c_issue, tm);
         mbar_wait(afull_bar, pi & 1);
+        NB_TACC(c_afull, tm);
         tc_fence_after();
         for (int it = 0; it < n_iter; ++it, ++ti) {
           const int b = ti & 1;
+          NB_TACC(c_issue, tm);
           mbar_wait(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
+          NB_TACC(c_tempty, tm);
           mbar_wait(&full_bar[s], ph);
+          NB_TACC(c_full, tm);
           tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)(TS_ACC0 + b * 2 * TS_BN);
           const uint32_t d1 = d0 + TS_BN;
           const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
           if (elect_one()) {
-            if (p.debug & 256) {  // timing experiment: N = 128 MMAs on every other tile (same MAC count, garbage)
+            if (NB200_DBG(p.debug, 256)) {  // timing experiment: N = 128 MMAs on every other tile (same MAC count, garbage)
               if (!(ti & 1)) {
                 constexpr uint32_t idesc2 = make_idesc_tf32(TC_BM, 128);
                 for (int kb = 0; kb < p.n_kb; ++kb) {
@@ -1131,7 +1162,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
                 umma_tf32(d0, d_ones, dbn, idesc2, 1);
                 umma_tf32(d0, d_ones, dbn, idesc2, 1);
               }
-            } else if (!(p.debug & 4)) {
+            } else if (!NB200_DBG(p.debug, 4)) {
               for (int kb = 0; kb < p.n_kb; ++kb) {
                 const uint64_t db = make_smem_desc(sb + (uint32_t)kb * TS_CHUNK);
                 const uint32_t a0 = tmem_base + (uint32_t)(kb * TC_KB);
@@ -1147,7 +1178,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
                 umma_tf32_ts(d0, a0 + 24, db + 6, idesc, 1);
                 umma_tf32_ts(d1, a1 + 24, db + 6, idesc, 1);
               }
-              if (p.use_nb && !(p.debug & 128)) {  // + 1.0 * (hi + mid + lo pieces of |x|^2)
+              if (p.use_nb && !NB200_DBG(p.debug, 128)) {  // + 1.0 * (hi + mid + lo pieces of |x|^2)
                 const uint64_t dbn = make_smem_desc(sb + (uint32_t)p.n_kb * TS_CHUNK);
                 umma_tf32(d0, d_ones, dbn, idesc, 1);
                 umma_tf32(d1, d_ones, dbn, idesc, 1);
@@ -1163,12 +1194,23 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
           }
         }
       }
+#ifdef NB200_EXPERIMENTS
+      NB_TACC(c_issue, tm);
+      if (p.counters && lane == 0) {
+        atomicAdd(p.counters + 10, c_afull);
+        atomicAdd(p.counters + 11, c_tempty);
+        atomicAdd(p.counters + 12, c_full);
+        atomicAdd(p.counters + 13, c_issue);
+      }
+#endif
     }
   } else {
     // ===================== epilogue: 8 warps, thread == one query row =====================
     const int e = warp - 2;
     const int h = e >> 2;
     const int quarter = warp & 3;
+    [[maybe_unused]] unsigned long long c_twait = 0, c_drain = 0, c_proc = 0, c_setup = 0;
+    NB_T0(te);
     const int row = quarter * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     unsigned ctr[4] = {0, 0, 0, 0};
@@ -1215,9 +1257,12 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       const int wa = ts_warm_tiles(p.warm_max, len);
       // wait for a tile's accumulators, pull this row's 64 columns into registers and hand the buffer back to
       // the tensor core at once (a warp inside a compaction must not hold up the other seven and the MMA)
+      NB_TACC(c_setup, te);
       auto drain = [&](uint32_t (&v0)[32], uint32_t (&v1)[32]) {
         const int b = ti & 1;
+        NB_TACC(c_proc, te);
         mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
+        NB_TACC(c_twait, te);
         tc_fence_after();
         const uint32_t tcol = trow + (uint32_t)(TS_ACC0 + (b * 2 + h) * TS_BN);
         tmem_ld32(tcol, v0);
@@ -1227,6 +1272,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[b]);
         ++ti;
+        NB_TACC(c_drain, te);
       };
       if (wa > 0) {  // warm start (see ts_warm_tiles)
         float gm[32];
@@ -1246,18 +1292,18 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         float t = gm[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) t = fmaxf(t, gm[j]);
-        if (row_valid && !(p.debug & 1)) thr = publish_thr(gthr, f32_ordered(t));
+        if (row_valid && !NB200_DBG(p.debug, 1)) thr = publish_thr(gthr, f32_ordered(t));
       }
       for (int tile = t_begin; tile < t_end; ++tile) {
         uint32_t v0[32], v1[32];
         drain(v0, v1);
-        if (p.debug & 1) {  // timing experiment: select nothing
+        if (NB200_DBG(p.debug, 1)) {  // timing experiment: select nothing
           if (__uint_as_float(v0[0]) == 1.2345e-30f || __uint_as_float(v1[0]) == 1.2345e-30f) thr = 0.f;
           continue;
         }
         // what the other pieces of this query have found in the meantime (fminf ignores the NaN of "nothing yet")
         if (((tile - t_begin) & p.refresh_mask) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
-        if (p.debug & 64) thr = __int_as_float(0xFF800000);  // timing experiment: fast path only, nothing passes
+        if (NB200_DBG(p.debug, 64)) thr = __int_as_float(0xFF800000);  // timing experiment: fast path only, nothing passes
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TS_BN);
         const int vtile = p.n - tile * TS_BN;
         epi_process<KPL, REG>(v0, pos_tile, vtile, buf, cnt, thr, tk, p.cap, p.kprime, p.slack, gthr, lane, ctr);
@@ -1280,6 +1326,13 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     if (p.counters && lane == 0) {
       for (int i = 0; i < 4; ++i) atomicAdd(p.counters + i, (unsigned long long)ctr[i]);
       atomicAdd(p.counters + 4, (unsigned long long)ti * 2);
+#ifdef NB200_EXPERIMENTS
+      NB_TACC(c_proc, te);
+      atomicAdd(p.counters + 14, c_twait);
+      atomicAdd(p.counters + 15, c_drain);
+      atomicAdd(p.counters + 16, c_proc);
+      atomicAdd(p.counters + 17, c_setup);
+#endif
     }
   }
 
@@ -1536,7 +1589,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
       cert = (worst + E + fabsf(worst) * 1e-6f < minthr) ? 1 : 0;
     }
     p.out_cert[q] = cert;
-    if (p.debug_cert && (q < 2 || (cert == 0 && q < 40))) {
+    if (NB200_DBG(p.debug_cert, 1) && (q < 2 || (cert == 0 && q < 40))) {
       float worst = __int_as_float(0xFF800000);
       for (int e = 0; e < p.k && e < p2e; ++e) worst = fmaxf(worst, srank[e]);
       printf("rerank q=%d cert=%d live=%d total=%d p2e=%d items=%d minthr=%g worst=%g qn2=%g n_split=%d cnt0=%d\n", q, cert,
@@ -1799,7 +1852,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   p.gthr = gthr;
   p.use_nb = use_nb ? 1 : 0;
   {
-    const char* dbg = getenv("NB200_TC_DEBUG");
+    const char* dbg = nb200_env("NB200_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
   p.pieces = nullptr;
@@ -1830,13 +1883,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
   return e;
 }
 
-bool tc_pair_enabled() {
-  static const bool off = [] {
-    const char* e = getenv("NB200_TC_PAIR");
-    return e && e[0] == '0';
-  }();
-  return !off;
-}
+bool tc_pair_enabled() { return nb200_option("tc_pair", 1) != 0; }
 int tc_pair_block_points() { return TP_BN; }
 
 // CTA-pair kernel for long rows: d_pieces / n_pairs from tc_ts_plan(nq, n, k, sm_count / 2, .., TP_BN, 2);
@@ -1879,7 +1926,7 @@ cudaError_t launch_tc_scan_pair(const float* qa, size_t q_pad, const float* dbB,
   p.gthr = gthr;
   p.use_nb = use_nb ? 1 : 0;
   {
-    const char* dbg = getenv("NB200_TC_DEBUG");
+    const char* dbg = nb200_env("NB200_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
   p.a_resident = 0;
@@ -1909,7 +1956,7 @@ cudaError_t launch_tc_scan_pair(const float* qa, size_t q_pad, const float* dbB,
 
 bool tc_ts_supported(int row_words) {
   static const bool off = [] {
-    const char* e = getenv("NB200_TC_NO_TS");
+    const char* e = nb200_env("NB200_TC_NO_TS");
     return e && e[0] == '1';
   }();
   return !off && row_words <= 128 && row_words % TC_KB == 0;
@@ -2043,13 +2090,13 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   p.hwm = std::min(p.cap / 2, std::max(64, 3 * p.kprime));
   p.warm_max = p.kprime <= 32 ? 64 : 0;
   p.refresh_mask = 15;
-  if (const char* e = getenv("NB200_TC_HWM")) p.hwm = std::max(p.kprime + p.slack + 8, std::min(p.cap - 40, atoi(e)));
-  if (const char* e = getenv("NB200_TC_WARM")) p.warm_max = p.kprime <= 32 ? std::max(0, atoi(e)) : 0;
-  if (const char* e = getenv("NB200_TC_REFRESH")) p.refresh_mask = std::max(0, atoi(e));
+  if (const char* e = nb200_env("NB200_TC_HWM")) p.hwm = std::max(p.kprime + p.slack + 8, std::min(p.cap - 40, atoi(e)));
+  if (const char* e = nb200_env("NB200_TC_WARM")) p.warm_max = p.kprime <= 32 ? std::max(0, atoi(e)) : 0;
+  if (const char* e = nb200_env("NB200_TC_REFRESH")) p.refresh_mask = std::max(0, atoi(e));
   p.gthr = gthr;
   p.use_nb = use_nb ? 1 : 0;
   {
-    const char* dbg = getenv("NB200_TC_DEBUG");
+    const char* dbg = nb200_env("NB200_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
   p.q = q;
@@ -2057,22 +2104,23 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   p.scale = scale;
   p.inexact_flag = inexact_flag;
   p.counters = nullptr;
-  static const bool count = [] {
-    const char* e = getenv("NB200_TC_COUNT");
-    return e && e[0] == '1';
-  }();
-  if (count) {  // diagnostics only: synchronous, prints the epilogue's event counts of the previous launch
+  const char* count_env = nb200_env("NB200_TC_COUNT");
+  if (count_env && count_env[0] == '1') {  // diagnostics only: synchronous, prints the epilogue's event counts of the previous launch
     static unsigned long long* d_ctr = nullptr;
     if (!d_ctr) {
-      cudaMalloc(&d_ctr, 64);
+      cudaMalloc(&d_ctr, 256);
     } else {
-      unsigned long long h[5];
+      unsigned long long h[18];
       cudaStreamSynchronize(stream);
-      cudaMemcpy(h, d_ctr, 40, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "tc_scan_ts counters: (unused) %llu, slow-path entries %llu, forced compactions %llu, deferred %llu, warp-chunks %llu\n",
               h[0], h[1], h[2], h[3], h[4]);
+      const double c = (double)n_cta;
+      fprintf(stderr, "  cycles per CTA: producer wait-empty %.0f of %.0f | mma wait-afull %.0f wait-tempty %.0f wait-full %.0f issue %.0f | "
+                      "epilogue (per warp) wait-tfull %.0f drain %.0f process %.0f setup %.0f\n",
+              h[8] / c, h[9] / c, h[10] / c, h[11] / c, h[12] / c, h[13] / c, h[14] / c / 8, h[15] / c / 8, h[16] / c / 8, h[17] / c / 8);
     }
-    cudaMemsetAsync(d_ctr, 0, 64, stream);
+    cudaMemsetAsync(d_ctr, 0, 256, stream);
     p.counters = d_ctr;
   }
   const int ones_bytes = use_nb ? CHUNK_BYTES : 0;
@@ -2088,7 +2136,7 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   if (e != cudaSuccess) return e;                                                                                 \
   tc_scan_ts_kernel<KPL, REG><<<n_cta, TC_THREADS, smem, stream>>>(tmB, tmN, tmO, p);
   static const bool no_reg = [] {
-    const char* e2 = getenv("NB200_TC_NO_REG");
+    const char* e2 = nb200_env("NB200_TC_NO_REG");
     return e2 && e2[0] == '1';
   }();
   // register list (16 ranks): k <= 12 leaves the certificate a margin of >= 4 ranks; a margin raised by the
@@ -2096,7 +2144,7 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   if (k + 4 <= TS_RK && kprime <= k + 6 && p.cap == 256 && !no_reg) {
     p.kprime = TS_RK;  // the register list always holds 16
     p.slack = 8;
-    if (!getenv("NB200_TC_WARM")) p.warm_max = 0;  // exact thresholds make the cold start cheaper than the re-scan
+    if (!nb200_env("NB200_TC_WARM")) p.warm_max = 0;  // exact thresholds make the cold start cheaper than the re-scan
     NB_TS(8, true);
   } else if (p.cap == 256) {
     NB_TS(8, false);
@@ -2147,7 +2195,7 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
   p.inexact_flags = inexact_flags;
   p.out_keys = out_keys;
   p.out_cert = out_cert;
-  p.debug_cert = getenv("NB200_TC_DEBUG_CERT") != nullptr;
+  p.debug_cert = nb200_env("NB200_TC_DEBUG_CERT") != nullptr;
   if (n_split > 64) return cudaErrorInvalidValue;
   // sort buffer: the live keys (pass-1 rank below the final threshold) are a few times k'; a query with more
   // than this many is left uncertified and re-run exactly

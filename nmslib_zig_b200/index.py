@@ -19,7 +19,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libnmslib_b200.so"
+# NB200_LIB: the tools point this at lib/libnmslib_b200_exp.so (the -DNB200_EXPERIMENTS build with the timing knobs)
+LIB_PATH = Path(os.environ["NB200_LIB"]) if os.environ.get("NB200_LIB") else _PKG / "lib" / "libnmslib_b200.so"
 
 # ---- nmslib_b200.h types -------------------------------------------------------------
 DATATYPE = {"DenseVector": 0, "SparseVector": 1, "DenseUInt8Vector": 2, "ObjectAsString": 3}
@@ -84,7 +85,7 @@ ABI_SYMBOLS = [
 EXT_SYMBOLS = [
     "nmslib_b200_set_device", "nmslib_b200_device_available", "nmslib_b200_set_shard", "nmslib_b200_import_hnsw",
     "nmslib_b200_prepare", "nmslib_b200_knn_device", "nmslib_b200_merge_topk", "nmslib_b200_get_stats",
-    "nmslib_b200_version", "nmslib_b200_scan_plan", "nmslib_b200_scan_plan_pairs",
+    "nmslib_b200_version", "nmslib_b200_scan_plan", "nmslib_b200_scan_plan_pairs", "nmslib_b200_set_option",
 ]
 
 _lib = None
@@ -174,6 +175,7 @@ def lib() -> C.CDLL:
         "nmslib_b200_merge_topk": (C.c_int, [vp, vp, vp, sz, sz, sz, vp, vp, vp]),
         "nmslib_b200_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "nmslib_b200_version": (C.c_char_p, []),
+        "nmslib_b200_set_option": (C.c_int, [C.c_char_p, C.c_int]),
         "nmslib_b200_scan_plan": (sz, [sz, sz, sz, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "nmslib_b200_scan_plan_pairs": (sz, [sz, sz, sz, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
@@ -514,6 +516,11 @@ def scan_plan_pairs(nq: int, n: int, k: int, sm_count: int = 148):
     out = np.zeros((m, 5), np.int32)
     L.nmslib_b200_scan_plan_pairs(nq, n, k, sm_count, out.ctypes.data, m, C.byref(nc), C.byref(sm))
     return out, nc.value, sm.value
+
+
+def set_option(name: str, value: int):
+    """Process-wide variant selector (include/nmslib_b200.h: tc_pair, hnsw_team, force_exact, tc_split, u8_imma)."""
+    _check(lib().nmslib_b200_set_option(name.encode(), int(value)))
 
 
 def version() -> str:

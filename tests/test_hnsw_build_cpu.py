@@ -114,3 +114,70 @@ def test_reference_searches_our_graph_through_its_cpp_api(tmp_path):
         assert np.array_equal(rc, pc) and np.mean(ri == pi) >= 0.995
     port.close()
     ref.close()
+
+
+def test_hostile_index_files_are_rejected(tmp_path):
+    """the reader checks LEVEL consistency, not only id ranges -- the device-side greedy descent reads the
+    level-l list of every node it reaches at level l, so an enterpoint with fewer levels than maxlevel, or a neighbour
+    listed at a level it does not have, must fail at load time instead of becoming an out-of-bounds device read."""
+    import struct
+    data = synth.gist_like(4000, 16, 43, clusters=8)
+    path = tmp_path / "g.hnsw"
+    _build("l2", data, {"M": 6, "efConstruction": 60}, path)
+    raw = bytearray(path.read_bytes())
+    total, = struct.unpack_from("<I", raw, 4)
+    mem_per_obj, = struct.unpack_from("<Q", raw, 8)
+    maxlevel, enter = struct.unpack_from("<iI", raw, 32)
+    maxM, = struct.unpack_from("<Q", raw, 40)
+    assert maxlevel >= 1 and total == 4000
+    ok = nb.Index.load(str(path))
+    ok.deinit()
+
+    bad1 = bytearray(raw)                                   # (1) maxlevel raised above the enterpoint's own level count
+    struct.pack_into("<i", bad1, 32, maxlevel + 1)
+    (tmp_path / "bad1.hnsw").write_bytes(bad1)
+    with pytest.raises(nb.NmslibError):
+        nb.Index.load(str(tmp_path / "bad1.hnsw"))
+
+    # (2) a level-1 neighbour replaced by a node that has no upper levels at all
+    off = 68 + total * mem_per_obj                          # header is 4+4+8+8+8+4+4+8+8+4+8 = 68 bytes
+    level0_only, victim = None, None
+    pos = off
+    blocks = []
+    for i in range(total):
+        nbytes, = struct.unpack_from("<I", raw, pos)
+        blocks.append((pos + 4, nbytes))
+        pos += 4 + nbytes
+    for i, (o, nbytes) in enumerate(blocks):
+        if nbytes == 0 and level0_only is None:
+            level0_only = i
+        if nbytes and victim is None and struct.unpack_from("<i", raw, o)[0] > 0:
+            victim = i
+    assert level0_only is not None and victim is not None
+    bad2 = bytearray(raw)
+    struct.pack_into("<i", bad2, blocks[victim][0] + 4, level0_only)
+    (tmp_path / "bad2.hnsw").write_bytes(bad2)
+    with pytest.raises(nb.NmslibError):
+        nb.Index.load(str(tmp_path / "bad2.hnsw"))
+
+
+def test_corrupt_dat_records_are_rejected(tmp_path):
+    """.dat records whose stored datalength disagrees with the record length (or is not a whole number of
+    floats) fail the load instead of reaching add_rows with a wrong element count."""
+    import struct
+    d = synth.uniform(20, 8, 44)
+    idx = nb.Index("l2", None, "seq_search")
+    idx.addDenseBatch(d)
+    idx.buildIndex()
+    path = tmp_path / "s.idx"
+    idx.save(str(path), True)
+    idx.deinit()
+    ok = nb.Index.load(str(path), load_data=True)
+    assert ok.dataQty() == 20
+    ok.deinit()
+    raw = bytearray(Path(str(path) + ".dat").read_bytes())
+    # file: u64 qty, then per record: u64 buflen | i32 id | i32 label | u64 datalen | payload
+    struct.pack_into("<Q", raw, 8 + 8 + 8, 8 * 4 - 1)       # first record: datalen no longer equals buflen - 16
+    Path(str(path) + ".dat").write_bytes(raw)
+    with pytest.raises(nb.NmslibError):
+        nb.Index.load(str(path), load_data=True)

@@ -174,6 +174,7 @@ def test_team_kernel_answers_are_bit_identical_to_the_one_warp_kernel(tmp_path):
         f"sys.path.insert(0, {str(Path(__file__).resolve().parents[1])!r})\n"
         "import nmslib_zig_b200 as nb\n"
         "from nmslib_zig_b200 import synth\n"
+        "nb.set_option('hnsw_team', int(sys.argv[2]))\n"
         "data, q = synth.gist_like(20000, 96, 5, clusters=16), synth.gist_like(700, 96, 6, clusters=16)\n"
         "idx = nb.Index('cosinesimil', None, 'hnsw'); idx.addDenseBatch(data)\n"
         "idx.buildIndex(nb.Params({'M': 16, 'efConstruction': 100, 'b200_build': 'host', 'indexThreadQty': 1}))\n"
@@ -185,7 +186,6 @@ def test_team_kernel_answers_are_bit_identical_to_the_one_warp_kernel(tmp_path):
     outs = []
     for mode in ("0", "2", "4"):
         path = tmp_path / f"team{mode}.npy"
-        env = dict(**__import__("os").environ, NB200_HNSW_TEAM=mode)
-        subprocess.run([sys.executable, "-c", script, str(path)], check=True, env=env, timeout=600)
+        subprocess.run([sys.executable, "-c", script, str(path), mode], check=True, timeout=600)
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])

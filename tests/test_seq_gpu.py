@@ -364,9 +364,8 @@ def test_range_query_errors_like_the_reference():
 
 
 def test_pair_kernel_and_single_cta_kernel_agree(tmp_path):
-    """NB200_TC_PAIR=0 keeps the single-CTA long-row kernel (tc_scan_kernel) for A/B runs: on the same data both
-    nominate candidates for the same exact re-rank, so ids and distances are equal.  The switch is read once per
-    process, hence two child processes."""
+    """Option tc_pair=0 keeps the single-CTA long-row kernel (tc_scan_kernel) for A/B runs: on the same data both
+    nominate candidates for the same exact re-rank, so ids and distances are equal."""
     import os
     import subprocess
     import sys
@@ -375,6 +374,7 @@ def test_pair_kernel_and_single_cta_kernel_agree(tmp_path):
         f"sys.path.insert(0, {str(Path(__file__).resolve().parents[1])!r})\n"
         "import nmslib_zig_b200 as nb\n"
         "from nmslib_zig_b200 import synth\n"
+        "nb.set_option('tc_pair', int(sys.argv[2]))\n"
         "out = []\n"
         "for space, dim, k in (('negdotprod', 768, 100), ('l2', 200, 10)):\n"
         "    data = synth.embedding_like(30000, dim, 9) if space == 'negdotprod' else synth.uniform(30000, dim, 1)\n"
@@ -387,7 +387,68 @@ def test_pair_kernel_and_single_cta_kernel_agree(tmp_path):
     outs = []
     for mode in ("1", "0"):
         path = tmp_path / f"pair{mode}.npy"
-        env = dict(os.environ, NB200_TC_PAIR=mode)
-        subprocess.run([sys.executable, "-c", script, str(path)], check=True, env=env, timeout=600)
+        subprocess.run([sys.executable, "-c", script, str(path), mode], check=True, timeout=600)
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_reset_then_shorter_rows_with_the_same_padded_length():
+    """the staged-query buffer keeps its allocation across nmslib_reset_index; going from 128 to 100 floats
+    (both pad to 128 words) must not leave the old queries' columns [100, 128) in the padding, which feeds the exact
+    re-rank, the cosine norms and the range scan."""
+    for space in ("l2", "cosinesimil", "negdotprod"):
+        d1, q1 = synth.uniform(3000, 128, 71) + 5.0, synth.uniform(300, 128, 72) + 5.0     # large stale values
+        idx = make_index(space, d1)
+        idx.knnQueryBatch(q1, 10)
+        idx.reset()
+        d2, q2 = synth.uniform(3000, 100, 73), synth.uniform(300, 100, 74)
+        idx.addDenseBatch(d2)
+        idx.buildIndex()
+        r = idx.knnQueryBatch(q2, 10)
+        oi, od, oc = O.seq_knn(space, d2, q2, 10)
+        assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, what=f"reset/{space}",
+                           atol=ATOL_COSINE if space == "cosinesimil" else None)
+        if space == "l2":
+            rr = idx.rangeQuery(q2[0], float(od[0, 4]) * 1.0001, capacity=64)
+            assert set(oi[0, :5].tolist()) <= set(rr.ids.tolist())
+        idx.deinit()
+
+
+def test_two_half_shards_on_one_gpu_merge_to_the_unsharded_answer():
+    """the cross-shard step (keys carrying global positions -> k-way merge, with and without id lists) on a
+    box with ONE GPU: two half-shard indexes on the same device play the two ranks."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n, dim, nq, k = 20_001, 64, 257, 10
+    data, q = synth.uniform(n, dim, 81), synth.uniform(nq, dim, 82)
+    data[n // 2 + 3] = data[5]
+    q[0] = data[5]
+    ext = np.arange(n, dtype=np.int32) * 2 + 1
+    d_q = torch.from_numpy(q).to(dev)
+    keys = torch.empty((2, nq, k), dtype=torch.int64, device=dev)
+    ids = torch.empty((2, nq, k), dtype=torch.int32, device=dev)
+    dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    shards = []
+    for r, (lo, hi) in enumerate(((0, n // 2), (n // 2, n))):
+        idx = nb.Index("l2", None, "seq_search")
+        idx.setShard(lo)
+        idx.addDenseBatch(data[lo:hi], ext[lo:hi])
+        idx.buildIndex()
+        idx.knnDevice(d_q.data_ptr(), nq, dim, k, ids[r].data_ptr(), dd.data_ptr(), keys[r].data_ptr(), 0)
+        shards.append(idx)
+    torch.cuda.synchronize(dev)
+    o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    o_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    p_ids, p_d = torch.empty_like(o_ids), torch.empty_like(o_d)
+    shards[0].mergeTopk(keys.data_ptr(), ids.data_ptr(), 2, nq, k, o_ids.data_ptr(), o_d.data_ptr(), 0)
+    shards[0].mergeTopk(keys.data_ptr(), 0, 2, nq, k, p_ids.data_ptr(), p_d.data_ptr(), 0)
+    torch.cuda.synchronize(dev)
+    assert torch.equal(p_ids * 2 + 1, o_ids) and torch.equal(p_d, o_d)   # no id lists: ids = global positions
+    whole = make_index("l2", data, ext)
+    w = whole.knnQueryBatch(q, k)
+    assert np.array_equal(o_ids.cpu().numpy(), w.ids) and np.array_equal(o_d.cpu().numpy(), w.distances)
+    assert w.ids[0, 0] == 5 * 2 + 1 and w.ids[0, 1] == (n // 2 + 3) * 2 + 1      # cross-shard tie: lower position first
+    oi, od, oc = O.seq_knn("l2", data, q, k, ext)
+    assert_knn_matches(w.ids, w.distances, w.sizes, oi, od, oc, what="two half shards")
+    for idx in shards + [whole]:
+        idx.deinit()
