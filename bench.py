@@ -94,7 +94,52 @@ def workload(name: str, n: int | None, nq: int | None, rank: int = 0, world: int
     lo, hi = shard_bounds(n, rank, world)
     data, queries = synth.make(name, n, nq, rows=(lo, hi) if world > 1 else None)
     return dict(name=name, space=space, method=method, dtype=dtype, dist=dist, dim=dim, k=k, data=data,
-                queries=queries, n=n, nq=queries.shape[0], lo=lo, hi=hi)
+                queries=queries, n=n, nq=queries.shape[0], lo=lo, hi=hi, full_size=(n == n0 and queries.shape[0] == nq0))
+
+
+
+def sample_queries(nq: int, want: int) -> np.ndarray:
+    """Indices of `want` queries spread evenly over the batch (every 256-query block of the scan is represented
+    as far as `want` allows)."""
+    return np.unique(np.linspace(0, nq - 1, min(want, nq)).astype(np.int64))
+
+
+def parity_seq(w, sel, got_ids, got_dists, rank, world, dist_on, threads=None):
+    """Check the final (merged) answers of the queries `sel` against the oracle (oracle/knn_oracle.c, the CPU
+    restatement of SeqSearch::Search + the distance kernels, pinned to the reference by tests/test_oracle.py).
+    N > 1: every rank runs the oracle over ITS OWN row shard (w["data"] holds nothing else), the per-shard oracle
+    lists go to rank 0 over the host channel and are merged there by (distance, global position) -- the
+    specification of the device merge (nmslib_zig_b200/shard.py).  Returns the `parity` record on rank 0."""
+    from oracle import oracle as O
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import ATOL_COSINE, RTOL, ATOL, count_mismatches
+    from nmslib_zig_b200.shard import make_keys
+    k, space = w["k"], w["space"]
+    u8 = w["dtype"] == "DenseUInt8Vector"
+    t0 = time.perf_counter()
+    pos = np.arange(w["lo"], w["hi"], dtype=np.int32)
+    thr = threads or max(1, (os.cpu_count() or 1) // world)
+    oi, od, oc = O.seq_knn(space, w["data"], w["queries"][sel], k, pos, threads=thr)
+    if dist_on:
+        import torch.distributed as dist
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((oi, od), gathered, dst=0)
+        if rank != 0:
+            return None
+        allp = np.concatenate([g[0] for g in gathered], axis=1)               # [q, world * k] global positions
+        alld = np.concatenate([g[1] for g in gathered], axis=1)
+        order = np.argsort(make_keys(alld, allp), axis=1, kind="stable")[:, :k]   # (distance, position) order
+        oi = np.take_along_axis(allp, order, axis=1)
+        od = np.take_along_axis(alld, order, axis=1)
+        oc = (oi >= 0).sum(axis=1).astype(np.int32)
+    gi, gd = np.asarray(got_ids)[sel], np.asarray(got_dists)[sel]
+    gc = (gi >= 0).sum(axis=1).astype(np.int32)
+    bad = count_mismatches(gi, gd, gc, oi, od, oc, exact=u8, atol=ATOL_COSINE if space == "cosinesimil" else None)
+    return {"checked": int(len(sel)), "mismatches": int(bad), "against": "oracle/knn_oracle.c over all "
+            f"{w['n']} rows" + (f" ({world} shard oracles merged on the host)" if dist_on else ""),
+            "tolerance": "bit-exact ids and distances (ties: set-equal)" if u8 else
+                         f"ids exact outside tie groups; |d - d_ref| <= {RTOL}*|d_ref| + {ATOL}",
+            "seconds": time.perf_counter() - t0}
 
 
 def synth_method(name: str) -> str:
@@ -138,7 +183,7 @@ def time_reference(w, sample: int, steps: int, warmup: int):
             "ms_per_step": dt * 1e3}
 
 
-def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
+def run_hnsw(args, w, rank, world, local_rank, dev, dist_on, n_steps, with_cpu):
     """Config 3: HNSW beam search (K3).  One graph does not shard without changing its answers: every
     rank holds a replica of the index -- built on the device by csrc/hnsw_build_gpu.cu -- and takes 1/N of the
     queries; there is no data-path collective.  efSearch = the smallest of the sweep that reaches recall@10 >= 0.95
@@ -200,7 +245,7 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         step_device()
     e1.record(stream)
     barrier()
@@ -211,19 +256,20 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
         idx.knnQueryBatch(q_np, k)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         idx.knnQueryBatch(q_np, k)
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_steps
     if dist_on:
         t = torch.tensor([ms, e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(t[0].item()), float(t[1].item())
     clocks = sampler.stop() if rank == 0 else None
+    line = None
     if rank == 0:
         peaks = load_peaks()
-        ms_per_step = ms / args.steps
-        steps = max(1, args.steps)
+        ms_per_step = ms / n_steps
+        steps = max(1, n_steps)
         evals = (st1["distance_evals"] - st0["distance_evals"]) / steps
         exps = (st1["hnsw_expansions"] - st0["hnsw_expansions"]) / steps
         kern_ms = (st1["scan_ms_sum"] - st0["scan_ms_sum"]) / max(1, st1["scan_count"] - st0["scan_count"])
@@ -233,12 +279,12 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
         traffic = None
         try:  # DRAM bytes per launch from the committed ncu capture (full-size config, one GPU, efSearch 400 only)
             tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
-            if world == 1 and args.n is None and args.nq is None and ef == 400 and w["name"] in tj:
+            if world == 1 and w["full_size"] and ef == 400 and w["name"] in tj:
                 traffic = tj[w["name"]]["bytes"]
         except Exception:
             traffic = None
-        cpu = None
-        if world == 1 and not args.no_cpu:
+        cpu, parity = None, None
+        if world == 1 and with_cpu:
             # the REFERENCE's own HNSW search (Index::LoadIndex + Search through oracle/_ref, OpenMP over queries on all
             # host cores) on the SAME device-built graph, same efSearch, a bounded query sample
             from oracle import oracle as O
@@ -253,6 +299,14 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
                 ri, _, _ = ref.knn(sample, k, threads=threads)
                 dt = time.perf_counter() - t0
                 rec_ref = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(ri, exact_ids)]))
+                # north_star: recall@10 at or above the reference HNSW's at the same efSearch on the same graph; the ids
+                # themselves agree except where fp32 rounding reorders near-ties inside the beam
+                agree = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(got, ri)]))
+                parity = {"checked": int(len(sample)), "mismatches": int(rec < rec_ref - 2e-3),
+                          "recall_ours": rec, "recall_reference_same_graph": rec_ref, "id_agreement_with_reference": agree,
+                          "against": "the reference's Hnsw::Search (oracle/_ref) on the same graph at the same efSearch; "
+                                     "ground truth for recall = this library's exact scan (itself checked against the oracle)",
+                          "tolerance": "recall_ours >= recall_reference - 2e-3"}
                 cpu = {"value": len(sample) / dt, "unit": "queries/s", "cores": threads, "kind": "reference",
                        "sample": f"{len(sample)} of {nq} queries, the reference's Hnsw::Search on the same (device-built) "
                                  f"graph at efSearch={ef}; its recall@{k} on that sample: {rec_ref:.4f} (ours: {rec:.4f})"}
@@ -263,7 +317,7 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
                     pass
         line = {
             "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": n_steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{w['name']}: hnsw {w['space']} {n}x{dim}, M=16 efConstruction=200 (graph built on the "
                                    f"device), efSearch={ef}, {nq} queries, k={k}", "space": w["space"], "k": k,
@@ -279,10 +333,10 @@ def run_hnsw(args, w, rank, world, local_rank, dev, dist_on):
                          "kernel_ms": kern_ms * launches_per_step,
                          "bytes_per_query": gbytes * 1e9 / max(1, my_nq),
                          "peak_src": f"{peaks['src']} HBM copy bandwidth"},
-            "cpu_baseline": cpu, "clocks": clocks,
+            "parity": parity, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line))
     idx.deinit()
+    return line if rank == 0 else None
 
 
 def main():
@@ -297,6 +351,12 @@ def main():
     ap.add_argument("--nq", type=int, default=None, help="override query count (debug)")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--workloads", default="c1,c4,c3",
+                    help="further single-GPU configs reported as sub-records of the default line ('none' to skip)")
+    ap.add_argument("--budget-s", type=float, default=420.0, help="no new sub-record is started after this many seconds")
+    ap.add_argument("--parity-sample", type=int, default=256, help="queries of the final answer checked against the oracle")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = the library's own NVLink peer-memory exchange, 'nccl' = all-gather + merge")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -336,14 +396,47 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    t_start = time.perf_counter()
 
-    if synth_method(args.workload) == "hnsw":          # config 3: replicas, queries split (no row shards)
-        w = workload(args.workload, args.n, args.nq)
-        run_hnsw(args, w, rank, world, local_rank, dev, dist_on)
-        if dist_on:
-            dist.destroy_process_group()
-        return
-    w = workload(args.workload, args.n, args.nq, rank, world)
+    def run(name, n=None, nq=None, steps=None, warmup=None, cpu=True):
+        if synth_method(name) == "hnsw":          # config 3: replicas, queries split (no row shards)
+            w = workload(name, n, nq)
+            return run_hnsw(args, w, rank, world, local_rank, dev, dist_on, steps or args.steps, cpu and not args.no_cpu)
+        w = workload(name, n, nq, rank, world)
+        return run_seq(args, w, rank, world, local_rank, dev, dist_on, steps or args.steps, warmup or args.warmup,
+                       cpu and not args.no_cpu)
+
+    line = run(args.workload, args.n, args.nq)
+    # the other single-GPU configurations of BASELINE.json as sub-records of the default line (driver-visible parity,
+    # roofline and cpu_baseline for each): config 1, config 4 at full size, config 3 at full size
+    subs = [x for x in args.workloads.split(",") if x and x != "none" and x != args.workload]
+    if world == 1 and args.n is None and args.nq is None and subs and line is not None:
+        line["workloads"] = {}
+        for name in subs:
+            if time.perf_counter() - t_start > args.budget_s:
+                line["workloads"][name] = {"skipped": f"time budget of {args.budget_s:.0f} s spent"}
+                continue
+            try:
+                rec = run(name, steps=max(3, min(args.steps, 10)), warmup=3)
+                for drop in ("metric", "unit", "higher_is_better", "vs_baseline", "data", "n_gpus", "clocks"):
+                    rec.pop(drop, None)
+                line["workloads"][name] = rec
+            except Exception as e:  # a sub-record must not take the headline line down with it
+                line["workloads"][name] = {"error": f"{type(e).__name__}: {e}"}
+    if rank == 0 and line is not None:
+        line["wall_s"] = time.perf_counter() - t_start
+        print(json.dumps(line))
+    if dist_on:
+        dist.destroy_process_group()
+
+
+def run_seq(args, w, rank, world, local_rank, dev, dist_on, steps, warmup, with_cpu):
+    """Sequential-search workloads (configs 1, 2, 4, 5): one rank per GPU, rows sharded, the per-shard key lists
+    exchanged and merged on the device every step.  Returns the JSON record on rank 0 (None elsewhere)."""
+    import torch
+    import nmslib_zig_b200 as nb
+    if dist_on:
+        import torch.distributed as dist
     n, nq, dim, k = w["n"], w["nq"], w["dim"], w["k"]
     u8 = w["dtype"] == "DenseUInt8Vector"
     lo, hi = w["lo"], w["hi"]
@@ -359,10 +452,33 @@ def main():
     d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
     d_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
     d_keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    exchange = "none"
     if dist_on:
-        g_keys = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-        o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        o_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        exchange = args.exchange
+        if exchange == "peer":
+            # the library's own exchange: every rank exports its key window (CUDA IPC), the 128-byte blobs travel over
+            # the host channel once, then nmslib_b200_knn_device returns the GLOBAL top-k on every rank with no
+            # collective call per step (publish + merge over NVLink peer memory inside the engine's stream)
+            try:
+                blob = idx.shardExport(nq, k)
+                blobs = [None] * world
+                dist.all_gather_object(blobs, bytes(blob))
+                idx.shardConnect(rank, world, b"".join(blobs))
+            except Exception as e:
+                if rank == 0:
+                    print(f"bench.py: peer exchange unavailable ({e}); falling back to NCCL all-gather", file=sys.stderr)
+                exchange = "nccl"
+            flag = torch.tensor([1 if exchange == "peer" else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # all ranks or none
+            if int(flag.item()) == 0 and exchange == "peer":
+                idx.shardDisconnect()
+                exchange = "nccl"
+        if exchange == "nccl":
+            g_keys = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+            o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+            o_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        else:
+            o_ids, o_dists = d_ids, d_dists
     # a dedicated non-default stream: the C ABI treats a NULL stream as "the engine's own stream", and CUDA
     # events only see the stream they are recorded on
     stream = torch.cuda.Stream(dev)
@@ -371,7 +487,7 @@ def main():
     def step_device():
         idx.knnDevice(d_q.data_ptr(), nq, dim, k, d_ids.data_ptr(), d_dists.data_ptr(), d_keys.data_ptr(),
                       stream.cuda_stream)
-        if dist_on:
+        if dist_on and exchange == "nccl":
             # the shards number their rows by global position (shard_ids above), which is what the keys carry: only
             # the (distance, position) keys cross NVLink, 8 bytes per candidate, and the merge takes the ids from them
             dist.all_gather_into_tensor(g_keys, d_keys)
@@ -382,7 +498,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     barrier()
     st0 = idx.stats()
@@ -392,7 +508,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     e1.record(stream)
     barrier()
@@ -402,9 +518,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     st1 = idx.stats()
-    ms_per_step = ms / args.steps
+    ms_per_step = ms / steps
     value = nq / (ms_per_step * 1e-3)
-    launches = int(st1["kernel_launches"] - st0["kernel_launches"]) + (args.steps if dist_on else 0)  # (+ the merge)
+    launches = int(st1["kernel_launches"] - st0["kernel_launches"]) + (steps if exchange == "nccl" else 0)  # (+ the merge)
     scan_ms = (st1["scan_ms_sum"] - st0["scan_ms_sum"]) / max(1, st1["scan_count"] - st0["scan_count"])
 
     # ---- end to end through the public API: pinned host queries in, host results out ----
@@ -429,60 +545,103 @@ def main():
         step_e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         res = step_e2e()
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
     if dist_on:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    st2 = idx.stats()
 
+    # ---- parity of the final answers (every N): a query sample spread over all query blocks against the oracle ----
+    if dist_on:
+        got_ids, got_d = (h_ids.numpy(), h_dists.numpy()) if rank == 0 else (None, None)
+    else:
+        got_ids, got_d = res.ids, res.distances
+    parity = parity_seq(w, sample_queries(nq, args.parity_sample), got_ids, got_d, rank, world, dist_on)
+
+    line = None
     if rank == 0:
         peaks = load_peaks()
-        flops = 2.0 * nq * (hi - lo) * dim                     # 2*Q*N*D per launch (this rank's shard)
-        achieved = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
-        # TF32 dense = 1/2 bf16.  A short timed region runs at burst clocks; one that keeps the tensor pipe busy for
-        # more than a second sits under the power cap like the sustained cuBLAS measurement does (MEASURED_PEAKS.json)
-        sustained = ms > 1000.0
-        tf32_peak = (peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]) / 2.0
+        ops = 2.0 * nq * (hi - lo) * dim                       # 2*Q*N*D per launch (this rank's shard)
+        achieved = ops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
+        imma = bool(u8 and st2.get("u8_imma", 0))
+        sustained = ms > 1000.0                                # a long timed region sits under the power cap
+        peak, peak_src = tensor_peak(peaks, "i8" if imma else "tf32", sustained)
         cpu = None
-        if world == 1 and not args.no_cpu:
-            base = time_reference(w, min(args.cpu_sample, nq), 3, 1)
-            cpu = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample", "as_shipped_1core")}
+        if with_cpu and world == 1:
+            cpu = cpu_baseline_seq(w, args.cpu_sample)
         traffic = None
         try:  # DRAM bytes per launch from the committed ncu capture of this workload (full-size, one GPU only)
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
-            if world == 1 and args.n is None and args.nq is None and w["name"] in tj:
+            tj = json.load(open(ROOT / "profiles" / "traffic.json"))
+            if world == 1 and w["full_size"] and w["name"] in tj:
                 traffic = tj[w["name"]]["bytes"]
         except Exception:
             traffic = None
         line = {
-            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u8 (widened to tf32 operands, exact integer sums in f32)" if u8 else "f32",
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": ("u8 (integer tensor pipe, exact int32 distances)" if imma else
+                      "u8 (widened to tf32 operands, exact integer sums in f32)") if u8 else "f32",
             "data": "synthetic",
             "config": {"workload": f"{w['name']}: {w['method']} {w['space']} {n}x{dim}, {nq} queries, k={k}",
                        "space": w["space"], "k": k, "rows_per_gpu": hi - lo,
-                       "parallelism": f"row-sharded x{world}" + (" + NCCL all-gather + device k-way merge" if dist_on else ""),
+                       "parallelism": f"row-sharded x{world}" + (
+                           " + key exchange over NVLink peer memory + device k-way merge inside the library"
+                           if exchange == "peer" else " + NCCL all-gather + device k-way merge" if dist_on else ""),
                        "l2_policy": f"inputs larger than L2 ({(hi - lo) * dim * (1 if u8 else 4) / 1e6:.0f} MB scanned per step)"},
             "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(q_np.nbytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
-            "uncertified_queries_per_step": (st1["fallback_queries"] - st0["fallback_queries"]) / args.steps,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak, "traffic": traffic, "kernel": "scan",
-                         "kernel_ms": scan_ms,
-                         "peak_src": (f"{peaks['src']} bf16 sustained {peaks['bf16_tflops_sustained']} TF/s / 2 (TF32 dense; "
-                                      f"timed region {ms / 1e3:.1f} s)" if sustained else
-                                      f"{peaks['src']} bf16 burst {peaks['bf16_tflops']} TF/s / 2 (TF32 dense)")},
-            "cpu_baseline": cpu, "clocks": clocks,
+            "uncertified_queries_per_step": (st1["fallback_queries"] - st0["fallback_queries"]) / steps,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s" if imma else "TFLOP/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "scan", "kernel_ms": scan_ms,
+                         "peak_src": peak_src},
+            "parity": parity, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line))
     idx.deinit()
-    if dist_on:
-        dist.destroy_process_group()
+    return line
+
+
+def tensor_peak(peaks, kind: str, sustained: bool):
+    """Roofline denominator of the scan: the tcgen05 micro-benchmark of tools/tc_peak.cu run on this pool's B200s
+    (profiles/r02_tc_peak.json: TF32 and INT8 MMA streams, operands resident, burst and sustained), as SURVEY 8d
+    asks; falls back to the driver's bf16 measurement / 2 (TF32) or x 2 (INT8) when that file is missing."""
+    try:
+        tp = json.load(open(ROOT / "profiles" / "r02_tc_peak.json"))
+        key = "tf32_m128n256k8_ts_cta1" if kind == "tf32" else "i8_m128n256k32_ts_cta1"
+        v = tp[key]["sustained" if sustained else "burst"]
+        return float(v), (f"tools/tc_peak.cu on this pool's B200 (profiles/r02_tc_peak.json): {kind} tcgen05 MMA stream, "
+                          f"{'sustained' if sustained else 'burst'} {v:.0f} T(FL)OP/s")
+    except Exception:
+        base = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
+        v = base / 2.0 if kind == "tf32" else base * 2.0
+        return v, f"{peaks['src']} bf16 {'sustained' if sustained else 'burst'} {base} TF/s {'/ 2' if kind == 'tf32' else 'x 2'}"
+
+
+def cpu_baseline_seq(w, cpu_sample: int):
+    """The reference's CPU path on a bounded sample of the workload (about 10-30 s of CPU work).  Configs whose full
+    scan would take minutes (10 M rows) are timed on a row subsample and scaled linearly in N -- seq_search costs
+    exactly Q x N distance calls."""
+    rows = w["n"]
+    sub = w
+    scale = 1.0
+    if w["n"] > 2_000_000 and w["lo"] == 0 and w["hi"] == w["n"]:
+        rows = 1_000_000
+        sub = dict(w, data=w["data"][:rows], n=rows)
+        scale = rows / w["n"]
+    base = time_reference(sub, min(cpu_sample, w["nq"]), 3 if scale == 1.0 else 2, 1)
+    out = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample", "as_shipped_1core")}
+    if scale != 1.0:
+        out["value"] = base["value"] * scale
+        if out["as_shipped_1core"]:
+            out["as_shipped_1core"] *= scale
+        out["sample"] += f"; timed on the first {rows} rows and scaled by {scale:g} to {w['n']} rows (cost is linear in N)"
+    return out
 
 
 if __name__ == "__main__":

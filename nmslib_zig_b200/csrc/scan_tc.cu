@@ -989,6 +989,8 @@ tc_scan_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 constexpr int TS_BN = 64;                 // database rows per tile
 constexpr int TS_CHUNK = TS_BN * 128;     // 8 KB: 64 rows x one 128-byte k-block
 constexpr int TS_ACC0 = 256;              // first accumulator column
+constexpr int TS_THREADS = 352;           // warps: 0 TMA producer, 1 MMA issuer (half 0), 2-9 epilogue, 10 MMA issuer (half 1)
+constexpr int TS_MMA_WARP2 = 10;
 
 
 struct TsParams {
@@ -1024,7 +1026,7 @@ __device__ __forceinline__ int ts_warm_tiles(int warm_max, int len) {
 // one 32-column chunk of one row: fast path = min tree + one compare; survivors are appended to the row's
 // buffer, a full buffer is compacted warp-cooperatively first (see compact_row)
 template <int KPL, bool REG>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TS_THREADS, 1)
 tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmN,
                   const __grid_constant__ CUtensorMap tmO, const TsParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -1049,10 +1051,10 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
   if (tid == 0) {
     for (int s = 0; s < p.n_stage; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);   // one commit from each MMA issuer
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tfull_bar[b], 2);   // one commit from each MMA issuer
       mbar_init(&tempty_bar[b], 8);
     }
     mbar_init(afull_bar, 256);
@@ -1117,12 +1119,19 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       }
 #endif
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == TS_MMA_WARP2) {
+    // ===================== MMA issuers: one warp per 128-query half =====================
+    // A single thread cannot issue N = 64 MMAs fast enough: cycle accounting (profiles/README.md, round 2) showed the
+    // one issuer busy 84 % of the time at ~40 clk per MMA against the 32 clk the tensor pipe needs (tools/tc_peak.cu
+    // reaches 32.0 with a bare loop), while the pipe was active 54 %.  Two issuers on different SM sub-partitions,
+    // each owning one half's accumulators, halve the instructions per thread; stage / accumulator barriers count
+    // one commit from each.
     {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TS_BN);
+      const int hh = warp == 1 ? 0 : 1;
       const uint32_t st_base = smem_u32(smem_st);
       const uint64_t d_ones = make_smem_desc(smem_u32(smem_ones));
+      const uint32_t a_half = tmem_base + (uint32_t)(hh * 128);
       if (p.use_nb) mbar_wait(ones_bar, 0);
       int s = 0;
       uint32_t ph = 0;
@@ -1145,47 +1154,24 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
           mbar_wait(&full_bar[s], ph);
           NB_TACC(c_full, tm);
           tc_fence_after();
-          const uint32_t d0 = tmem_base + (uint32_t)(TS_ACC0 + b * 2 * TS_BN);
-          const uint32_t d1 = d0 + TS_BN;
+          const uint32_t d = tmem_base + (uint32_t)(TS_ACC0 + (b * 2 + hh) * TS_BN);
           const uint32_t sb = st_base + (uint32_t)s * (uint32_t)stage_bytes;
           if (elect_one()) {
-            if (NB200_DBG(p.debug, 256)) {  // timing experiment: N = 128 MMAs on every other tile (same MAC count, garbage)
-              if (!(ti & 1)) {
-                constexpr uint32_t idesc2 = make_idesc_tf32(TC_BM, 128);
-                for (int kb = 0; kb < p.n_kb; ++kb) {
-                  const uint64_t db = make_smem_desc(sb + (uint32_t)kb * TS_CHUNK);
-                  const uint32_t a0 = tmem_base + (uint32_t)(kb * TC_KB);
-                  for (int j = 0; j < 4; ++j) umma_tf32_ts(d0, a0 + 8 * j, db + 2 * j, idesc2, (kb | j) != 0);
-                  for (int j = 0; j < 4; ++j) umma_tf32_ts(d0, a0 + 128u + 8 * j, db + 2 * j, idesc2, 1);
-                }
-                const uint64_t dbn = make_smem_desc(sb + (uint32_t)(p.n_kb - 1) * TS_CHUNK);
-                umma_tf32(d0, d_ones, dbn, idesc2, 1);
-                umma_tf32(d0, d_ones, dbn, idesc2, 1);
-              }
-            } else if (!NB200_DBG(p.debug, 4)) {
+            if (!NB200_DBG(p.debug, 4)) {
               for (int kb = 0; kb < p.n_kb; ++kb) {
                 const uint64_t db = make_smem_desc(sb + (uint32_t)kb * TS_CHUNK);
-                const uint32_t a0 = tmem_base + (uint32_t)(kb * TC_KB);
-                const uint32_t a1 = a0 + 128u;
-                const uint32_t acc = kb != 0;
+                const uint32_t a = a_half + (uint32_t)(kb * TC_KB);
                 // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes (+2 in the descriptor) of B
-                umma_tf32_ts(d0, a0, db, idesc, acc);
-                umma_tf32_ts(d1, a1, db, idesc, acc);
-                umma_tf32_ts(d0, a0 + 8, db + 2, idesc, 1);
-                umma_tf32_ts(d1, a1 + 8, db + 2, idesc, 1);
-                umma_tf32_ts(d0, a0 + 16, db + 4, idesc, 1);
-                umma_tf32_ts(d1, a1 + 16, db + 4, idesc, 1);
-                umma_tf32_ts(d0, a0 + 24, db + 6, idesc, 1);
-                umma_tf32_ts(d1, a1 + 24, db + 6, idesc, 1);
+                umma_tf32_ts(d, a, db, idesc, kb != 0);
+                umma_tf32_ts(d, a + 8, db + 2, idesc, 1);
+                umma_tf32_ts(d, a + 16, db + 4, idesc, 1);
+                umma_tf32_ts(d, a + 24, db + 6, idesc, 1);
               }
-              if (p.use_nb && !NB200_DBG(p.debug, 128)) {  // + 1.0 * (hi + mid + lo pieces of |x|^2)
-                const uint64_t dbn = make_smem_desc(sb + (uint32_t)p.n_kb * TS_CHUNK);
-                umma_tf32(d0, d_ones, dbn, idesc, 1);
-                umma_tf32(d1, d_ones, dbn, idesc, 1);
-              }
+              if (p.use_nb && !NB200_DBG(p.debug, 128))  // + 1.0 * (hi + mid + lo pieces of |x|^2)
+                umma_tf32(d, d_ones, make_smem_desc(sb + (uint32_t)p.n_kb * TS_CHUNK), idesc, 1);
             }
-            tc_commit(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
-            tc_commit(&tfull_bar[b]);   // accumulators of this tile are complete
+            tc_commit(&empty_bar[s]);   // the stage may be refilled once both issuers' MMAs have read it
+            tc_commit(&tfull_bar[b]);   // this half's accumulators of the tile are complete
           }
           __syncwarp();
           if (++s == p.n_stage) {
@@ -1196,7 +1182,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       }
 #ifdef NB200_EXPERIMENTS
       NB_TACC(c_issue, tm);
-      if (p.counters && lane == 0) {
+      if (p.counters && lane == 0 && hh == 0) {
         atomicAdd(p.counters + 10, c_afull);
         atomicAdd(p.counters + 11, c_tempty);
         atomicAdd(p.counters + 12, c_full);
@@ -2134,7 +2120,7 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
 #define NB_TS(KPL, REG)                                                                                           \
   e = cudaFuncSetAttribute(tc_scan_ts_kernel<KPL, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
   if (e != cudaSuccess) return e;                                                                                 \
-  tc_scan_ts_kernel<KPL, REG><<<n_cta, TC_THREADS, smem, stream>>>(tmB, tmN, tmO, p);
+  tc_scan_ts_kernel<KPL, REG><<<n_cta, TS_THREADS, smem, stream>>>(tmB, tmN, tmO, p);
   static const bool no_reg = [] {
     const char* e2 = nb200_env("NB200_TC_NO_REG");
     return e2 && e2[0] == '1';

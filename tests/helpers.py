@@ -73,3 +73,16 @@ def recall(ids, exact_ids):
     for a, e in zip(np.asarray(ids), np.asarray(exact_ids)):
         hits += len(set(a[a >= 0].tolist()) & set(e[e >= 0].tolist()))
     return hits / float(np.sum(np.asarray(exact_ids) >= 0))
+
+
+def count_mismatches(ids, dists, counts, ref_ids, ref_dists, ref_counts, *, exact=False, atol=None):
+    """Number of queries on which assert_knn_matches would fail (bench.py's `parity` record)."""
+    bad = 0
+    for q in range(np.asarray(ref_ids).shape[0]):
+        try:
+            assert_knn_matches(np.asarray(ids)[q:q + 1], np.asarray(dists)[q:q + 1], np.asarray(counts).reshape(-1)[q:q + 1],
+                               np.asarray(ref_ids)[q:q + 1], np.asarray(ref_dists)[q:q + 1],
+                               np.asarray(ref_counts).reshape(-1)[q:q + 1], exact=exact, atol=atol)
+        except AssertionError:
+            bad += 1
+    return bad
