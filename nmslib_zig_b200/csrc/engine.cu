@@ -125,6 +125,8 @@ Engine::Engine(Space space, Method method, bool is_u8, int device)
 }
 
 Engine::~Engine() {
+  if (xch_) xch_destroy(xch_);
+  xch_ = nullptr;
   if (stream_ || d_db_.p) cudaSetDevice(device_);
   for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
                     &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
@@ -170,6 +172,7 @@ Status Engine::add_rows(const void* rows, size_t count, size_t elem_count, const
   }
   for (size_t i = 0; i < count; ++i) h_ids_.push_back(ids ? ids[i] : (int32_t)i);  // nmslib_c.cpp:768
   n_ += count;
+  ++data_gen_;
   data_dirty_ = true;
   rows_normalized_ = false;
   h_hnsw_rows_.clear();
@@ -204,6 +207,7 @@ void Engine::reset() {
   rows_normalized_ = false;
   h_hnsw_rows_.clear();
   d_q_dim_ = -1;  // the staged-query buffer is re-zeroed before its next use (stale padding columns)
+  ++data_gen_;
 }
 
 float Engine::host_distance(size_t a, size_t b) const {
@@ -704,12 +708,36 @@ Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d
   s = use_tc ? run_seq_tc(dq, nq, k, keys, stream) : run_seq_exact(dq, nq, k, keys, stream);
   if (!s.ok()) return s;
   if (dry_run_ && use_tc) return Status::OK();
+  if (sharded()) {
+    // row-sharded: publish this shard's sorted lists to the peers' view and merge all ranks' lists over NVLink peer
+    // memory (exchange.cu) -- the chunk merge of SeqSearch::Search (seqsearch.cc:151-175) with a GPU per chunk
+    const size_t q0 = std::min(slice_q0_, nq), q1 = std::min(slice_q1_, nq);
+    stats_.kernel_launches += 2;
+    s = xch_publish(xch_, keys, d_ids_.as<int32_t>(), pos_base_, nq, k, stream);
+    if (s.ok() && xch_hook_) s = xch_hook_(stream);
+    if (!s.ok()) return s;
+    return xch_merge(xch_, k, finalize_kind(), q0, q1 > q0 ? q1 - q0 : 0, d_keys, d_ids, d_dists, d_counts, stream);
+  }
   // sorted (distance, position) keys -> external ids + float distances (extract_knn_results, nmslib_c.cpp:293-328)
   s = check_cuda(launch_merge_topk(keys, nullptr, 1, 0, k, (int)nq, (int)k, finalize_kind(), d_ids_.as<int32_t>(),
                                    pos_base_, d_keys, d_ids, d_dists, d_counts, stream),
                  "finalize");
   ++stats_.kernel_launches;
   return s;
+}
+
+Status Engine::shard_export(size_t max_q, size_t max_k, void* blob256) {
+  if (method_ != METHOD_SEQ) return Status::Err(kErrIncompat, "only seq_search shards by rows (hnsw: replicas, SURVEY 8e)");
+  if (!device_available()) return Status::Err(kErrQuery, "no CUDA device available");
+  return xch_export(&xch_, device_, max_q, max_k, blob256);
+}
+Status Engine::shard_connect(int rank, int world, const void* blobs) {
+  if (!xch_) return Status::Err(kErrInvalid, "call nmslib_b200_shard_export first");
+  return xch_connect(xch_, rank, world, blobs);
+}
+void Engine::shard_disconnect() {
+  if (xch_) xch_destroy(xch_);
+  xch_ = nullptr;
 }
 
 // Exact scan on the CUDA cores (uint8 always; float spaces when the tensor-core answer of a query could
@@ -1071,6 +1099,40 @@ Status Engine::range_host(const void* query, size_t elem_count, double radius, s
   stats_.queries += 1;
   stats_.distance_evals += n_dev_;
   return Status::OK();
+}
+
+// ShardGroup worker: this rank's part of one batch.  Queries come from host memory (pinned when the group staged them),
+// the rows [q0, q1) this rank finalises go straight into the group's shared pinned result arrays.
+Status Engine::knn_host_slice(const void* queries, size_t nq, size_t elem_count, size_t k, size_t q0, size_t q1,
+                              int32_t* h_ids, float* h_dists, int32_t* h_counts) {
+  if (!built_) return Status::Err(kErrBuild, "Index not built");
+  Status s = prepare();
+  if (!s.ok()) return s;
+  if (n_dev_ == 0) return Status::Err(kErrQuery, "shard holds no data");
+  if (elem_count != (size_t)dim_)
+    return Status::Err(kErrQuery, "query length " + std::to_string(elem_count) + " != index dimension " + std::to_string(dim_));
+  if (k > (size_t)scan_exact_max_k())
+    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported yet");
+  const size_t out_n = nq * k;
+  if (!(s = check_cuda(d_out_ids_.ensure(out_n * 4), "cudaMalloc(out ids)")).ok()) return s;
+  if (!(s = check_cuda(d_out_dists_.ensure(out_n * 4), "cudaMalloc(out dists)")).ok()) return s;
+  if (!(s = check_cuda(d_out_counts_.ensure(nq * 4), "cudaMalloc(out counts)")).ok()) return s;
+  if (!(s = stage_queries_device(queries, false, nq, elem_count, stream_)).ok()) return s;
+  set_merge_slice(q0, q1);
+  s = run(d_q_.p, nq, k, d_out_ids_.as<int32_t>(), d_out_dists_.as<float>(), nullptr, d_out_counts_.as<int32_t>(), stream_);
+  if (!s.ok()) return s;
+  if (q1 > q0) {
+    const size_t cnt = q1 - q0;
+    if (!(s = check_cuda(cudaMemcpyAsync(h_ids + q0 * k, d_out_ids_.as<int32_t>() + q0 * k, cnt * k * 4, cudaMemcpyDeviceToHost, stream_), "D2H(ids)")).ok()) return s;
+    if (!(s = check_cuda(cudaMemcpyAsync(h_dists + q0 * k, d_out_dists_.as<float>() + q0 * k, cnt * k * 4, cudaMemcpyDeviceToHost, stream_), "D2H(dists)")).ok()) return s;
+    if (!(s = check_cuda(cudaMemcpyAsync(h_counts + q0, d_out_counts_.as<int32_t>() + q0, cnt * 4, cudaMemcpyDeviceToHost, stream_), "D2H(counts)")).ok()) return s;
+  }
+  s = check_cuda(cudaStreamSynchronize(stream_), "sharded query batch");
+  if (s.ok()) {
+    stats_.queries += nq;
+    stats_.distance_evals += (uint64_t)nq * n_dev_;
+  }
+  return s;
 }
 
 Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_t k, const int32_t** ids,

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -94,6 +95,21 @@ struct HnswBuildInfo {
 Status build_hnsw_device(const float* d_rows, size_t n, int dim, int row_words, int dist_func, const int32_t* ext_ids,
                          const HnswBuildParams& bp, int device, HnswGraph* out, HnswBuildInfo* info);
 
+// ---- cross-shard exchange over peer memory (exchange.cu) ----
+constexpr int kMaxShardWorld = 16;
+struct PeerExchange;
+Status xch_export(PeerExchange** out, int device, size_t max_q, size_t max_k, void* blob256);
+Status xch_connect(PeerExchange* x, int rank, int world, const void* blobs);
+void xch_destroy(PeerExchange* x);
+bool xch_connected(const PeerExchange* x);
+int xch_world(const PeerExchange* x);
+int xch_rank(const PeerExchange* x);
+Status xch_publish(PeerExchange* x, const uint64_t* local_keys, const int32_t* ext_ids, uint32_t pos_base, size_t nq, size_t k,
+                   cudaStream_t stream);
+Status xch_merge(PeerExchange* x, size_t k, int finalize, size_t q_begin, size_t q_count, uint64_t* out_keys,
+                 int32_t* out_ids, float* out_dists, int32_t* out_counts, cudaStream_t stream);
+bool xch_take_error(PeerExchange* x);
+
 struct Stats {
   uint64_t queries = 0, kernel_launches = 0, distance_evals = 0, hnsw_expansions = 0;
   double last_kernel_ms = 0, last_total_ms = 0, last_scan_ms = 0, scan_ms_sum = 0;
@@ -150,6 +166,22 @@ class Engine {
   // src_pitch: bytes between query rows (0 = dense rows of elem_count elements)
   Status knn_device(const void* d_queries, size_t nq, size_t elem_count, size_t k, int32_t* d_ids,
                     float* d_dists, uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream, size_t src_pitch = 0);
+
+  // ---- row-sharded search: this engine is rank `rank` of `world` (exchange.cu).  Once connected, every knn call
+  // returns the GLOBAL top-k (all ranks' lists merged); merge_slice restricts the finalised rows to [q0, q1) of the
+  // batch (a ShardGroup lets device g finalise slice g only).
+  Status shard_export(size_t max_q, size_t max_k, void* blob256);
+  Status shard_connect(int rank, int world, const void* blobs);
+  void shard_disconnect();
+  bool sharded() const { return xch_connected(xch_); }
+  void set_merge_slice(size_t q0, size_t q1) { slice_q0_ = q0; slice_q1_ = q1; }
+  // called between publish and merge with the engine's stream (ShardGroup: the devices of one process meet at a host
+  // barrier and order their streams with events, so no kernel of the group ever spins on a kernel not yet launched)
+  void set_exchange_hook(std::function<Status(cudaStream_t)> h) { xch_hook_ = std::move(h); }
+  // host in, host out for the rows [q0, q1) this rank finalises: h_* are [nq][k] / [nq] pinned arrays shared by a group
+  Status knn_host_slice(const void* queries, size_t nq, size_t elem_count, size_t k, size_t q0, size_t q1,
+                        int32_t* h_ids, float* h_dists, int32_t* h_counts);
+  uint64_t data_generation() const { return data_gen_; }
 
   Stats stats();  // also resolves the dominant-kernel event pair if it has completed
   int device() const { return device_; }
@@ -239,6 +271,10 @@ class Engine {
   DevBuf d_q_, d_qaux_, d_partial_, d_keys_, d_out_ids_, d_out_dists_, d_out_counts_;
   PinBuf h_out_ids_, h_out_dists_, h_out_counts_, h_q_;
   Stats stats_;
+  PeerExchange* xch_ = nullptr;
+  std::function<Status(cudaStream_t)> xch_hook_;
+  uint64_t data_gen_ = 0;
+  size_t slice_q0_ = 0, slice_q1_ = (size_t)-1;
   std::mutex mu_;
   int sm_count_ = 148;
 };

@@ -365,6 +365,64 @@ __device__ __forceinline__ void epi_process(const uint32_t (&v)[32], uint32_t po
   }
 }
 
+// ---- tile-at-a-time selection of the TS kernels -------------------------------------------------------------
+// The fast path of a tile must be ONE branch: ncu's source page of the round-1 epilogue showed the ~18 FMNMX3 of a
+// 32-column chunk surrounded by ~10 small branches (overflow ballot, tail-column mask, threshold refresh, group
+// tests), each with its branch-resolving / reconvergence stall -- ~350 clk per chunk for ~40 useful instructions.
+// Here a row's 64 values are reduced to their minimum first (group minima kept), and everything else -- refresh of
+// the shared threshold, masking of columns past the end of the shard, compaction, selection -- sits behind a single
+// warp-uniform test.
+__device__ __forceinline__ float group_min8(const float (&r)[32], int q) {
+  return min3(min3(r[8 * q], r[8 * q + 1], r[8 * q + 2]), min3(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
+              fminf(r[8 * q + 6], r[8 * q + 7]));
+}
+
+// Per-lane selection of one 32-column chunk whose group minima are g[0..3] (divergent: only lanes that hold a
+// survivor work).  About a third of all (warp, tile) pairs of config 2 have a survivor in SOME lane, so this path is
+// hot for the instruction cache and has to stay small: one copy of the insertion code per group of 8 values, walked
+// by a bit mask (two other shapes were measured and rejected: fully unrolled over the 64 registers -- 40 KB of code,
+// 2 x slower, stall_no_inst -- and a per-thread scratch array in local memory walked with dynamic indices -- 3 x
+// slower, the stores delay the next tile's tensor-memory drain).
+template <bool REG>
+__device__ __forceinline__ void epi_select(const float (&r)[32], const float (&g)[4], uint32_t pos0, uint64_t* buf, int& cnt,
+                                           float& thr, float (&tk)[TS_RK], uint32_t* gthr) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (g[q] < thr) {
+      unsigned mk = 0;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] < thr ? 1u : 0u) << jj;
+#pragma unroll 1
+      while (mk) {
+        const int jj = __ffs(mk) - 1;
+        mk &= mk - 1;
+        const float lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
+        const float hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
+        const float x = (jj & 4) ? hi4 : lo4;
+        if (!REG || x < thr) {  // (REG: the threshold may have moved since the mask was made)
+          buf[cnt] = ((uint64_t)__float_as_uint(x) << 32) | (uint64_t)(pos0 + 8 * q + jj);
+          ++cnt;
+          if constexpr (REG) {
+            // sorted insertion with every slot computed independently (depth 2 instead of a 16-step chain):
+            // new tk[i] = max(tk[i-1], min(tk[i], x)); x < thr <= tk[15], so the old tk[15] drops out
+            float prev = __int_as_float(0xFF800000);
+#pragma unroll
+            for (int i = 0; i < TS_RK; ++i) {
+              const float cur = tk[i];
+              tk[i] = fmaxf(prev, fminf(cur, x));
+              prev = cur;
+            }
+            if (tk[TS_RK - 1] < thr) {
+              thr = tk[TS_RK - 1];
+              atomicMin(gthr, f32_ordered(thr));  // (result unused: a fire-and-forget reduction)
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 struct TcParams {
   int n, nq, n_kb;
   int n_tiles;             // 128-row tiles per query block (whole shard)
@@ -1038,9 +1096,10 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + (size_t)p.n_stage * stage_bytes);
   uint64_t* full_bar = bars;                   // [n_stage] a whole tile has landed
   uint64_t* empty_bar = bars + p.n_stage;      // [n_stage] every MMA of the tile has read it
-  uint64_t* tfull_bar = bars + 2 * p.n_stage;  // [2] accumulators complete
-  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulators drained (8 warps)
-  uint64_t* afull_bar = tempty_bar + 2;        // [1] the piece's query rows are in tensor memory (256 threads)
+  uint64_t* tfull_bar = bars + 2 * p.n_stage;  // [2 buffers][2 halves] a half's accumulators of a tile are complete
+  uint64_t* tempty_bar = tfull_bar + 4;        // [2][2] ... drained (the 4 warps of that half): the halves run decoupled,
+                                               // a warp that is busy selecting only holds up its own half's issuer
+  uint64_t* afull_bar = tempty_bar + 4;        // [1] the piece's query rows are in tensor memory (256 threads)
   uint64_t* ones_bar = afull_bar + 1;          // [1]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ones_bar + 1);
 
@@ -1054,8 +1113,10 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       mbar_init(&empty_bar[s], 2);   // one commit from each MMA issuer
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tfull_bar[b], 2);   // one commit from each MMA issuer
-      mbar_init(&tempty_bar[b], 8);
+      for (int hh = 0; hh < 2; ++hh) {
+        mbar_init(&tfull_bar[b * 2 + hh], 1);
+        mbar_init(&tempty_bar[b * 2 + hh], 4);
+      }
     }
     mbar_init(afull_bar, 256);
     mbar_init(ones_bar, 1);
@@ -1149,7 +1210,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         for (int it = 0; it < n_iter; ++it, ++ti) {
           const int b = ti & 1;
           NB_TACC(c_issue, tm);
-          mbar_wait(&tempty_bar[b], ((ti >> 1) & 1) ^ 1);
+          mbar_wait(&tempty_bar[b * 2 + hh], ((ti >> 1) & 1) ^ 1);
           NB_TACC(c_tempty, tm);
           mbar_wait(&full_bar[s], ph);
           NB_TACC(c_full, tm);
@@ -1171,7 +1232,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
                 umma_tf32(d, d_ones, make_smem_desc(sb + (uint32_t)p.n_kb * TS_CHUNK), idesc, 1);
             }
             tc_commit(&empty_bar[s]);   // the stage may be refilled once both issuers' MMAs have read it
-            tc_commit(&tfull_bar[b]);   // this half's accumulators of the tile are complete
+            tc_commit(&tfull_bar[b * 2 + hh]);   // this half's accumulators of the tile are complete
           }
           __syncwarp();
           if (++s == p.n_stage) {
@@ -1247,7 +1308,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       auto drain = [&](uint32_t (&v0)[32], uint32_t (&v1)[32]) {
         const int b = ti & 1;
         NB_TACC(c_proc, te);
-        mbar_wait(&tfull_bar[b], (ti >> 1) & 1);
+        mbar_wait(&tfull_bar[b * 2 + h], (ti >> 1) & 1);
         NB_TACC(c_twait, te);
         tc_fence_after();
         const uint32_t tcol = trow + (uint32_t)(TS_ACC0 + (b * 2 + h) * TS_BN);
@@ -1256,7 +1317,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[b]);
+        if (lane == 0) mbar_arrive(&tempty_bar[b * 2 + h]);
         ++ti;
         NB_TACC(c_drain, te);
       };
@@ -1280,6 +1341,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         for (int j = 1; j < 32; ++j) t = fmaxf(t, gm[j]);
         if (row_valid && !NB200_DBG(p.debug, 1)) thr = publish_thr(gthr, f32_ordered(t));
       }
+      const int guard = REG ? p.cap - TS_BN - 1 : p.hwm;  // a row above this many keys sends its warp to the slow path
       for (int tile = t_begin; tile < t_end; ++tile) {
         uint32_t v0[32], v1[32];
         drain(v0, v1);
@@ -1287,18 +1349,61 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
           if (__uint_as_float(v0[0]) == 1.2345e-30f || __uint_as_float(v1[0]) == 1.2345e-30f) thr = 0.f;
           continue;
         }
+        float r0[32], r1[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          r0[j] = __uint_as_float(v0[j]);
+          r1[j] = __uint_as_float(v1[j]);
+        }
+        float g0[4], g1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          g0[q] = group_min8(r0, q);
+          g1[q] = group_min8(r1, q);
+        }
+        const float m = fminf(min3(g0[0], g0[1], g0[2]), min3(g0[3], g1[0], g1[1]));
+        const float mm = min3(m, g1[2], g1[3]);
+        const int vtile = p.n - tile * TS_BN;
+        // warp-uniform reasons to leave the fast path: threshold refresh (every refresh_mask + 1 tiles), the shard's
+        // last, partial tile; per-lane reasons: a value below the row's threshold, a buffer close to its limit
+        const bool uni = (((tile - t_begin) & p.refresh_mask) == 0) | (vtile < TS_BN) | (NB200_DBG(p.debug, 64) != 0);
+        const bool mine = (mm < thr) | (cnt > guard);
+        if (!uni && !__any_sync(FULL, mine)) continue;
+        // ------------------------------------------------------------------ slow path
         // what the other pieces of this query have found in the meantime (fminf ignores the NaN of "nothing yet")
         if (((tile - t_begin) & p.refresh_mask) == 0 && row_valid) thr = fminf(thr, f32_from_ordered(*gthr));
-        if (NB200_DBG(p.debug, 64)) thr = __int_as_float(0xFF800000);  // timing experiment: fast path only, nothing passes
+        if (NB200_DBG(p.debug, 64)) thr = __int_as_float(0xFF800000);  // timing experiment: nothing passes
+        if (vtile < TS_BN) {  // rows past the end of the shard: never candidates
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j >= vtile) r0[j] = __int_as_float(0x7F800000);
+            if (j + 32 >= vtile) r1[j] = __int_as_float(0x7F800000);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            g0[q] = group_min8(r0, q);
+            g1[q] = group_min8(r1, q);
+          }
+        }
+        unsigned need = __ballot_sync(FULL, cnt > p.cap - TS_BN - 1);
+        while (need) {  // about to overflow: compact at once (!REG: normally the deferred path keeps rows far from here)
+          ++ctr[2];
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const float keep = thr;
+          compact_lane<KPL>(src, buf, cnt, thr, p.kprime, p.slack, gthr, lane);
+          if (REG) thr = fminf(thr, keep);  // (the cut is never below the 16th best, the list stays authoritative)
+        }
+        ++ctr[1];
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TS_BN);
-        const int vtile = p.n - tile * TS_BN;
-        epi_process<KPL, REG>(v0, pos_tile, vtile, buf, cnt, thr, tk, p.cap, p.kprime, p.slack, gthr, lane, ctr);
-        epi_process<KPL, REG>(v1, pos_tile + 32, vtile - 32, buf, cnt, thr, tk, p.cap, p.kprime, p.slack, gthr, lane,
-                              ctr);
+        if (mm < thr || vtile < TS_BN) {
+          epi_select<REG>(r0, g0, pos_tile, buf, cnt, thr, tk, gthr);
+          epi_select<REG>(r1, g1, pos_tile + 32, buf, cnt, thr, tk, gthr);
+        }
         if constexpr (REG) continue;
         // deferred compaction: a row past the high-water mark is compacted here, at most one row per warp and
         // tile, so the bursts (all rows of a warp fill at the same rate) are spread over the slack that every
-        // tile leaves; only a row that is about to overflow is compacted at once (epi_process)
+        // tile leaves; only a row that is about to overflow is compacted at once (above)
         const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);
         if (pend) {
           ++ctr[3];
@@ -1921,7 +2026,7 @@ cudaError_t launch_tc_scan_pair(const float* qa, size_t q_pad, const float* dbB,
   const int budget = 214 * 1024;
   p.n_stage = (budget - ones_bytes) / stage_bytes;
   if (p.n_stage > 8) p.n_stage = 8;
-  const size_t smem = 1024 + (size_t)ones_bytes + (size_t)p.n_stage * stage_bytes + (2 * 8 + 8) * 8 + 16;
+  const size_t smem = 1024 + (size_t)ones_bytes + (size_t)p.n_stage * stage_bytes + (2 * 8 + 12) * 8 + 16;
   cudaError_t e;
 #define NB_TP(KPL)                                                                                            \
   e = cudaFuncSetAttribute(tc_scan_pair_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -2115,7 +2220,7 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   p.n_stage = (budget - ones_bytes) / stage_bytes;
   if (p.n_stage > 8) p.n_stage = 8;
   if (p.n_stage < 2) return cudaErrorInvalidValue;
-  const size_t smem = 1024 + (size_t)ones_bytes + (size_t)p.n_stage * stage_bytes + (2 * 8 + 8) * 8 + 16;
+  const size_t smem = 1024 + (size_t)ones_bytes + (size_t)p.n_stage * stage_bytes + (2 * 8 + 12) * 8 + 16;
   cudaError_t e;
 #define NB_TS(KPL, REG)                                                                                           \
   e = cudaFuncSetAttribute(tc_scan_ts_kernel<KPL, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
