@@ -280,6 +280,7 @@ typedef struct {
   uint64_t build_batches;    /* insertion batches over all levels */
   uint64_t build_prunes;     /* neighbour lists re-pruned because they overflowed */
   uint64_t split_queries;    /* queries re-run by the 3xTF32 (split operand) scan after a failed certificate */
+  uint64_t u8_imma;          /* 1: uint8 rows are scanned on the integer tensor pipe (tcgen05.mma.kind::i8), 0: widened to TF32 */
 } nmslib_b200_stats_t;
 nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_stats_t* out);
 
@@ -295,6 +296,28 @@ size_t nmslib_b200_scan_plan(size_t query_count, size_t n, size_t k, int sm_coun
  * pairs, tiles are 256 rows, every piece fills two candidate lists (*s_max counts lists). */
 size_t nmslib_b200_scan_plan_pairs(size_t query_count, size_t n, size_t k, int sm_count, int32_t* pieces,
                                    size_t capacity, int* n_pairs, int* s_max);
+
+/* ---- row-sharded multi-GPU search behind this ABI (the reference's chunk-and-merge, seqsearch.cc:151-175,
+ * with a GPU per chunk).  seq_search / brute_force only; an hnsw graph does not shard without changing its answers.
+ *
+ * (A) ONE process, several devices: pass the index parameter  b200_devices=0,1,2,3  ("0-7", "all") to
+ *     nmslib_create_index.  nmslib_add_data_point* and nmslib_knn_query_batch / _fill are used unchanged: the rows are
+ *     cut into contiguous shards at the first query, every batch is scanned by all devices concurrently, the per-shard
+ *     (distance, global position) lists are exchanged through NVLink peer memory and merged on the devices.  Answers
+ *     are bit-identical to the one-device index.
+ *
+ * (B) one process PER device (torchrun, MPI): every rank creates an ordinary index over its row shard
+ *     (nmslib_b200_set_shard(first global row)), then
+ *         nmslib_b200_shard_export(index, max_queries, max_k, blob)     allocates this rank's exchange window
+ *         ... the caller all-gathers the NMSLIB_B200_SHARD_BLOB_BYTES-byte blobs over any host channel ...
+ *         nmslib_b200_shard_connect(index, rank, world, blobs)          maps the peers' windows (CUDA IPC)
+ *     after which nmslib_knn_query_batch and nmslib_b200_knn_device return the GLOBAL top-k on every rank: the call
+ *     publishes this shard's lists, waits (on the device) for the peers' lists of the same call and merges them.  Like
+ *     a collective, every rank must make the same sequence of calls (same query_count and k). */
+#define NMSLIB_B200_SHARD_BLOB_BYTES 256
+nmslib_error_t nmslib_b200_shard_export(nmslib_index_handle_t index, size_t max_queries, size_t max_k, void* blob);
+nmslib_error_t nmslib_b200_shard_connect(nmslib_index_handle_t index, int rank, int world, const void* blobs);
+nmslib_error_t nmslib_b200_shard_disconnect(nmslib_index_handle_t index);
 
 /* Process-wide variant selectors (every variant returns the same answers; used for A/B comparisons):
  *   "tc_pair"     1 (default) rows of more than 128 floats on CTA pairs / 0 the single-CTA long-row kernel

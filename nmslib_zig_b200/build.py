@@ -23,7 +23,7 @@ LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libnmslib_b200.so"
 STAMP = LIBDIR / ".build_stamp"
 
-SOURCES = ["scan_exact.cu", "scan_tc.cu", "topk_merge.cu", "range_scan.cu", "hnsw_search.cu", "hnsw_build_gpu.cu", "exchange.cu", "engine.cu", "hnsw_format.cpp", "hnsw_build.cpp",
+SOURCES = ["scan_exact.cu", "scan_tc.cu", "topk_merge.cu", "range_scan.cu", "hnsw_search.cu", "hnsw_build_gpu.cu", "exchange.cu", "shard_group.cu", "engine.cu", "hnsw_format.cpp", "hnsw_build.cpp",
            "c_abi.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

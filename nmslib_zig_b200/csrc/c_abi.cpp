@@ -14,6 +14,7 @@
 
 #include "../../include/nmslib_b200.h"
 #include "engine.h"
+#include "shard_group.h"
 
 using nb200::Engine;
 using nb200::Status;
@@ -81,7 +82,8 @@ bool parse_space(const std::string& s, nb200::Space* out) {
 // from the caller's allocator.
 struct nmslib_index_t {
   nmslib_index_header_t header;
-  Engine* engine;
+  Engine* engine;             // the index itself; with a shard group: the host store of the rows
+  nb200::ShardGroup* group;   // index parameter b200_devices: row shards on several GPUs of this process
   std::string method;
   std::string space_type;
   nmslib_allocator_t allocator;
@@ -127,6 +129,7 @@ nmslib_error_t new_index(const std::string& space, const std::string& method, nm
   if (m == nb200::METHOD_HNSW && (sp == nb200::SPACE_L1 || sp == nb200::SPACE_LINF || sp == nb200::SPACE_ANGULAR))
     idx->method_served = false;
   idx->engine = new Engine(sp, m, u8, nb200::default_device());
+  idx->group = nullptr;
   *out = idx;
   return NB_OK("Index created");
 }
@@ -150,6 +153,7 @@ nmslib_error_t nmslib_index_create(const char* space, nmslib_params_handle_t /*s
 void nmslib_index_destroy(nmslib_index_handle_t handle) {
   if (!handle) return;
   nmslib_allocator_t a = handle->allocator;
+  delete handle->group;
   delete handle->engine;
   handle->~nmslib_index_t();
   a.free(handle, a.ctx);
@@ -164,7 +168,8 @@ nmslib_error_t nmslib_create_index(nmslib_index_handle_t index, nmslib_params_ha
           return NB_ERR(NMSLIB_ERROR_INDEX_BUILD_FAILED,
                         "method '" + index->method + "' is not served by the B200 engine (seq_search, brute_force, hnsw)");
         // AnyParamManager::CheckUnused throws on unknown names (params.h:241-251) -> error 8
-        static const char* seq_names[] = {"copyMem", "multiThread", "threadQty"};  // seqsearch.cc:63-68
+        static const char* seq_names[] = {"copyMem", "multiThread", "threadQty",  // seqsearch.cc:63-68
+                                          "b200_devices"};  // + row shards over several GPUs (extension)
         static const char* hnsw_names[] = {"M", "efConstruction", "maxM", "maxM0", "mult", "delaunay_type", "post",
                                            "indexThreadQty", "skip_optimized_index", "searchMethod",
                                            "b200_build"};  // hnsw.cc:189-208 + where to build (extension)
@@ -180,7 +185,24 @@ nmslib_error_t nmslib_create_index(nmslib_index_handle_t index, nmslib_params_ha
             return NB_ERR(NMSLIB_ERROR_INDEX_BUILD_FAILED, "Failed to create index: unknown parameter '" + name + "'");
         }
         std::lock_guard<std::mutex> lock(index->engine->mutex());
-        index->engine->mark_built(params_of(index_params));
+        std::vector<std::string> kept;
+        std::string devices;
+        for (const std::string& p : params_of(index_params)) {
+          if (p.compare(0, 13, "b200_devices=") == 0) devices = p.substr(13);
+          else kept.push_back(p);
+        }
+        delete index->group;
+        index->group = nullptr;
+        if (!devices.empty()) {
+          std::vector<int> devs;
+          Status ds = nb200::ShardGroup::parse_devices(devices, &devs);
+          if (!ds.ok()) return NB_ERR(NMSLIB_ERROR_INDEX_BUILD_FAILED, "Failed to create index: " + ds.msg);
+          if (devs.size() > 1) {
+            index->group = new nb200::ShardGroup(index->engine->space(), index->engine->is_u8(), devs);
+            index->group->set_index_params(kept);
+          }
+        }
+        index->engine->mark_built(kept);
         return NB_OK("Index created successfully");
       },
       NMSLIB_ERROR_INDEX_BUILD_FAILED, "Failed to create index");
@@ -197,6 +219,15 @@ nmslib_error_t nmslib_reset_index(nmslib_index_handle_t index) {
 // Here: "make sure the device copy exists"; failures surface at the query call.
 void nmslib_initialize_pool(nmslib_index_handle_t index) {
   if (!index || !index->engine->built()) return;
+  if (index->group) {  // shards are cut (and uploaded) here, like the single-device copy below
+    try {
+      std::lock_guard<std::mutex> lock(index->engine->mutex());
+      Status s = index->group->prepare(index->engine, 1, 1);
+      if (!s.ok()) NB_STATUS(s);
+    } catch (...) {
+    }
+    return;
+  }
   try {
     std::lock_guard<std::mutex> lock(index->engine->mutex());
     Status s = index->engine->prepare();
@@ -424,7 +455,8 @@ nmslib_error_t nmslib_knn_query_batch(nmslib_index_handle_t index, const void* q
         std::lock_guard<std::mutex> lock(e->mutex());
         const int32_t *ids, *counts;
         const float* dists;
-        Status s = e->knn_host(queries, query_count, elem_count, k, &ids, &dists, &counts);
+        Status s = index->group ? index->group->knn_host(e, queries, query_count, elem_count, k, &ids, &dists, &counts)
+                                : e->knn_host(queries, query_count, elem_count, k, &ids, &dists, &counts);
         if (!s.ok()) {
           for (size_t i = 0; i < query_count; ++i) results[i].size = 0;
           return NB_STATUS(s);
@@ -719,7 +751,7 @@ nmslib_error_t nmslib_b200_prepare(nmslib_index_handle_t index) {
   return guarded(
       [&]() -> nmslib_error_t {
         std::lock_guard<std::mutex> lock(index->engine->mutex());
-        Status s = index->engine->prepare();
+        Status s = index->group ? index->group->prepare(index->engine, 1, 1) : index->engine->prepare();
         if (!s.ok()) return NB_STATUS(s);
         return NB_OK("Device copy ready");
       },
@@ -731,6 +763,8 @@ nmslib_error_t nmslib_b200_knn_device(nmslib_index_handle_t index, const void* d
                                       uint64_t* d_keys, void* stream) {
   if (!index || !d_queries || query_count == 0 || elem_count == 0 || k == 0)
     return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid device knn inputs");
+  if (index->group)
+    return NB_ERR(NMSLIB_ERROR_SPACE_INCOMPATIBLE, "device-resident queries address one device: not available on a b200_devices index");
   return guarded(
       [&]() -> nmslib_error_t {
         std::lock_guard<std::mutex> lock(index->engine->mutex());
@@ -762,7 +796,7 @@ nmslib_error_t nmslib_b200_merge_topk(nmslib_index_handle_t index, const uint64_
 nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_stats_t* out) {
   if (!index || !out) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid stats request");
   std::lock_guard<std::mutex> lock(index->engine->mutex());
-  const nb200::Stats s = index->engine->stats();
+  const nb200::Stats s = index->group ? index->group->stats() : index->engine->stats();
   out->queries = s.queries;
   out->kernel_launches = s.kernel_launches;
   out->distance_evals = s.distance_evals;
@@ -782,6 +816,8 @@ nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_st
   out->build_batches = (uint64_t)bi.batches;
   out->build_prunes = bi.prunes;
   out->split_queries = s.split_queries;
+  out->u8_imma = (!index->group && index->engine->is_u8() && index->engine->method() == nb200::METHOD_SEQ &&
+                  index->engine->u8_imma()) ? 1 : 0;
   return NMSLIB_SUCCESS;
 }
 
@@ -821,6 +857,38 @@ static size_t scan_plan_impl(size_t query_count, size_t n, size_t k, int units, 
       ++out;
     }
   return out;
+}
+
+nmslib_error_t nmslib_b200_shard_export(nmslib_index_handle_t index, size_t max_queries, size_t max_k, void* blob) {
+  if (!index || !blob || max_queries == 0 || max_k == 0) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid shard export inputs");
+  if (index->group) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "a b200_devices index manages its own shards");
+  return guarded(
+      [&]() -> nmslib_error_t {
+        std::lock_guard<std::mutex> lock(index->engine->mutex());
+        Status s = index->engine->shard_export(max_queries, max_k, blob);
+        if (!s.ok()) return NB_STATUS(s);
+        return NB_OK("Exchange window exported");
+      },
+      NMSLIB_ERROR_RUNTIME, "Failed to export the exchange window");
+}
+
+nmslib_error_t nmslib_b200_shard_connect(nmslib_index_handle_t index, int rank, int world, const void* blobs) {
+  if (!index || !blobs) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid shard connect inputs");
+  return guarded(
+      [&]() -> nmslib_error_t {
+        std::lock_guard<std::mutex> lock(index->engine->mutex());
+        Status s = index->engine->shard_connect(rank, world, blobs);
+        if (!s.ok()) return NB_STATUS(s);
+        return NB_OK("Shard exchange connected");
+      },
+      NMSLIB_ERROR_RUNTIME, "Failed to connect the shard exchange");
+}
+
+nmslib_error_t nmslib_b200_shard_disconnect(nmslib_index_handle_t index) {
+  if (!index) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid index");
+  std::lock_guard<std::mutex> lock(index->engine->mutex());
+  index->engine->shard_disconnect();
+  return NB_OK("Shard exchange closed");
 }
 
 nmslib_error_t nmslib_b200_set_option(const char* name, int value) {

@@ -121,6 +121,7 @@ void PinBuf::release() {
 Engine::Engine(Space space, Method method, bool is_u8, int device)
     : space_(space), method_(method), is_u8_(is_u8), device_(device) {
   force_exact_ = nb200_option("force_exact", 0) != 0;  // A/B switch: CUDA-core exact scan only
+  u8_imma_ = is_u8 && method == METHOD_SEQ && !force_exact_ && nb200_option("u8_imma", 1) != 0;
   if (const char* e = nb200_env("NB200_TC_MARGIN")) tc_margin_ = std::max(1, atoi(e));
 }
 
@@ -134,7 +135,11 @@ Engine::~Engine() {
                     &d_tc_keys_, &d_cert_, &d_plan_, &d_gthr_, &d_u8tmp_, &d_range_, &d_fb_idx_, &d_fb_q_, &d_fb_keys_, &d_nblock_, &d_ones_,
                     &d_db_split_, &d_q_split_, &d_sp_idx_, &d_sp_q_, &d_sp_keys_})
     b->release();
-  for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_}) b->release();
+  d_fb_cnt_.release();
+  d_digits_.release();
+  for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_, &h_fb_cnt_}) b->release();
+  for (auto& e : fb_ev_)
+    if (e) cudaEventDestroy(e);
   for (auto& e : ev_)
     if (e) cudaEventDestroy(e);
   for (auto& pr : scan_ev_)
@@ -340,6 +345,7 @@ void Engine::scan_end(cudaStream_t s) {
 }
 
 Stats Engine::stats() {
+  absorb_async_counts(false);
   for (int i = 0; i < kScanRing; ++i) {
     if (!scan_pending_[i] || cudaEventQuery(scan_ev_[i][1]) != cudaSuccess) continue;
     float ms = 0;
@@ -385,7 +391,7 @@ const float* Engine::hnsw_host_rows() {
 
 int Engine::finalize_kind() const {
   if (method_ == METHOD_HNSW) return FIN_FLOAT;  // squared / cosine / negdot / (uint8: exact integers held in fp32)
-  if (dev_u8_rows()) return FIN_INT;  // (widened uint8 rows carry fp32 keys: exact integers as floats)
+  if (is_u8_) return FIN_INT;  // every uint8 path ends in i32_ordered(int distance) keys (re-rank, dp4a scan)
   // l2 + seq_search reports the root; l2 + hnsw reports the squared distance
   if (space_ == SPACE_L2 && method_ == METHOD_SEQ) return FIN_SQRT;
   return FIN_FLOAT;
@@ -475,6 +481,25 @@ Status Engine::upload_data() {
     s = check_cuda(launch_row_aux(dev_u8, d_db_.p, (int)n_, row_words_, d_aux_.p, stream_), "row_aux");
     if (!s.ok()) return s;
     ++stats_.kernel_launches;
+  }
+  if (dev_u8 && u8_imma_) {
+    // integer tensor pipe: M = ceil(max |x|^2 / 2) and the rows' norm digits (scan_tc.cu); rows whose norms do not fit
+    // the digit block send the whole index back to the widened TF32 path
+    if (!(s = check_cuda(d_flags_.ensure(16), "cudaMalloc(flags)")).ok()) return s;
+    if (!(s = check_cuda(launch_u8_max_norm(d_aux_.as<int>(), (int)n_, d_flags_.as<int>() + 3, stream_), "u8_max_norm")).ok()) return s;
+    int max_norm2 = 0;
+    if (!(s = check_cuda(cudaMemcpyAsync(&max_norm2, d_flags_.as<int>() + 3, 4, cudaMemcpyDeviceToHost, stream_), "D2H(max norm)")).ok()) return s;
+    if (!(s = check_cuda(cudaStreamSynchronize(stream_), "upload sync")).ok()) return s;
+    stats_.kernel_launches += 1;
+    if (max_norm2 > u8_imma_max_norm2()) {
+      u8_imma_ = false;
+      return upload_data();
+    }
+    u8_m_half_ = (max_norm2 + 1) / 2;
+    if (!(s = check_cuda(d_digits_.ensure(n_pad * 32), "cudaMalloc(norm digits)")).ok()) return s;
+    s = check_cuda(launch_u8_norm_digits(d_aux_.as<int>(), (int)n_, (int)n_pad, u8_m_half_, d_digits_.as<uint8_t>(), stream_), "u8_norm_digits");
+    if (!s.ok()) return s;
+    stats_.kernel_launches += 1;
   }
   x_max_ = 0.f;
   tc_split_ = false;
@@ -664,7 +689,7 @@ Status Engine::stage_queries_device(const void* src, bool src_on_device, size_t 
 }
 
 Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d_dists, uint64_t* d_keys,
-                   int32_t* d_counts, cudaStream_t stream) {
+                   int32_t* d_counts, cudaStream_t stream, bool async) {
   Status s;
   if (method_ == METHOD_HNSW) {
     HnswDeviceGraph g;
@@ -703,9 +728,9 @@ Status Engine::run(const void* dq, size_t nq, size_t k, int32_t* d_ids, float* d
   // ---- sequential search ----
   if (!(s = check_cuda(d_tc_keys_.ensure(nq * k * 8), "cudaMalloc(keys)")).ok()) return s;
   uint64_t* keys = d_tc_keys_.as<uint64_t>();
-  const bool use_tc = !dev_u8_rows() && !force_exact_ && k <= (size_t)tc_max_k() && space_ != SPACE_L1 &&
-                      space_ != SPACE_LINF;  // (no dot-product form: exact CUDA-core scan)
-  s = use_tc ? run_seq_tc(dq, nq, k, keys, stream) : run_seq_exact(dq, nq, k, keys, stream);
+  const bool use_tc = ((!dev_u8_rows() && space_ != SPACE_L1 && space_ != SPACE_LINF) || u8_imma_) && !force_exact_ &&
+                      k <= (size_t)tc_max_k();  // (l1 / linf have no dot-product form: exact CUDA-core scan)
+  s = use_tc ? run_seq_tc(dq, nq, k, keys, stream, true, async) : run_seq_exact(dq, nq, k, keys, stream);
   if (!s.ok()) return s;
   if (dry_run_ && use_tc) return Status::OK();
   if (sharded()) {
@@ -742,7 +767,8 @@ void Engine::shard_disconnect() {
 
 // Exact scan on the CUDA cores (uint8 always; float spaces when the tensor-core answer of a query could
 // not be certified, or when NB200_FORCE_EXACT is set).  Writes the k best keys per query.
-Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream) {
+Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream,
+                             const int* d_nq) {
   Status s;
   const int bq = scan_exact_block_queries(), bn = scan_exact_block_points();
   const int n_tiles = (int)((n_dev_ + bn - 1) / bn);
@@ -769,7 +795,7 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
   if (mode == SCAN_COSINE || mode == SCAN_ANGULAR || mode == SCAN_SIFT) {
     s = check_cuda(d_qaux_.ensure(round_up(nq, bq) * 4), "cudaMalloc(qaux)");
     if (!s.ok()) return s;
-    s = check_cuda(launch_row_aux(dev_u8_rows(), dq, (int)nq, row_words_, d_qaux_.p, stream), "query_aux");
+    s = check_cuda(launch_row_aux(dev_u8_rows(), dq, (int)nq, row_words_, d_qaux_.p, stream, d_nq), "query_aux");
     if (!s.ok()) return s;
     q_aux = d_qaux_.p;
     ++stats_.kernel_launches;
@@ -779,12 +805,12 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
   const bool dominant = force_exact_ || space_ == SPACE_L1 || space_ == SPACE_LINF;
   if (dominant) scan_begin(stream);
   s = check_cuda(launch_scan_exact(mode, d_db_.p, dq, d_aux_.p, q_aux, (int)n_dev_, (int)nq, row_words_, (int)k,
-                                   pos_base_, d_partial_.as<uint64_t>(), n_split, tiles_per_split, stream),
+                                   pos_base_, d_partial_.as<uint64_t>(), n_split, tiles_per_split, stream, d_nq),
                  "scan_exact");
   if (dominant) scan_end(stream);
   if (!s.ok()) return s;
   s = check_cuda(launch_merge_topk(d_partial_.as<uint64_t>(), nullptr, n_split, k, (size_t)n_split * k, (int)nq,
-                                   (int)k, FIN_FLOAT, nullptr, pos_base_, out_keys, nullptr, nullptr, nullptr, stream),
+                                   (int)k, FIN_FLOAT, nullptr, pos_base_, out_keys, nullptr, nullptr, nullptr, stream, d_nq),
                  "merge_topk");
   stats_.kernel_launches += 2;
   return s;
@@ -818,8 +844,15 @@ Status Engine::enable_split(cudaStream_t stream) {
 }
 
 Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream,
-                          bool allow_split_retry) {
+                          bool allow_split_retry, bool async) {
   Status s;
+  absorb_async_counts(false);  // what earlier device-resident batches reported in the meantime (may enable split mode)
+  const bool dev_fb = async && !approx_ok_ && !dry_run_;
+  if (dev_fb) {
+    if (!(s = check_cuda(d_fb_cnt_.ensure(16), "cudaMalloc(fb count)")).ok()) return s;
+    if (!(s = check_cuda(d_fb_idx_.ensure(nq * 4), "cudaMalloc(fb idx)")).ok()) return s;
+    if (!(s = check_cuda(cudaMemsetAsync(d_fb_cnt_.p, 0, 4, stream), "memset(fb count)")).ok()) return s;
+  }
   const bool split = tc_split_;
   const int rw = split ? 3 * row_words_ : row_words_;  // operand row length the scan kernels see
   const int mode = (space_ == SPACE_COSINE || space_ == SPACE_ANGULAR) ? SCAN_COSINE
@@ -884,7 +917,17 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   // which at k = 100 spans tens of ranks: start with half of k there (the margin doubles when certificates fail)
   // (approx_ok_: graph construction takes the tensor-core ranking as it is -- small margin, no error band in the re-rank)
   const int kprime_req = (int)k + (db_inexact_ && !approx_ok_ && !split ? std::max(tc_margin_, (int)k / 2) : tc_margin_);
-  if (ts) {
+  if (u8_imma_) {  // uint8 rows on the integer tensor pipe: byte queries / rows / norm digits, the TS piece table
+    scan_begin(stream);
+    s = check_cuda(launch_tc_scan_u8(static_cast<const uint8_t*>(dq), d_db_.as<uint8_t>(), d_digits_.as<uint8_t>(), n_pad,
+                                     (int)n_dev_, (int)nq, (int)k, kprime_req, u8_m_half_, pos_base_, n_cta, s_max,
+                                     d_plan_.as<int>(), d_cand_.as<uint64_t>(), d_cand_cnt_.as<int>(), d_cand_thr_.as<float>(),
+                                     d_gthr_.as<uint32_t>(), stream),
+                   "tc_scan_u8");
+    scan_end(stream);
+    if (!s.ok()) return s;
+    stats_.kernel_launches += 1;
+  } else if (ts) {
     scan_begin(stream);
     s = check_cuda(launch_tc_scan_ts(split ? d_q_split_.as<float>() : static_cast<const float*>(dq), dbB, n_pad,
                                      mode == SCAN_L2 ? d_nblock_.as<float>() : nullptr, d_ones_.as<float>(),
@@ -945,13 +988,48 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
                                         // split operands: accumulation error + the dropped q_lo.x_lo / re-truncated terms
                                         split ? (float)row_words_ * 2.384185791015625e-07f * 1.01f +
                                                     3.0f * 9.5367431640625e-07f + 1e-6f
-                                              : 0.f),
+                                              : 0.f,
+                                        dev_fb ? d_fb_cnt_.as<int>() : nullptr, dev_fb ? d_fb_idx_.as<int>() : nullptr,
+                                        u8_imma_ ? d_db_.as<uint8_t>() : nullptr, u8_imma_ ? static_cast<const uint8_t*>(dq) : nullptr,
+                                        u8_imma_ ? 1.0f : 0.f, is_u8_ ? 1 : 0),
                        "tc_rerank");
         if (!s.ok()) return s;
         ++stats_.kernel_launches;
       }
       b0 = b1;
     }
+  }
+  if (dev_fb) {
+    // Device-predicated exact re-run of the (normally empty) set of uncertified queries: gather -> exact scan ->
+    // merge -> scatter are launched for the worst case (all nq) and leave at once past the count the re-rank left
+    // on the device.  Nothing here waits for the host, so a caller's steps queue back to back.
+    const int* d_cnt = d_fb_cnt_.as<int>();
+    const size_t fb_pad = round_up(nq, (size_t)scan_exact_block_queries());
+    if (!(s = check_cuda(d_fb_q_.ensure(fb_pad * (size_t)row_words_ * 4), "cudaMalloc(fb q)")).ok()) return s;
+    if (!(s = check_cuda(d_fb_keys_.ensure(nq * k * 8), "cudaMalloc(fb keys)")).ok()) return s;
+    s = check_cuda(launch_gather_rows(static_cast<const uint32_t*>(dq), d_fb_idx_.as<int>(), (int)nq, row_words_,
+                                      d_fb_q_.as<uint32_t>(), stream, d_cnt, scan_exact_block_queries()),
+                   "gather");
+    if (!s.ok()) return s;
+    if (!(s = run_seq_exact(d_fb_q_.p, nq, k, d_fb_keys_.as<uint64_t>(), stream, d_cnt)).ok()) return s;
+    s = check_cuda(launch_scatter_keys(d_fb_keys_.as<uint64_t>(), d_fb_idx_.as<int>(), (int)nq, (int)k, out_keys, stream,
+                                       d_cnt, u8_widened() ? 1 : 0),
+                   "scatter");
+    if (!s.ok()) return s;
+    stats_.kernel_launches += 2;
+    // the count, for the statistics and for the adaptation of later batches
+    if (!(s = check_cuda(h_fb_cnt_.ensure(kFbRing * 4), "cudaMallocHost(fb count)")).ok()) return s;
+    const int slot = fb_head_;
+    if (fb_pending_[slot]) absorb_async_counts(true);  // (ring full: that copy is kFbRing calls old)
+    fb_head_ = (fb_head_ + 1) % kFbRing;
+    if (!fb_ev_[slot] && !(s = check_cuda(cudaEventCreateWithFlags(&fb_ev_[slot], cudaEventDisableTiming), "cudaEventCreate")).ok())
+      return s;
+    s = check_cuda(cudaMemcpyAsync(h_fb_cnt_.as<int>() + slot, d_fb_cnt_.p, 4, cudaMemcpyDeviceToHost, stream), "D2H(fb count)");
+    if (!s.ok()) return s;
+    if (!(s = check_cuda(cudaEventRecord(fb_ev_[slot], stream), "cudaEventRecord")).ok()) return s;
+    fb_nq_[slot] = nq;
+    fb_pending_[slot] = true;
+    return Status::OK();
   }
   // certificates back to the host; re-run the (normally empty) set of uncertified queries exactly
   s = check_cuda(cudaMemcpyAsync(h_cert_.p, d_cert_.p, nq * 4, cudaMemcpyDeviceToHost, stream), "D2H(cert)");
@@ -1010,12 +1088,31 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
   s = run_seq_exact(d_fb_q_.p, nfb, k, d_fb_keys_.as<uint64_t>(), stream);
   if (!s.ok()) return s;
   s = check_cuda(launch_scatter_keys(d_fb_keys_.as<uint64_t>(), d_fb_idx_.as<int>(), (int)nfb, (int)k, out_keys,
-                                     stream),
+                                     stream, nullptr, u8_widened() ? 1 : 0),
                  "scatter");
   if (!s.ok()) return s;
   stats_.kernel_launches += 2;
   // fb (host vector) must outlive the async H2D above
   return check_cuda(cudaStreamSynchronize(stream), "fallback scan");
+}
+
+// Counts of uncertified queries that device-resident batches left in pinned memory: into the statistics, and into the
+// same adaptation the host entry applies at once -- split (3xTF32) operands when a quarter of a batch failed on data
+// that is not TF32-exact, a wider candidate margin when certificates fail in numbers.
+void Engine::absorb_async_counts(bool wait) {
+  for (int i = 0; i < kFbRing; ++i) {
+    if (!fb_pending_[i]) continue;
+    if (wait) cudaEventSynchronize(fb_ev_[i]);
+    else if (cudaEventQuery(fb_ev_[i]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    fb_pending_[i] = false;
+    const size_t c = (size_t)h_fb_cnt_.as<int>()[i], nq = fb_nq_[i];
+    stats_.fallback_queries += c;
+    if (!tc_split_ && db_inexact_ && c * 4 > nq) enable_split(stream_);
+    if (c * 64 > nq && tc_margin_ < 128) tc_margin_ *= 2;
+  }
 }
 
 Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, size_t k, int32_t* d_ids,
@@ -1040,7 +1137,7 @@ Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, s
   cudaStream_t st = stream ? stream : stream_;
   s = stage_queries_device(d_queries, true, nq, elem_count, st, src_pitch);
   if (!s.ok()) return s;
-  s = run(d_q_.p, nq, k, d_ids, d_dists, d_keys, d_counts, st);
+  s = run(d_q_.p, nq, k, d_ids, d_dists, d_keys, d_counts, st, /*async=*/true);
   if (s.ok()) stats_.queries += nq;
   if (s.ok() && method_ == METHOD_SEQ) stats_.distance_evals += (uint64_t)nq * n_dev_;
   return s;
@@ -1060,7 +1157,6 @@ Status Engine::range_host(const void* query, size_t elem_count, double radius, s
   if (elem_count != (size_t)dim_)
     return Status::Err(kErrQuery, "query length " + std::to_string(elem_count) + " != index dimension " +
                                       std::to_string(dim_));
-  if (dev_u8_rows()) return Status::Err(kErrIncompat, "range queries need the widened rows (unset NB200_FORCE_EXACT)");
   const int cap = (int)std::min<size_t>(capacity, n_dev_);
   s = stage_queries_device(query, false, 1, elem_count, stream_);
   if (!s.ok()) return s;
@@ -1070,7 +1166,8 @@ Status Engine::range_host(const void* query, size_t elem_count, double radius, s
   int32_t* d_ids = reinterpret_cast<int32_t*>(d_range_.as<char>() + tmp_bytes);
   float* d_d = reinterpret_cast<float*>(d_range_.as<char>() + tmp_bytes + out_bytes);
   int* d_cnt = reinterpret_cast<int*>(d_range_.as<char>() + tmp_bytes + 2 * out_bytes);
-  const int mode = space_ == SPACE_COSINE    ? SCAN_COSINE
+  const int mode = dev_u8_rows()             ? SCAN_SIFT  // byte rows (128 per row)
+                   : space_ == SPACE_COSINE  ? SCAN_COSINE
                    : space_ == SPACE_ANGULAR ? SCAN_ANGULAR
                    : space_ == SPACE_NEGDOT  ? SCAN_NEGDOT
                    : space_ == SPACE_L1      ? SCAN_L1

@@ -191,20 +191,29 @@ class Engine {
   // uint8 + seq_search normally runs on the tensor cores: rows widened to fp32 on upload (0..255 is TF32-exact
   // and every partial sum stays an integer below 2^24, so the fp32 pipeline returns the int32 distances bit
   // for bit).  NB200_FORCE_EXACT=1 keeps the byte rows and the dp4a scan (K2) instead.
-  bool dev_u8_rows() const { return is_u8_ && method_ == METHOD_SEQ && force_exact_; }
-  bool u8_widened() const { return is_u8_ && method_ == METHOD_SEQ && !force_exact_; }
+  // Default since round 2: BYTE rows on the integer tensor pipe (tcgen05.mma.kind::i8, tc_scan_u8_kernel) when the
+  // rows' norms fit its digit block; the widened TF32 path remains for data beyond that and as option u8_imma=0.
+  bool dev_u8_rows() const { return is_u8_ && method_ == METHOD_SEQ && (force_exact_ || u8_imma_); }
+  bool u8_widened() const { return is_u8_ && method_ == METHOD_SEQ && !force_exact_ && !u8_imma_; }
+  bool u8_imma() const { return u8_imma_; }
 
  private:
   Status check_cuda(cudaError_t e, const char* what);
   const float* hnsw_host_rows();
   Status upload_data();
   Status upload_graph();
-  Status run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream);
+  // d_nq: the query count lives on the device (<= nq): kernels are launched for nq and leave early past *d_nq
+  Status run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream,
+                       const int* d_nq = nullptr);
+  // async: no host round trip -- uncertified queries are listed and re-run exactly by device-predicated launches, the
+  // count reaches the host later (stats / adaptation of the next batches); !async (host entry, which synchronises
+  // anyway): the host reads the certificates and can re-run a mostly-failed batch with split operands at once
   Status run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_keys, cudaStream_t stream,
-                    bool allow_split_retry = true);
+                    bool allow_split_retry = true, bool async = false);
+  void absorb_async_counts(bool wait);
   Status enable_split(cudaStream_t stream);
   Status run(const void* d_queries_padded, size_t nq, size_t k, int32_t* d_ids, float* d_dists,
-             uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream);
+             uint64_t* d_keys, int32_t* d_counts, cudaStream_t stream, bool async = false);
   Status stage_queries_device(const void* src, bool src_on_device, size_t nq, size_t elem_count,
                               cudaStream_t stream, size_t src_pitch = 0);
   Status build_graph_device();
@@ -261,8 +270,20 @@ class Engine {
   DevBuf d_bias_, d_db_unit_, d_flags_, d_qa_, d_cand_, d_cand_cnt_, d_cand_thr_, d_tc_keys_, d_cert_, d_fb_idx_,
       d_fb_q_, d_fb_keys_, d_nblock_, d_ones_;
   PinBuf h_cert_;
+  // device-predicated re-run of uncertified queries (knn_device): count + index list on the device, the count is
+  // copied to a ring of pinned words and absorbed into the statistics / the adaptation later
+  DevBuf d_fb_cnt_;
+  static constexpr int kFbRing = 16;
+  PinBuf h_fb_cnt_;
+  cudaEvent_t fb_ev_[kFbRing] = {};
+  size_t fb_nq_[kFbRing] = {};
+  bool fb_pending_[kFbRing] = {};
+  int fb_head_ = 0;
   float x_max_ = 0.f;
   bool force_exact_ = false;
+  bool u8_imma_ = false;   // uint8 + seq_search on the integer tensor pipe (decided at upload from the rows' norms)
+  int u8_m_half_ = 0;      // M = ceil(max |x|^2 / 2) of the uploaded rows
+  DevBuf d_digits_;        // [n_pad][32] norm digits (scan_tc.cu: u8_norm_digits_kernel)
   bool approx_ok_ = false, rows_borrowed_ = false, dry_run_ = false;
   HnswBuildInfo build_info_;
   size_t n_dev_ = 0;

@@ -38,12 +38,14 @@ enum ScanMode : int { SCAN_L2 = 0, SCAN_NEGDOT = 1, SCAN_COSINE = 2, SCAN_SIFT =
 // partial: [nq][n_split][k] keys, each split's list ascending, KEY_MAX padded.
 cudaError_t launch_scan_exact(int mode, const void* db, const void* queries, const void* db_aux,
                               const void* q_aux, int n, int nq, int row_words, int k, uint32_t pos_base,
-                              uint64_t* partial, int n_split, int tiles_per_split, cudaStream_t stream);
+                              uint64_t* partial, int n_split, int tiles_per_split, cudaStream_t stream,
+                              const int* d_nq = nullptr);  // d_nq: query count read on the device (<= nq)
 int scan_exact_max_k();
 int scan_exact_block_queries();
 int scan_exact_block_points();
 int scan_exact_stage_words();
-cudaError_t launch_row_aux(bool is_u8, const void* rows, int n, int row_words, void* out, cudaStream_t stream);
+cudaError_t launch_row_aux(bool is_u8, const void* rows, int n, int row_words, void* out, cudaStream_t stream,
+                           const int* d_n = nullptr);
 
 // ---- topk_merge.cu -------------------------------------------------------------------
 // Merge `lists` ascending key lists per query into the k best and finalise them.
@@ -53,16 +55,18 @@ cudaError_t launch_row_aux(bool is_u8, const void* rows, int n, int row_words, v
 cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int lists, size_t list_stride,
                               size_t query_stride, int nq, int k, int finalize, const int32_t* ext_ids,
                               uint32_t pos_base, uint64_t* out_keys, int32_t* out_ids, float* out_dists,
-                              int32_t* out_counts, cudaStream_t stream);
+                              int32_t* out_counts, cudaStream_t stream, const int* d_nq = nullptr);
 int merge_topk_max_items();
 
 // gather rows idx[i] of a [*, row_words] array into dst[i] / scatter k-key rows back
 // uint8 rows [rows][dim] -> fp32 rows [rows][row_words] (padding columns are left untouched)
 cudaError_t launch_widen_u8(const uint8_t* src, size_t rows, int dim, int row_words, float* dst, cudaStream_t stream);
+// d_count (optional): row count read on the device (<= count); rows up to the next multiple of `pad` are zero-filled
 cudaError_t launch_gather_rows(const uint32_t* src, const int* idx, int count, int row_words, uint32_t* dst,
-                               cudaStream_t stream);
+                               cudaStream_t stream, const int* d_count = nullptr, int pad = 1);
+// f2i: the source keys carry f32_ordered(exact-integer float distance), the destination wants i32_ordered (uint8 indexes)
 cudaError_t launch_scatter_keys(const uint64_t* src, const int* idx, int count, int k, uint64_t* dst,
-                                cudaStream_t stream);
+                                cudaStream_t stream, const int* d_count = nullptr, int f2i = 0);
 
 // ---- scan_tc.cu (tcgen05 TF32 candidates + exact fp32 re-rank) -------------------------
 int tc_block_queries();   // queries per CTA (256): query buffers are padded to this
@@ -116,7 +120,19 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
                              uint64_t* out_keys, int* out_cert, cudaStream_t stream,  // mode may be SCAN_ANGULAR
                              int q_begin = 0, int q_count = -1, int n_lists = -1,  // a query range whose blocks use
-                             float eps_override = 0.f);  // only the first n_lists lists; eps: error band of split operands
+                             float eps_override = 0.f,  // only the first n_lists lists; eps: error band of split operands
+                             int* fb_count = nullptr, int* fb_idx = nullptr,  // device-side list of uncertified queries
+                             const uint8_t* db_u8 = nullptr, const uint8_t* q_u8 = nullptr,  // byte rows (uint8 on the integer pipe)
+                             float abs_err = 0.f, int int_keys = 0);  // absolute pass-1 error bound; int-ordered out keys
+// ---- uint8 rows on the integer tensor pipe (tcgen05.mma.kind::i8; scan_tc.cu: tc_scan_u8_kernel) ----
+// q / db: byte rows of 128; digits: [n_pad][32] norm digits (launch_u8_norm_digits) of V(x) = m_half - ceil(|x|^2 / 2);
+// candidates / thresholds / gthr as for launch_tc_scan_ts (ranks = |x|^2 - 2 q.x + (|x|^2 odd), exact even integers)
+int u8_imma_max_norm2();  // largest max |x|^2 the digit block can carry
+cudaError_t launch_u8_max_norm(const int* norm2, int n, int* d_out, cudaStream_t stream);
+cudaError_t launch_u8_norm_digits(const int* norm2, int n, int n_pad, int m_half, uint8_t* out, cudaStream_t stream);
+cudaError_t launch_tc_scan_u8(const uint8_t* q, const uint8_t* db, const uint8_t* digits, size_t n_pad, int n, int nq, int k,
+                              int kprime, int m_half, uint32_t pos_base, int n_cta, int s_max, const int* d_pieces,
+                              uint64_t* cand, int* cand_cnt, float* cand_thr, uint32_t* gthr, cudaStream_t stream);
 // 3xTF32 operand split: dst[r] = [hi | lo | hi] (layout 0, database) or [hi | hi | lo] (layout 1, queries) of
 // scale * src[r], hi = the TF32-exact part, lo = the TF32-exact part of the rest; dst rows are 3 * row_words long
 cudaError_t launch_tc_split_rows(const float* src, size_t rows, int row_words, float scale, int layout, float* dst,

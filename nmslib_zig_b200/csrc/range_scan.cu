@@ -32,6 +32,15 @@ __global__ void __launch_bounds__(256) range_dist_kernel(const float* __restrict
   const float4* q4 = reinterpret_cast<const float4*>(q);
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < n; row += warps) {
+    if (mode == SCAN_SIFT) {  // byte rows of 128 (row_words = 32): exact int32 sum (x - y)^2, reported as a float
+      const uchar4 x = __ldg(reinterpret_cast<const uchar4*>(db + (size_t)row * row_words) + lane);
+      const uchar4 y = reinterpret_cast<const uchar4*>(q)[lane];
+      const int d0 = (int)x.x - y.x, d1 = (int)x.y - y.y, d2 = (int)x.z - y.z, d3 = (int)x.w - y.w;
+      int di = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      di = __reduce_add_sync(FULL, di);
+      if (lane == 0) dist[row] = (float)di;
+      continue;
+    }
     const float4* x4 = reinterpret_cast<const float4*>(db + (size_t)row * row_words);
     float acc = 0.f, nxs = 0.f, nqs = 0.f;
     for (int e = lane; e < rw4; e += 32) {

@@ -91,8 +91,12 @@ __global__ void __launch_bounds__(NT, (MODE == SCAN_SIFT) ? 1 : 1)
 scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qs,
                   const void* __restrict__ db_aux_v, const void* __restrict__ q_aux_v, int n, int nq,
                   int row_words, int k, int tiles_per_split, uint32_t pos_base,
-                  uint64_t* __restrict__ partial, int n_split) {
+                  uint64_t* __restrict__ partial, int n_split, const int* __restrict__ d_nq) {
   using acc_t = typename Acc<MODE>::type;
+  if (d_nq) {  // query count decided on the device (the re-run of uncertified queries): surplus blocks leave at once
+    nq = min(nq, *d_nq);
+    if ((int)blockIdx.y * BQ >= nq) return;
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw);                     // NSTAGE*(BQ+BN)*LDW
   uint64_t* lists = reinterpret_cast<uint64_t*>(tiles + NSTAGE * (BQ + BN) * LDW);  // BQ*k
@@ -333,7 +337,8 @@ int scan_exact_max_k() { return 144; }
 
 cudaError_t launch_scan_exact(int mode, const void* db, const void* queries, const void* db_aux,
                               const void* q_aux, int n, int nq, int row_words, int k, uint32_t pos_base,
-                              uint64_t* partial, int n_split, int tiles_per_split, cudaStream_t stream) {
+                              uint64_t* partial, int n_split, int tiles_per_split, cudaStream_t stream,
+                              const int* d_nq) {
   if (nq <= 0 || n <= 0) return cudaSuccess;
   const size_t smem = scan_exact_smem(k);
   dim3 grid(n_split, (nq + BQ - 1) / BQ);
@@ -344,7 +349,7 @@ cudaError_t launch_scan_exact(int mode, const void* db, const void* queries, con
   e = cudaFuncSetAttribute(scan_exact_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return e;                                                                      \
   scan_exact_kernel<M><<<grid, NT, smem, stream>>>(d, q, db_aux, q_aux, n, nq, row_words, k,           \
-                                                   tiles_per_split, pos_base, partial, n_split);
+                                                   tiles_per_split, pos_base, partial, n_split, d_nq);
   switch (mode) {
     case SCAN_L2: NB_LAUNCH(SCAN_L2); break;
     case SCAN_NEGDOT: NB_LAUNCH(SCAN_NEGDOT); break;
@@ -369,8 +374,10 @@ int scan_exact_stage_words() { return BW; }
 // One warp per row, 128-bit loads.
 // ---------------------------------------------------------------------------------------
 namespace {
-__global__ void row_aux_f32_kernel(const float* __restrict__ rows, int n, int row_words, float* __restrict__ out) {
+__global__ void row_aux_f32_kernel(const float* __restrict__ rows, int n, int row_words, float* __restrict__ out,
+                                   const int* __restrict__ d_n) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (d_n) n = min(n, *d_n);
   if (warp >= n) return;
   const float4* r = reinterpret_cast<const float4*>(rows + (size_t)warp * row_words);
   float s = 0.f;
@@ -385,8 +392,10 @@ __global__ void row_aux_f32_kernel(const float* __restrict__ rows, int n, int ro
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[warp] = s;
 }
-__global__ void row_aux_u8_kernel(const uint32_t* __restrict__ rows, int n, int row_words, int* __restrict__ out) {
+__global__ void row_aux_u8_kernel(const uint32_t* __restrict__ rows, int n, int row_words, int* __restrict__ out,
+                                  const int* __restrict__ d_n) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (d_n) n = min(n, *d_n);
   if (warp >= n) return;
   unsigned s = 0;
   for (int c = lane; c < row_words; c += 32) {
@@ -399,16 +408,17 @@ __global__ void row_aux_u8_kernel(const uint32_t* __restrict__ rows, int n, int 
 }
 }  // namespace
 
-cudaError_t launch_row_aux(bool is_u8, const void* rows, int n, int row_words, void* out, cudaStream_t stream) {
+cudaError_t launch_row_aux(bool is_u8, const void* rows, int n, int row_words, void* out, cudaStream_t stream,
+                           const int* d_n) {
   if (n <= 0) return cudaSuccess;
   const int threads = 256;
   const int blocks = (int)(((size_t)n * 32 + threads - 1) / threads);
   if (is_u8)
     row_aux_u8_kernel<<<blocks, threads, 0, stream>>>(static_cast<const uint32_t*>(rows), n, row_words,
-                                                      static_cast<int*>(out));
+                                                      static_cast<int*>(out), d_n);
   else
     row_aux_f32_kernel<<<blocks, threads, 0, stream>>>(static_cast<const float*>(rows), n, row_words,
-                                                       static_cast<float*>(out));
+                                                       static_cast<float*>(out), d_n);
   return cudaGetLastError();
 }
 

@@ -1435,6 +1435,387 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------- K1 for uint8 rows: the integer tensor pipe
+// l2sqr_sift (config 4; reference: l2SqrSIFTPrecompAVX, distcomp_l2sqr_sift.cc:100-151: n1 + n2 - 2 x.y over 128 bytes
+// with the int32 norms kept behind each payload).  Same structure as tc_scan_ts_kernel -- a CTA's 256 queries live in
+// tensor memory, one 64-row database tile per stage, two MMA issuers, eight epilogue warps -- on
+// tcgen05.mma.kind::i8 (u8 x u8 -> s32, K = 32 per instruction, 4 x the TF32 rate; tools/tc_peak.cu):
+//   * rows stay BYTES in HBM and in shared memory: 128 B per row instead of the 512 B of the widened fp32 copy;
+//   * the accumulator is made to carry the whole rank: with M = ceil(max |x|^2 / 2) and V(x) = M - ceil(|x|^2 / 2)
+//     >= 0 written as 32 base-255 "digits" d_j(x) (one more 32-byte k-block per row, against the constant operand
+//     row c = [1, 255, 255, ...]),      acc = q.x + sum_j c_j d_j(x) = q.x + V(x),
+//     so that  2 (M - acc) = |x|^2 - 2 q.x + (|x|^2 odd)  is the pass-1 rank: exact up to +1, larger acc = nearer.
+//     One extra K = 32 MMA per tile and half; needs max |x|^2 <= 4 032 060 (else the engine keeps the widened path);
+//   * tensor memory: [0, 128) operand rows (per half 32 columns of query bytes + 8 columns of constants),
+//     [128, 512) THREE accumulator buffers x two halves x 64 columns -- one more than the TF32 kernel has room for,
+//     which is what absorbs the epilogue's jitter now that a tile's MMAs take ~320 clk instead of ~1100;
+//   * the epilogue works on the raw int32 accumulators (max tree, acc > threshold); survivors become the same
+//     (float rank, position) keys as everywhere else (an int below 2^24 is exact in fp32), so re-rank, certificate
+//     (error bound: 1) and merge are shared.
+constexpr int U8_ACC0 = 128;   // first accumulator column
+constexpr int U8_NBUF = 3;     // accumulator buffers
+constexpr int U8_ROW = 128;    // bytes per database row (SIFT_DIM, space_l2sqr_sift.h)
+constexpr int U8_NROW = 32;    // bytes per row of the norm-digit block
+constexpr int U8_STAGE = TS_BN * (U8_ROW + U8_NROW);  // 10 KB per tile
+
+struct U8Params {
+  int n, nq, s_max;
+  const int4* pieces;
+  uint32_t pos_base;
+  uint64_t* cand;
+  int* cand_cnt;
+  float* cand_thr;
+  int cap, kprime, slack, hwm, n_stage, refresh_mask, debug;
+  uint32_t* gthr;           // [q_pad] ordered float bits of the best rank threshold published per query
+  const uint8_t* q;         // [q_pad][128] query bytes (zero rows past nq)
+  int m_half;               // M = ceil(max |x|^2 / 2)
+  unsigned long long* counters;
+};
+
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::i8: D = S32 (2 @4), A = B = unsigned 8-bit (0 @7, 0 @10), both K-major, N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t make_idesc_u8(int m, int n) {
+  return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// K-major tile with rows of 32 bytes, 32B swizzle (the norm-digit block): 8-row atoms of 256 B
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
+__device__ __forceinline__ int group_max8(const int (&r)[32], int q) {
+  return max3i(max3i(r[8 * q], r[8 * q + 1], r[8 * q + 2]), max3i(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
+               max(r[8 * q + 6], r[8 * q + 7]));
+}
+// accumulator <-> rank (an even integer, exact in fp32: |2 (M - acc)| < 2^24)
+__device__ __forceinline__ float u8_rank_of(int acc, int m_half) { return (float)(2 * (m_half - acc)); }
+__device__ __forceinline__ int u8_acc_of_rank(float rank, int m_half) {  // pass iff acc > result  <=>  rank' < rank
+  if (!(rank < 3.0e38f)) return -1;          // +inf / NaN ("no threshold yet"): every accumulator (>= 0) passes
+  return m_half - (__float2int_rd(rank) >> 1) - ((__float2int_rd(rank) & 1) ? 1 : 0) + 0;
+}
+
+// per-lane selection of one 32-column chunk (integer twin of epi_select): acc > thr passes
+template <bool REG>
+__device__ __forceinline__ void epi_select_i(const int (&r)[32], const int (&g)[4], uint32_t pos0, uint64_t* buf, int& cnt,
+                                             int& thr, int (&tk)[TS_RK], uint32_t* gthr, int m_half) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (g[q] > thr) {
+      unsigned mk = 0;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] > thr ? 1u : 0u) << jj;
+#pragma unroll 1
+      while (mk) {
+        const int jj = __ffs(mk) - 1;
+        mk &= mk - 1;
+        const int lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
+        const int hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
+        const int x = (jj & 4) ? hi4 : lo4;
+        if (!REG || x > thr) {
+          buf[cnt] = ((uint64_t)__float_as_uint(u8_rank_of(x, m_half)) << 32) | (uint64_t)(pos0 + 8 * q + jj);
+          ++cnt;
+          if constexpr (REG) {  // 16 best accumulators, descending; every slot computed independently
+            int prev = 0x7FFFFFFF;
+#pragma unroll
+            for (int i = 0; i < TS_RK; ++i) {
+              const int cur = tk[i];
+              tk[i] = min(prev, max(cur, x));
+              prev = cur;
+            }
+            if (tk[TS_RK - 1] > thr) {
+              thr = tk[TS_RK - 1];
+              atomicMin(gthr, f32_ordered(u8_rank_of(thr, m_half)));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int KPL, bool REG>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+tc_scan_u8_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmN, const U8Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem_st = smem;  // stage s: [64 rows x 128 B, 128B swizzle][64 rows x 32 B, 32B swizzle]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + (size_t)p.n_stage * U8_STAGE);
+  uint64_t* full_bar = bars;                       // [n_stage]
+  uint64_t* empty_bar = bars + p.n_stage;          // [n_stage] one commit from each issuer
+  uint64_t* tfull_bar = bars + 2 * p.n_stage;      // [3 buffers][2 halves]
+  uint64_t* tempty_bar = tfull_bar + 2 * U8_NBUF;  // [3][2] the 4 warps of the half
+  uint64_t* afull_bar = tempty_bar + 2 * U8_NBUF;  // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(afull_bar + 1);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(FULL, tid >> 5, 0), lane = tid & 31;
+  const int4* my_pieces = p.pieces + (size_t)blockIdx.x * TS_MAXP;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.n_stage; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);
+    }
+    for (int b = 0; b < 2 * U8_NBUF; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    mbar_init(afull_bar, 256);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmN);
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer: one whole tile (rows + norm digits) per stage =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pi = 0; pi < TS_MAXP; ++pi) {
+      const int4 pc = __ldg(my_pieces + pi);
+      if (pc.x < 0) break;
+      for (int t = pc.y; t < pc.z; ++t) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* st = smem_st + (size_t)s * U8_STAGE;
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[s], (uint32_t)U8_STAGE);
+          tma_load_2d(&tmB, &full_bar[s], st, 0, t * TS_BN);
+          tma_load_2d(&tmN, &full_bar[s], st + TS_BN * U8_ROW, 0, t * TS_BN);
+        }
+        __syncwarp();
+        if (++s == p.n_stage) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 || warp == TS_MMA_WARP2) {
+    // ===================== MMA issuers: one warp per 128-query half =====================
+    constexpr uint32_t idesc = make_idesc_u8(TC_BM, TS_BN);
+    const int hh = warp == 1 ? 0 : 1;
+    const uint32_t st_base = smem_u32(smem_st);
+    const uint32_t a_half = tmem_base + (uint32_t)(hh * 64);
+    int s = 0;
+    uint32_t ph = 0;
+    int ti = 0, b = 0;
+    uint32_t bph = 0;  // parity of the accumulator ring's current round
+    [[maybe_unused]] unsigned long long c_tempty = 0, c_full = 0, c_issue = 0;
+    NB_T0(tm);
+    for (int pi = 0; pi < TS_MAXP; ++pi) {
+      const int4 pc = __ldg(my_pieces + pi);
+      if (pc.x < 0) break;
+      mbar_wait(afull_bar, pi & 1);
+      tc_fence_after();
+      for (int t = pc.y; t < pc.z; ++t, ++ti) {
+        NB_TACC(c_issue, tm);
+        mbar_wait(&tempty_bar[b * 2 + hh], bph ^ 1);
+        NB_TACC(c_tempty, tm);
+        mbar_wait(&full_bar[s], ph);
+        NB_TACC(c_full, tm);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(U8_ACC0 + (b * 2 + hh) * TS_BN);
+        const uint32_t sb = st_base + (uint32_t)s * (uint32_t)U8_STAGE;
+        if (elect_one()) {
+          const uint64_t db = make_smem_desc(sb);
+          // UMMA_K = 32 bytes: 8 TMEM columns of A, +2 in the descriptor of B
+          umma_i8_ts(d, a_half, db, idesc, 0);
+          umma_i8_ts(d, a_half + 8, db + 2, idesc, 1);
+          umma_i8_ts(d, a_half + 16, db + 4, idesc, 1);
+          umma_i8_ts(d, a_half + 24, db + 6, idesc, 1);
+          umma_i8_ts(d, a_half + 32, make_smem_desc_sw32(sb + TS_BN * U8_ROW), idesc, 1);  // + V(x)
+          tc_commit(&empty_bar[s]);
+          tc_commit(&tfull_bar[b * 2 + hh]);
+        }
+        __syncwarp();
+        if (++s == p.n_stage) {
+          s = 0;
+          ph ^= 1;
+        }
+        if (++b == U8_NBUF) {
+          b = 0;
+          bph ^= 1;
+        }
+      }
+    }
+#ifdef NB200_EXPERIMENTS
+    NB_TACC(c_issue, tm);
+    if (p.counters && lane == 0 && hh == 0) {
+      atomicAdd(p.counters + 11, c_tempty);
+      atomicAdd(p.counters + 12, c_full);
+      atomicAdd(p.counters + 13, c_issue);
+    }
+#endif
+  } else {
+    // ===================== epilogue: 8 warps, thread == one query row =====================
+    const int e = warp - 2;
+    const int h = e >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    unsigned ctr[4] = {0, 0, 0, 0};
+    int b = 0;
+    uint32_t bph = 0;
+    [[maybe_unused]] unsigned long long c_twait = 0, c_drain = 0, c_proc = 0;
+    NB_T0(te);
+    for (int pi = 0; pi < TS_MAXP; ++pi) {
+      const int4 pc = __ldg(my_pieces + pi);
+      if (pc.x < 0) break;
+      const int qb = pc.x, t_begin = pc.y, t_end = pc.z;
+      const size_t unit = (size_t)qb * p.s_max + pc.w;
+      const int qrow = qb * TC_QB + h * TC_BM + row;
+      const bool row_valid = qrow < p.nq;
+      uint64_t* buf = p.cand + (unit * TC_QB + h * TC_BM + row) * (size_t)p.cap;
+      uint32_t* gthr = p.gthr + qrow;
+      int cnt = 0;
+      int thr = row_valid ? -1 : 0x7FFFFFFF;  // pass iff acc > thr (accumulators are >= 0)
+      int tk[TS_RK];
+#pragma unroll
+      for (int i = 0; i < TS_RK; ++i) tk[i] = -1;
+      {
+        // operand rows -> tensor memory: 128 query bytes = 32 columns (byte k in column k / 4), then the constant
+        // k-block [1, 255 x 31] that multiplies the norm digits
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + (size_t)qrow * U8_ROW);
+        const uint32_t ta = trow + (uint32_t)(h * 64);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 u0 = __ldg(src + 2 * c), u1 = __ldg(src + 2 * c + 1);
+          const uint32_t v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          tmem_st8(ta + (uint32_t)(c * 8), v);
+        }
+        const uint32_t cv[8] = {0xFFFFFF01u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        tmem_st8(ta + 32u, cv);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(afull_bar);
+      }
+      const int guard = REG ? p.cap - TS_BN - 1 : p.hwm;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        uint32_t v0[32], v1[32];
+        NB_TACC(c_proc, te);
+        mbar_wait(&tfull_bar[b * 2 + h], bph);
+        NB_TACC(c_twait, te);
+        tc_fence_after();
+        const uint32_t tcol = trow + (uint32_t)(U8_ACC0 + (b * 2 + h) * TS_BN);
+        tmem_ld32(tcol, v0);
+        tmem_ld32(tcol + 32u, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[b * 2 + h]);
+        if (++b == U8_NBUF) {
+          b = 0;
+          bph ^= 1;
+        }
+        NB_TACC(c_drain, te);
+        if (NB200_DBG(p.debug, 1)) {
+          if (v0[0] == 0x12345678u || v1[0] == 0x12345678u) thr = 0;
+          continue;
+        }
+        int r0[32], r1[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          r0[j] = (int)v0[j];
+          r1[j] = (int)v1[j];
+        }
+        int g0[4], g1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          g0[q] = group_max8(r0, q);
+          g1[q] = group_max8(r1, q);
+        }
+        const int mm = max3i(max(max3i(g0[0], g0[1], g0[2]), max3i(g0[3], g1[0], g1[1])), g1[2], g1[3]);
+        const int vtile = p.n - tile * TS_BN;
+        const bool uni = (((tile - t_begin) & p.refresh_mask) == 0) | (vtile < TS_BN);
+        const bool mine = (mm > thr) | (cnt > guard);
+        if (!uni && !__any_sync(FULL, mine)) continue;
+        // ------------------------------------------------------------------ slow path
+        if (((tile - t_begin) & p.refresh_mask) == 0 && row_valid)
+          thr = max(thr, u8_acc_of_rank(f32_from_ordered(*gthr), p.m_half));
+        if (vtile < TS_BN) {  // rows past the end of the shard: never candidates
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j >= vtile) r0[j] = -2;
+            if (j + 32 >= vtile) r1[j] = -2;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            g0[q] = group_max8(r0, q);
+            g1[q] = group_max8(r1, q);
+          }
+        }
+        unsigned need = __ballot_sync(FULL, cnt > p.cap - TS_BN - 1);
+        while (need) {
+          ++ctr[2];
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          float tf = u8_rank_of(thr, p.m_half);
+          compact_lane<KPL>(src, buf, cnt, tf, p.kprime, p.slack, gthr, lane);
+          if (lane == src) thr = max(thr, u8_acc_of_rank(tf, p.m_half));
+        }
+        ++ctr[1];
+        const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TS_BN);
+        if (mm > thr || vtile < TS_BN) {
+          epi_select_i<REG>(r0, g0, pos_tile, buf, cnt, thr, tk, gthr, p.m_half);
+          epi_select_i<REG>(r1, g1, pos_tile + 32, buf, cnt, thr, tk, gthr, p.m_half);
+        }
+        if constexpr (REG) continue;
+        const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);
+        if (pend) {
+          ++ctr[3];
+          const int src = __ffs(pend) - 1;
+          float tf = u8_rank_of(thr, p.m_half);
+          compact_lane<KPL>(src, buf, cnt, tf, p.kprime, p.slack, gthr, lane);
+          if (lane == src) thr = max(thr, u8_acc_of_rank(tf, p.m_half));
+        }
+      }
+      const size_t slot = unit * TC_QB + h * TC_BM + row;
+      p.cand_cnt[slot] = row_valid ? cnt : 0;
+      p.cand_thr[slot] = thr < 0 ? __int_as_float(0x7F800000) : u8_rank_of(thr, p.m_half);
+    }
+    if (p.counters && lane == 0) {
+      for (int i = 0; i < 4; ++i) atomicAdd(p.counters + i, (unsigned long long)ctr[i]);
+#ifdef NB200_EXPERIMENTS
+      NB_TACC(c_proc, te);
+      atomicAdd(p.counters + 14, c_twait);
+      atomicAdd(p.counters + 15, c_drain);
+      atomicAdd(p.counters + 16, c_proc);
+#endif
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------- pass 2: exact re-rank
 struct RerankParams {
   const float* db;         // [n_pad][row_words] ORIGINAL vectors
@@ -1451,6 +1832,12 @@ struct RerankParams {
   const int* inexact_flags;       // [2]: nonzero if the database / this query batch is not TF32-exact
   uint64_t* out_keys;             // [nq][k]
   int* out_cert;                  // [nq] 1 = certified exact
+  const uint8_t* db_u8;           // uint8 index on byte rows (tc_scan_u8_kernel): [n_pad][128] rows / queries, exact
+  const uint8_t* q_u8;            //   int32 arithmetic here; NULL: float rows
+  float abs_err;                  // > 0: absolute pass-1 error bound (uint8 on the integer pipe: 1), else eps * norms
+  int int_keys;                   // uint8 indexes: out keys carry i32_ordered(int distance) (FIN_INT), like the dp4a scan
+  int* fb_count;                  // device-side list of the uncertified queries (count + indices), or NULL:
+  int* fb_idx;                    // what the device-predicated exact re-run works from (no host round trip)
   int debug_cert;                 // NB200_TC_DEBUG_CERT: print the certificate inputs of the first queries
 };
 
@@ -1491,8 +1878,15 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   if (tid == 0) s_live = 0;
   if (warp == 2) {
     float s = 0.f;
-    for (int c = lane; c < p.row_words; c += 32) s = fmaf(qv[c], qv[c], s);
-    s = warp_sum_f(s);
+    if (p.q_u8) {  // 128 bytes: one uchar4 per lane, exact integer sum
+      const uchar4 y = reinterpret_cast<const uchar4*>(p.q_u8 + (size_t)q * U8_ROW)[lane];
+      int si = (int)y.x * y.x + (int)y.y * y.y + (int)y.z * y.z + (int)y.w * y.w;
+      si = __reduce_add_sync(FULL, si);
+      s = (float)si;
+    } else {
+      for (int c = lane; c < p.row_words; c += 32) s = fmaf(qv[c], qv[c], s);
+      s = warp_sum_f(s);
+    }
     if (lane == 0) s_qn2 = s;
   }
   __syncthreads();
@@ -1519,7 +1913,8 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   int total = min(s_live, items_pow2);
   // pass-1 error bound of this query (same E as the certificate below)
   const bool inexact_q = p.inexact_flags[0] != 0 || p.inexact_flags[1] != 0;
-  const float E_q = (inexact_q ? p.eps_inexact : p.eps_exact) * (p.mode == SCAN_L2 ? 2.f : 1.f) * sqrtf(qn2) * p.x_max + 1e-30f;
+  const float E_q = p.abs_err > 0.f ? p.abs_err
+                                    : (inexact_q ? p.eps_inexact : p.eps_exact) * (p.mode == SCAN_L2 ? 2.f : 1.f) * sqrtf(qn2) * p.x_max + 1e-30f;
   {
     // Second filter.  Let a_k be the k-th smallest PASS-1 rank among the live keys.  The k keys at or below it
     // have exact rank <= a_k + E, so the true k-th best exact rank is <= a_k + E and every true neighbour has
@@ -1582,6 +1977,19 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   for (int i0 = warp; i0 < total; i0 += 4) {
     const uint32_t pos = spos[i0];
     const size_t local = (size_t)(pos - p.pos_base);
+    if (p.db_u8) {  // sum (x - y)^2 over 128 bytes in int32: the reference's n1 + n2 - 2 x.y (distcomp_l2sqr_sift.cc:41-50)
+      const uchar4 x = __ldg(reinterpret_cast<const uchar4*>(p.db_u8 + local * U8_ROW) + lane);
+      const uchar4 y = reinterpret_cast<const uchar4*>(p.q_u8 + (size_t)q * U8_ROW)[lane];
+      const int d0 = (int)x.x - y.x, d1 = (int)x.y - y.y, d2 = (int)x.z - y.z, d3 = (int)x.w - y.w;
+      int di = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      di = __reduce_add_sync(FULL, di);
+      __syncwarp();
+      if (lane == 0) {
+        sk[i0] = make_key(i32_ordered(di), pos);
+        srank[i0] = (float)di - qn2;
+      }
+      continue;
+    }
     const float4* x4 = reinterpret_cast<const float4*>(p.db + local * p.row_words);
     float acc = 0.f, nxs = 0.f, nqs = 0.f;
     const bool cosfam = p.mode == SCAN_COSINE || p.mode == SCAN_ANGULAR;
@@ -1634,7 +2042,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
     }
     __syncwarp();  // every lane has read spos[i0] before the slot is reused for the rank
     if (lane == 0) {
-      sk[i0] = make_key(f32_ordered(dist), pos);
+      sk[i0] = p.int_keys ? make_key(i32_ordered((int)dist), pos) : make_key(f32_ordered(dist), pos);
       srank[i0] = rank;
     }
   }
@@ -1680,6 +2088,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
       cert = (worst + E + fabsf(worst) * 1e-6f < minthr) ? 1 : 0;
     }
     p.out_cert[q] = cert;
+    if (!cert && p.fb_idx) p.fb_idx[atomicAdd(p.fb_count, 1)] = q;
     if (NB200_DBG(p.debug_cert, 1) && (q < 2 || (cert == 0 && q < 40))) {
       float worst = __int_as_float(0xFF800000);
       for (int e = 0; e < p.k && e < p2e; ++e) worst = fmaxf(worst, srank[e]);
@@ -1802,7 +2211,141 @@ bool make_tmap(CUtensorMap* map, const void* base, size_t rows, int row_elems, i
   return r == CUDA_SUCCESS;
 }
 
+// byte rows [rows][row_bytes] (row_bytes = 128: 128B swizzle; 32: 32B swizzle), boxes of box_rows whole rows
+bool make_tmap_u8(CUtensorMap* map, const void* base, size_t rows, int row_bytes, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)row_bytes, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// uint8 rows: int32 |x|^2 per row (aux, from launch_row_aux) -> the 32 norm digits of V(x) = m_half - ceil(|x|^2 / 2)
+// (d0 = V mod 255, then floor(V / 255) spread over 31 digits of at most 255); padding rows get V = 0
+__global__ void u8_norm_digits_kernel(const int* __restrict__ norm2, int n, int n_pad, int m_half, uint8_t* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_pad) return;
+  int v = 0;
+  if (r < n) v = m_half - ((norm2[r] + 1) >> 1);
+  uint32_t w[8];
+  int rest = v / 255;
+  uint32_t d0 = (uint32_t)(v % 255);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      uint32_t d;
+      if (j == 0 && b == 0) d = d0;
+      else {
+        d = (uint32_t)min(rest, 255);
+        rest -= (int)d;
+      }
+      word |= d << (8 * b);
+    }
+    w[j] = word;
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)r * U8_NROW);
+  o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__global__ void max_int_kernel(const int* __restrict__ v, int n, int* __restrict__ out) {
+  int m = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+  m = __reduce_max_sync(FULL, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 }  // namespace
+
+// ---- uint8 rows on the integer tensor pipe (tc_scan_u8_kernel) ----
+int u8_imma_max_norm2() { return 2 * (255 + 31 * 255 * 255) - 1; }  // V(x) <= 255 + 31 * 255 * 255 must hold
+cudaError_t launch_u8_max_norm(const int* norm2, int n, int* d_out, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(d_out, 0, 4, stream);
+  if (e != cudaSuccess || n <= 0) return e;
+  max_int_kernel<<<std::min(296, (n + 255) / 256), 256, 0, stream>>>(norm2, n, d_out);
+  return cudaGetLastError();
+}
+cudaError_t launch_u8_norm_digits(const int* norm2, int n, int n_pad, int m_half, uint8_t* out, cudaStream_t stream) {
+  if (n_pad <= 0) return cudaSuccess;
+  u8_norm_digits_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(norm2, n, n_pad, m_half, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_scan_u8(const uint8_t* q, const uint8_t* db, const uint8_t* digits, size_t n_pad, int n, int nq, int k,
+                              int kprime, int m_half, uint32_t pos_base, int n_cta, int s_max, const int* d_pieces,
+                              uint64_t* cand, int* cand_cnt, float* cand_thr, uint32_t* gthr, cudaStream_t stream) {
+  if (n <= 0 || nq <= 0) return cudaSuccess;
+  CUtensorMap tmB, tmN;
+  if (!make_tmap_u8(&tmB, db, n_pad, U8_ROW, TS_BN) || !make_tmap_u8(&tmN, digits, n_pad, U8_NROW, TS_BN)) return cudaErrorUnknown;
+  U8Params p;
+  p.n = n;
+  p.nq = nq;
+  p.s_max = s_max;
+  p.pieces = reinterpret_cast<const int4*>(d_pieces);
+  p.pos_base = pos_base;
+  p.cand = cand;
+  p.cand_cnt = cand_cnt;
+  p.cand_thr = cand_thr;
+  int kp_default;
+  tc_candidate_shape(k, &kp_default, &p.cap);
+  if (p.cap < 128) return cudaErrorInvalidValue;
+  p.kprime = std::max(k + 1, std::min(kprime, kp_default));
+  p.slack = std::max(8, p.kprime / 2);
+  p.hwm = std::min(p.cap / 2, std::max(64, 3 * p.kprime));
+  p.refresh_mask = 15;
+  p.gthr = gthr;
+  p.q = q;
+  p.m_half = m_half;
+  p.counters = nullptr;
+  {
+    const char* dbg = nb200_env("NB200_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  const char* count_env = nb200_env("NB200_TC_COUNT");
+  if (count_env && count_env[0] == '1') {  // diagnostics only: prints the sums of the previous launch
+    static unsigned long long* d_ctr = nullptr;
+    if (!d_ctr) {
+      cudaMalloc(&d_ctr, 256);
+    } else {
+      unsigned long long h[18];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost);
+      const double c = (double)n_cta;
+      fprintf(stderr, "tc_scan_u8: slow-path tiles (lane 0s) %llu, forced compactions %llu, deferred %llu | cycles per CTA: mma wait-tempty "
+                      "%.0f wait-full %.0f issue %.0f | epilogue (per warp) wait-tfull %.0f drain %.0f process %.0f\n",
+              h[1], h[2], h[3], h[11] / c, h[12] / c, h[13] / c, h[14] / c / 8, h[15] / c / 8, h[16] / c / 8);
+    }
+    cudaMemsetAsync(d_ctr, 0, 256, stream);
+    p.counters = d_ctr;
+  }
+  p.n_stage = 16;
+  const size_t smem = 1024 + (size_t)p.n_stage * U8_STAGE + (2 * 16 + 4 * U8_NBUF + 2) * 8 + 16;
+  cudaError_t e;
+#define NB_U8(KPL, REG)                                                                                          \
+  e = cudaFuncSetAttribute(tc_scan_u8_kernel<KPL, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e != cudaSuccess) return e;                                                                                \
+  tc_scan_u8_kernel<KPL, REG><<<n_cta, TS_THREADS, smem, stream>>>(tmB, tmN, p);
+  if (k + 4 <= TS_RK && kprime <= k + 6 && p.cap == 256) {
+    p.kprime = TS_RK;
+    p.slack = 8;
+    NB_U8(8, true);
+  } else if (p.cap == 256) {
+    NB_U8(8, false);
+  } else {
+    NB_U8(16, false);
+  }
+#undef NB_U8
+  e = cudaGetLastError();
+  if (e != cudaSuccess)
+    fprintf(stderr, "nmslib_b200: tc_scan_u8 launch (grid %d, smem %zu) failed: %s\n", n_cta, smem, cudaGetErrorString(e));
+  return e;
+}
 
 int tc_block_queries() { return TC_QB; }
 int tc_block_points() { return TC_BN; }
@@ -2254,7 +2797,8 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
                              uint64_t* out_keys, int* out_cert, cudaStream_t stream, int q_begin, int q_count,
-                             int n_lists, float eps_override) {
+                             int n_lists, float eps_override, int* fb_count, int* fb_idx, const uint8_t* db_u8,
+                             const uint8_t* q_u8, float abs_err, int int_keys) {
   if (nq <= 0) return cudaSuccess;
   if (q_count < 0) q_count = nq - q_begin;
   if (q_count <= 0) return cudaSuccess;
@@ -2262,6 +2806,12 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
   RerankParams p;
   p.q_begin = q_begin;
   p.n_lists = n_lists;
+  p.fb_count = fb_count;
+  p.fb_idx = fb_idx;
+  p.db_u8 = db_u8;
+  p.q_u8 = q_u8;
+  p.abs_err = abs_err;
+  p.int_keys = int_keys;
   p.db = db;
   p.queries = queries;
   p.db_norm2 = db_norm2;

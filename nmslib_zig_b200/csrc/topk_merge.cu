@@ -25,8 +25,9 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ keys, const int32
                                   int items_pow2, int finalize, const int32_t* __restrict__ ext_ids,
                                   uint32_t pos_base, uint64_t* __restrict__ out_keys,
                                   int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
-                                  int32_t* __restrict__ out_counts) {
+                                  int32_t* __restrict__ out_counts, const int* __restrict__ d_nq) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (d_nq && (int)blockIdx.x >= *d_nq) return;  // (query count decided on the device)
   uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
   int32_t* sid = reinterpret_cast<int32_t*>(sk + items_pow2);
   const int q = blockIdx.x;
@@ -99,18 +100,38 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ keys, const int32
 }  // namespace
 
 namespace {
+// d_count (optional): the number of rows is decided on the device; rows [count, count rounded up to `pad`) are
+// zero-filled so that the consumer's last query block reads defined padding, blocks past that leave at once
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, int count,
-                                   int row_vec, uint4* __restrict__ dst) {
+                                   int row_vec, uint4* __restrict__ dst, const int* __restrict__ d_count, int pad) {
   const int r = blockIdx.x;
-  if (r >= count) return;
+  if (d_count) {
+    const int c = min(count, *d_count);
+    if (r >= c) {
+      if (r < (c + pad - 1) / pad * pad) {
+        uint4* d = dst + (size_t)r * row_vec;
+        for (int j = threadIdx.x; j < row_vec; j += blockDim.x) d[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      return;
+    }
+  } else if (r >= count) {
+    return;
+  }
   const uint4* s = src + (size_t)idx[r] * row_vec;
   uint4* d = dst + (size_t)r * row_vec;
   for (int c = threadIdx.x; c < row_vec; c += blockDim.x) d[c] = s[c];
 }
 __global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, const int* __restrict__ idx, int count, int k,
-                                    uint64_t* __restrict__ dst) {
+                                    uint64_t* __restrict__ dst, const int* __restrict__ d_count, int f2i) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_count) count = min(count, *d_count);
   if (i >= count * k) return;
+  if (f2i) {
+    const int r = i / k, e = i - r * k;
+    const uint64_t key = src[i];
+    dst[(size_t)idx[r] * k + e] = key == KEY_MAX ? key : make_key(i32_ordered((int)f32_from_ordered((uint32_t)(key >> 32))), (uint32_t)key);
+    return;
+  }
   const int r = i / k, e = i - r * k;
   dst[(size_t)idx[r] * k + e] = src[i];
 }
@@ -138,17 +159,18 @@ cudaError_t launch_widen_u8(const uint8_t* src, size_t rows, int dim, int row_wo
 }
 
 cudaError_t launch_gather_rows(const uint32_t* src, const int* idx, int count, int row_words, uint32_t* dst,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, const int* d_count, int pad) {
   if (count <= 0) return cudaSuccess;
-  gather_rows_kernel<<<count, 64, 0, stream>>>(reinterpret_cast<const uint4*>(src), idx, count, row_words / 4,
-                                               reinterpret_cast<uint4*>(dst));
+  const int blocks = d_count ? (count + pad - 1) / pad * pad : count;
+  gather_rows_kernel<<<blocks, 64, 0, stream>>>(reinterpret_cast<const uint4*>(src), idx, count, row_words / 4,
+                                                reinterpret_cast<uint4*>(dst), d_count, pad);
   return cudaGetLastError();
 }
 cudaError_t launch_scatter_keys(const uint64_t* src, const int* idx, int count, int k, uint64_t* dst,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, const int* d_count, int f2i) {
   if (count <= 0) return cudaSuccess;
   const int total = count * k;
-  scatter_keys_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, idx, count, k, dst);
+  scatter_keys_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, idx, count, k, dst, d_count, f2i);
   return cudaGetLastError();
 }
 
@@ -157,7 +179,7 @@ int merge_topk_max_items() { return MAX_ITEMS; }
 cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int lists, size_t list_stride,
                               size_t query_stride, int nq, int k, int finalize, const int32_t* ext_ids,
                               uint32_t pos_base, uint64_t* out_keys, int32_t* out_ids, float* out_dists,
-                              int32_t* out_counts, cudaStream_t stream) {
+                              int32_t* out_counts, cudaStream_t stream, const int* d_nq) {
   if (nq <= 0) return cudaSuccess;
   const int items = lists * k;
   if (items > MAX_ITEMS) return cudaErrorInvalidValue;
@@ -172,7 +194,7 @@ cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int l
   if (e != cudaSuccess) return e;
   merge_topk_kernel<<<nq, threads, smem, stream>>>(keys, ids_in, lists, list_stride, query_stride, nq, k, p2,
                                                    finalize, ext_ids, pos_base, out_keys, out_ids, out_dists,
-                                                   out_counts);
+                                                   out_counts, d_nq);
   return cudaGetLastError();
 }
 

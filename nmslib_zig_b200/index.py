@@ -66,7 +66,8 @@ class Stats(C.Structure):
                 ("fallback_queries", C.c_uint64), ("device_bytes", C.c_uint64), ("last_scan_ms", C.c_double),
                 ("scan_ms_sum", C.c_double), ("scan_count", C.c_uint64), ("build_total_ms", C.c_double),
                 ("build_scan_ms", C.c_double), ("build_select_ms", C.c_double), ("build_link_ms", C.c_double),
-                ("build_batches", C.c_uint64), ("build_prunes", C.c_uint64), ("split_queries", C.c_uint64)]
+                ("build_batches", C.c_uint64), ("build_prunes", C.c_uint64), ("split_queries", C.c_uint64),
+                ("u8_imma", C.c_uint64)]
 
 
 # every symbol include/nmslib_b200.h declares (the CPU-side test checks this list against the header)
@@ -86,6 +87,7 @@ EXT_SYMBOLS = [
     "nmslib_b200_set_device", "nmslib_b200_device_available", "nmslib_b200_set_shard", "nmslib_b200_import_hnsw",
     "nmslib_b200_prepare", "nmslib_b200_knn_device", "nmslib_b200_merge_topk", "nmslib_b200_get_stats",
     "nmslib_b200_version", "nmslib_b200_scan_plan", "nmslib_b200_scan_plan_pairs", "nmslib_b200_set_option",
+    "nmslib_b200_shard_export", "nmslib_b200_shard_connect", "nmslib_b200_shard_disconnect",
 ]
 
 _lib = None
@@ -176,6 +178,9 @@ def lib() -> C.CDLL:
         "nmslib_b200_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "nmslib_b200_version": (C.c_char_p, []),
         "nmslib_b200_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+        "nmslib_b200_shard_export": (C.c_int, [vp, sz, sz, vp]),
+        "nmslib_b200_shard_connect": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "nmslib_b200_shard_disconnect": (C.c_int, [vp]),
         "nmslib_b200_scan_plan": (sz, [sz, sz, sz, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "nmslib_b200_scan_plan_pairs": (sz, [sz, sz, sz, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     }
@@ -481,6 +486,22 @@ class Index:
         """Device-resident query: raw device pointers (e.g. torch.Tensor.data_ptr())."""
         _check(lib().nmslib_b200_knn_device(self.handle, d_queries_ptr, nq, dim, k, d_ids_ptr, d_dists_ptr,
                                             d_keys_ptr or None, stream or None))
+
+    # -- row shards across processes (one rank per GPU): include/nmslib_b200.h, mode (B) --------------------
+    def shardExport(self, max_queries: int, max_k: int) -> bytes:
+        """This rank's exchange window; returns the 256-byte blob the launcher all-gathers."""
+        blob = C.create_string_buffer(256)
+        _check(lib().nmslib_b200_shard_export(self.handle, max_queries, max_k, blob))
+        return blob.raw
+
+    def shardConnect(self, rank: int, world: int, blobs: bytes):
+        """blobs = the ranks' blobs concatenated in rank order; afterwards every knn call returns the global top-k."""
+        assert len(blobs) == 256 * world
+        buf = C.create_string_buffer(bytes(blobs), len(blobs))
+        _check(lib().nmslib_b200_shard_connect(self.handle, rank, world, buf))
+
+    def shardDisconnect(self):
+        _check(lib().nmslib_b200_shard_disconnect(self.handle))
 
     def mergeTopk(self, d_keys_ptr: int, d_ids_ptr: int, lists: int, nq: int, k: int, d_out_ids_ptr: int,
                   d_out_dists_ptr: int, stream: int = 0):

@@ -452,3 +452,74 @@ def test_two_half_shards_on_one_gpu_merge_to_the_unsharded_answer():
     assert_knn_matches(w.ids, w.distances, w.sizes, oi, od, oc, what="two half shards")
     for idx in shards + [whole]:
         idx.deinit()
+
+
+def test_device_entry_reruns_uncertified_queries_without_the_host():
+    """nmslib_b200_knn_device never synchronises: the re-rank lists the uncertified queries on the device and gather ->
+    exact scan -> merge -> scatter run predicated on that count.  Near-duplicate rows (differences far below the TF32
+    bound) force the path; the count reaches the statistics afterwards; answers equal the host entry's and the oracle's."""
+    import torch
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(11)
+    base = rng.random((1, 128), dtype=np.float32)
+    dup = base + rng.normal(0, 1e-6, (6_000, 128)).astype(np.float32)
+    data = np.concatenate([dup, synth.uniform(14_000, 128, 1)]).astype(np.float32)
+    rng.shuffle(data, axis=0)
+    q = np.concatenate([base + rng.normal(0, 1e-6, (40, 128)).astype(np.float32), synth.uniform(300, 128, 2)])
+    nq, k = len(q), 10
+    idx = make_index("l2", data)
+    d_q = torch.from_numpy(q).to(dev)
+    d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    d_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    st0 = idx.stats()["fallback_queries"]
+    for _ in range(3):
+        idx.knnDevice(d_q.data_ptr(), nq, 128, k, d_ids.data_ptr(), d_d.data_ptr(), 0, 0)
+    idx.prepare()
+    torch.cuda.synchronize(dev)
+    oi, od, oc = O.seq_knn("l2", data, q, k)
+    dist_of = lambda qi, i: O.pair_distance("l2", data[i], q[qi])
+    assert_knn_matches(d_ids.cpu().numpy(), d_d.cpu().numpy(), oc, oi, od, oc, dist_of=dist_of, what="device entry, near-duplicates")
+    import time
+    time.sleep(0.05)
+    assert idx.stats()["fallback_queries"] - st0 >= 3 * 40, "the near-duplicate queries cannot have been certified"
+    r = idx.knnQueryBatch(q, k)
+    assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, dist_of=dist_of, what="host entry, near-duplicates")
+    idx.deinit()
+
+
+def test_uint8_on_the_integer_tensor_pipe_equals_the_widened_path_bit_for_bit():
+    """l2sqr_sift runs on tcgen05.mma.kind::i8 by default (byte rows, norm digits folded into the MMA); option
+    u8_imma=0 keeps the round-1 path (rows widened to TF32 operands).  Same ids, same int32 distances, ties included;
+    rows whose norms exceed the digit block (all-255 vectors) fall back to the widened path on their own."""
+    rng = np.random.default_rng(5)
+    n, nq = 70_001, 700
+    data, q = synth.sift_like_u8(n, 7), synth.sift_like_u8(nq, 8)
+    data[1000:1010] = data[10:20]                      # exact ties across tiles
+    q[:10] = data[10:20]
+    q[10] = 0
+    data[5] = 0
+    outs = {}
+    for mode in (1, 0):
+        nb.set_option("u8_imma", mode)
+        idx = make_index("l2sqr_sift", data)
+        for k in (10, 100):
+            r = idx.knnQueryBatch(q, k)
+            outs[(mode, k)] = (r.ids.copy(), r.distances.copy())
+        assert idx.stats()["u8_imma"] == mode
+        assert idx.stats()["fallback_queries"] <= 0.02 * nq
+        idx.deinit()
+    nb.set_option("u8_imma", 1)
+    for k in (10, 100):
+        assert np.array_equal(outs[(1, k)][0], outs[(0, k)][0]) and np.array_equal(outs[(1, k)][1], outs[(0, k)][1])
+        oi, od, oc = O.seq_knn("l2sqr_sift", data, q, k)
+        assert_knn_matches(outs[(1, k)][0], outs[(1, k)][1], oc, oi, od, oc, exact=True, what=f"imma k={k}")
+    # the extreme: rows of 255s (|x|^2 = 128 * 255^2 is more than the digit block carries) -> widened path, still exact
+    ext = np.concatenate([data[:5000], np.full((8, 128), 255, np.uint8)])
+    qe = np.concatenate([q[:50], np.full((2, 128), 255, np.uint8), np.zeros((1, 128), np.uint8)])
+    idx = make_index("l2sqr_sift", ext)
+    r = idx.knnQueryBatch(qe, 10)
+    assert idx.stats()["u8_imma"] == 0
+    oi, od, oc = O.seq_knn("l2sqr_sift", ext, qe, 10)
+    assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, exact=True, what="255-extreme")
+    assert r.distances[52].max() <= 128 * 255 ** 2
+    idx.deinit()
