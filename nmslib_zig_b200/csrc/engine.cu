@@ -137,6 +137,7 @@ Engine::~Engine() {
     b->release();
   d_fb_cnt_.release();
   d_digits_.release();
+  d_glists_.release();
   for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_, &h_fb_cnt_}) b->release();
   for (auto& e : fb_ev_)
     if (e) cudaEventDestroy(e);
@@ -802,10 +803,14 @@ Status Engine::run_seq_exact(const void* dq, size_t nq, size_t k, uint64_t* out_
   }
   s = check_cuda(d_partial_.ensure(nq * (size_t)n_split * k * 8), "cudaMalloc(partial)");
   if (!s.ok()) return s;
-  const bool dominant = force_exact_ || space_ == SPACE_L1 || space_ == SPACE_LINF;
+  const bool dominant = force_exact_ || space_ == SPACE_L1 || space_ == SPACE_LINF || k > (size_t)tc_max_k();
+  // k beyond what the shared-memory lists hold: the blocks keep their sorted lists in a global scratch array
+  const size_t gl_bytes = scan_exact_glists_bytes((int)nq, (int)k, n_split);
+  if (gl_bytes && !(s = check_cuda(d_glists_.ensure(gl_bytes), "cudaMalloc(large-k lists)")).ok()) return s;
   if (dominant) scan_begin(stream);
   s = check_cuda(launch_scan_exact(mode, d_db_.p, dq, d_aux_.p, q_aux, (int)n_dev_, (int)nq, row_words_, (int)k,
-                                   pos_base_, d_partial_.as<uint64_t>(), n_split, tiles_per_split, stream, d_nq),
+                                   pos_base_, d_partial_.as<uint64_t>(), n_split, tiles_per_split, stream, d_nq,
+                                   gl_bytes ? d_glists_.as<uint64_t>() : nullptr),
                  "scan_exact");
   if (dominant) scan_end(stream);
   if (!s.ok()) return s;
@@ -1130,7 +1135,7 @@ Status Engine::knn_device(const void* d_queries, size_t nq, size_t elem_count, s
   // k never come into play)
   const bool approx_tc = approx_ok_ && !force_exact_ && k <= (size_t)tc_max_k();
   if (method_ == METHOD_SEQ && !approx_tc && k > (size_t)scan_exact_max_k())
-    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported yet");
+    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported");
   if (method_ == METHOD_HNSW && k > (size_t)hnsw_max_ef()) return Status::Err(kErrTooLarge, "k too large for hnsw");
   if (is_u8_ && method_ == METHOD_HNSW)
     return Status::Err(kErrIncompat, "device-resident uint8 queries are not supported for hnsw (use the host entry)");
@@ -1209,7 +1214,7 @@ Status Engine::knn_host_slice(const void* queries, size_t nq, size_t elem_count,
   if (elem_count != (size_t)dim_)
     return Status::Err(kErrQuery, "query length " + std::to_string(elem_count) + " != index dimension " + std::to_string(dim_));
   if (k > (size_t)scan_exact_max_k())
-    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported yet");
+    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported");
   const size_t out_n = nq * k;
   if (!(s = check_cuda(d_out_ids_.ensure(out_n * 4), "cudaMalloc(out ids)")).ok()) return s;
   if (!(s = check_cuda(d_out_dists_.ensure(out_n * 4), "cudaMalloc(out dists)")).ok()) return s;
@@ -1243,7 +1248,7 @@ Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_
     return Status::Err(kErrQuery, "query length " + std::to_string(elem_count) + " != index dimension " +
                                       std::to_string(dim_));
   if (method_ == METHOD_SEQ && k > (size_t)scan_exact_max_k())
-    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported yet");
+    return Status::Err(kErrTooLarge, "k above " + std::to_string(scan_exact_max_k()) + " is not supported");
   if (method_ == METHOD_HNSW && k > (size_t)hnsw_max_ef()) return Status::Err(kErrTooLarge, "k too large for hnsw");
 
   const size_t out_n = nq * k;

@@ -284,6 +284,7 @@ class Engine {
   bool u8_imma_ = false;   // uint8 + seq_search on the integer tensor pipe (decided at upload from the rows' norms)
   int u8_m_half_ = 0;      // M = ceil(max |x|^2 / 2) of the uploaded rows
   DevBuf d_digits_;        // [n_pad][32] norm digits (scan_tc.cu: u8_norm_digits_kernel)
+  DevBuf d_glists_;        // exact scan with k > 144: the blocks' sorted lists (scan_exact.cu)
   bool approx_ok_ = false, rows_borrowed_ = false, dry_run_ = false;
   HnswBuildInfo build_info_;
   size_t n_dev_ = 0;

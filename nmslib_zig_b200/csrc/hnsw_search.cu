@@ -29,7 +29,7 @@ namespace nb200 {
 namespace {
 
 constexpr int WARPS = 4;          // warps (queries in flight) per block
-constexpr int MAX_EF = 2048;      // beam capacity limit (shared memory)
+constexpr int MAX_EF = 6144;      // beam capacity limit: 4 warps x (row + 8 B per beam entry) must fit 227 KB of shared memory
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int USED_BIT = 0x80000000;
 
@@ -571,6 +571,7 @@ cudaError_t launch_hnsw_search(const HnswDeviceGraph& g, const float* queries, i
   const int cap_r = (cap + 31) / 32 * 32;
   const size_t per_warp = (size_t)g.row_words * 4 + (size_t)cap_r * 8 + 32 * 4;
   const size_t smem = per_warp * WARPS;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;  // (rows this long leave no room for a beam this wide)
   int blocks = slots / WARPS;
   const int need = (nq + WARPS - 1) / WARPS;
   if (blocks > need) blocks = need;

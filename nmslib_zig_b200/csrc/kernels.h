@@ -39,8 +39,11 @@ enum ScanMode : int { SCAN_L2 = 0, SCAN_NEGDOT = 1, SCAN_COSINE = 2, SCAN_SIFT =
 cudaError_t launch_scan_exact(int mode, const void* db, const void* queries, const void* db_aux,
                               const void* q_aux, int n, int nq, int row_words, int k, uint32_t pos_base,
                               uint64_t* partial, int n_split, int tiles_per_split, cudaStream_t stream,
-                              const int* d_nq = nullptr);  // d_nq: query count read on the device (<= nq)
+                              const int* d_nq = nullptr,   // d_nq: query count read on the device (<= nq)
+                              uint64_t* glists = nullptr);  // k > scan_exact_smem_k(): scratch of scan_exact_glists_bytes()
 int scan_exact_max_k();
+int scan_exact_smem_k();
+size_t scan_exact_glists_bytes(int nq, int k, int n_split);
 int scan_exact_block_queries();
 int scan_exact_block_points();
 int scan_exact_stage_words();

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(NT, (MODE == SCAN_SIFT) ? 1 : 1)
 scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ qs,
                   const void* __restrict__ db_aux_v, const void* __restrict__ q_aux_v, int n, int nq,
                   int row_words, int k, int tiles_per_split, uint32_t pos_base,
-                  uint64_t* __restrict__ partial, int n_split, const int* __restrict__ d_nq) {
+                  uint64_t* __restrict__ partial, int n_split, const int* __restrict__ d_nq,
+                  uint64_t* __restrict__ glists) {
   using acc_t = typename Acc<MODE>::type;
   if (d_nq) {  // query count decided on the device (the re-run of uncertified queries): surplus blocks leave at once
     nq = min(nq, *d_nq);
@@ -99,8 +100,11 @@ scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
   }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw);                     // NSTAGE*(BQ+BN)*LDW
-  uint64_t* lists = reinterpret_cast<uint64_t*>(tiles + NSTAGE * (BQ + BN) * LDW);  // BQ*k
-  uint64_t* thr_key = lists + (size_t)BQ * k;                                   // BQ
+  // per-query sorted lists: BQ * k keys in shared memory, or -- k above scan_exact_smem_k(): the reference's KNNQueue
+  // has no capacity limit (knnqueue.h:55-64) -- this block's slice of a global scratch array (slower, but unbounded)
+  uint64_t* slists = reinterpret_cast<uint64_t*>(tiles + NSTAGE * (BQ + BN) * LDW);
+  uint64_t* lists = glists ? glists + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)BQ * k : slists;
+  uint64_t* thr_key = slists + (glists ? 0 : (size_t)BQ * k);                   // BQ
   uint64_t* qkey = thr_key + BQ;                                                // QCAP
   uint32_t* thr_fast = reinterpret_cast<uint32_t*>(qkey + QCAP);                // BQ (bit pattern)
   int* cnt = reinterpret_cast<int*>(thr_fast + BQ);                             // BQ
@@ -326,20 +330,27 @@ scan_exact_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
   }
 }
 
+constexpr int SMEM_K = 144;  // largest k whose lists fit shared memory
 size_t scan_exact_smem(int k) {
-  return (size_t)NSTAGE * (BQ + BN) * LDW * 4 + (size_t)BQ * k * 8 + BQ * 8 + QCAP * 8 + BQ * 4 + BQ * 4 +
+  return (size_t)NSTAGE * (BQ + BN) * LDW * 4 + (size_t)BQ * (k <= SMEM_K ? k : 0) * 8 + BQ * 8 + QCAP * 8 + BQ * 4 + BQ * 4 +
          QCAP * 2 + 64;
 }
 
 }  // namespace
 
-int scan_exact_max_k() { return 144; }
+int scan_exact_max_k() { return 8192; }   // (what the finalising merge sorts in one block)
+int scan_exact_smem_k() { return SMEM_K; }
+size_t scan_exact_glists_bytes(int nq, int k, int n_split) {
+  return k <= SMEM_K ? 0 : (size_t)n_split * ((nq + BQ - 1) / BQ) * BQ * (size_t)k * 8;
+}
 
 cudaError_t launch_scan_exact(int mode, const void* db, const void* queries, const void* db_aux,
                               const void* q_aux, int n, int nq, int row_words, int k, uint32_t pos_base,
                               uint64_t* partial, int n_split, int tiles_per_split, cudaStream_t stream,
-                              const int* d_nq) {
+                              const int* d_nq, uint64_t* glists) {
   if (nq <= 0 || n <= 0) return cudaSuccess;
+  if (k > SMEM_K && !glists) return cudaErrorInvalidValue;
+  if (k <= SMEM_K) glists = nullptr;
   const size_t smem = scan_exact_smem(k);
   dim3 grid(n_split, (nq + BQ - 1) / BQ);
   const uint32_t* d = static_cast<const uint32_t*>(db);
@@ -349,7 +360,7 @@ cudaError_t launch_scan_exact(int mode, const void* db, const void* queries, con
   e = cudaFuncSetAttribute(scan_exact_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return e;                                                                      \
   scan_exact_kernel<M><<<grid, NT, smem, stream>>>(d, q, db_aux, q_aux, n, nq, row_words, k,           \
-                                                   tiles_per_split, pos_base, partial, n_split, d_nq);
+                                                   tiles_per_split, pos_base, partial, n_split, d_nq, glists);
   switch (mode) {
     case SCAN_L2: NB_LAUNCH(SCAN_L2); break;
     case SCAN_NEGDOT: NB_LAUNCH(SCAN_NEGDOT); break;

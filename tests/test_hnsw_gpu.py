@@ -153,7 +153,7 @@ def test_same_graph_live_reference_ef_sweep(space, n, dim, params, tmp_path):
     exact_ids, _, _ = O.seq_knn(space, data, q, 10)
     idx = nb.Index(space, None, "hnsw")
     idx.importHnsw(path)
-    for ef in (50, 100, 200, 400, 1000):
+    for ef in (50, 100, 200, 400, 1000, 4096):         # (>= 1000: the reference's SearchOld; 4096: above the round-1 cap)
         ref.set_query_params(f"efSearch={ef}")
         ri, rd, rc = ref.knn(q, 10, threads=8)
         idx.setQueryTimeParams(nb.Params({"efSearch": ef}))

@@ -523,3 +523,25 @@ def test_uint8_on_the_integer_tensor_pipe_equals_the_widened_path_bit_for_bit():
     assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, exact=True, what="255-extreme")
     assert r.distances[52].max() <= 128 * 255 ** 2
     idx.deinit()
+
+
+@pytest.mark.parametrize("space,k", [("l2", 200), ("l2", 500), ("negdotprod", 1000), ("l2sqr_sift", 1000), ("cosinesimil", 300)])
+def test_large_k_has_no_cap_like_the_reference_queue(space, k):
+    """KNNQueue grows to any k (knnqueue.h:55-64).  k <= 256 stays on the tensor-core path (the exact re-run of
+    uncertified queries keeps its lists in a global scratch array above 144); larger k runs the exact scan with
+    global lists.  k > n returns n results."""
+    u8 = space == "l2sqr_sift"
+    n, nq = 6_000, 40
+    data = synth.sift_like_u8(n, 7) if u8 else synth.uniform(n, 48, 1)
+    q = synth.sift_like_u8(nq, 8) if u8 else synth.uniform(nq, 48, 2)
+    idx = make_index(space, data)
+    r = idx.knnQueryBatch(q, k)
+    oi, od, oc = O.seq_knn(space, data, q, k)
+    dist_of = lambda qi, i: O.pair_distance(space, data[i], q[qi])
+    assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, exact=u8, dist_of=dist_of, what=f"{space} k={k}",
+                       atol=ATOL_COSINE if space == "cosinesimil" else None)
+    small = make_index(space, data[:300])
+    r = small.knnQueryBatch(q[:5], k)
+    assert np.all(r.sizes == min(k, 300))
+    idx.deinit()
+    small.deinit()
