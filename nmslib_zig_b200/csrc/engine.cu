@@ -302,6 +302,20 @@ Status Engine::set_query_params(const std::vector<std::string>& params) {
 
 Status Engine::adopt_graph(HnswGraph&& g) {
   if (method_ != METHOD_HNSW) return Status::Err(kErrIncompat, "graph import needs method hnsw");
+  if (g.dim == 0 && g.vectors.empty()) {
+    // The reference's REGULAR index (SaveRegularIndexBin, hnsw.cc:810-842: what Hnsw<int>, i.e. l2sqr_sift + hnsw,
+    // saves): links only.  The data set is this index's own; the search is baseSearchAlgorithmV1Merge / Old
+    // (hnsw.cc:1076-1300) -- the same beam rule as the flat index over the space's own distance.
+    if (g.total != n_) return Status::Err(kErrIncompat, "regular HNSW index: " + std::to_string(g.total) + " nodes but " +
+                                                            std::to_string(n_) + " data points (add the data first)");
+    g.dim = dim_;
+    g.dist_func = space_ == SPACE_COSINE ? 3 : space_ == SPACE_NEGDOT ? 4 : (dim_ % 16 == 0 ? 1 : 2);
+    g.ext_ids = h_ids_;
+    graph_ = std::move(g);
+    graph_dirty_ = true;
+    built_ = true;
+    return Status::OK();
+  }
   if (is_u8_) return Status::Err(kErrIncompat, "the optimized HNSW index holds float vectors only");
   const int want = (space_ == SPACE_COSINE) ? 3 : (space_ == SPACE_NEGDOT) ? 4 : 0;
   const bool l2 = (space_ == SPACE_L2 || space_ == SPACE_L2SQR) && (g.dist_func == 1 || g.dist_func == 2);

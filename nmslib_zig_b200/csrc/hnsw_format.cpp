@@ -37,6 +37,75 @@ bool wr(FILE* f, const T& v) {
 constexpr int kErrIO = 10;  // NMSLIB_ERROR_DATA_IO_FAILED
 }  // namespace
 
+namespace {
+// Hnsw::SaveRegularIndexBin (hnsw.cc:810-842): total (u32), maxlevel (i32), enterpoint (u32), M / maxM / maxM0 (size_t),
+// then per node its level and, per level 0..level, the friend count and the friend ids.  No vectors, no external ids:
+// the data set is the caller's (LoadRegularIndexBin CHECKs that the counts agree, hnsw.cc:956-959).  The result has
+// dim == 0 and empty vectors / ext_ids; dist_func is filled in by the engine from the index space.
+Status read_regular(FILE* f, HnswGraph* out) {
+  uint32_t total = 0, enterpoint = 0;
+  int32_t maxlevel = 0;
+  uint64_t M = 0, maxM = 0, maxM0 = 0;
+  if (!(rd(f, &total) && rd(f, &maxlevel) && rd(f, &enterpoint) && rd(f, &M) && rd(f, &maxM) && rd(f, &maxM0)))
+    return Status::Err(kErrIO, "truncated regular HNSW header");
+  if (maxM0 == 0 || maxM0 > 4096 || maxM == 0 || maxM > 4096 || maxlevel < 0 || maxlevel > 64 ||
+      (total > 0 && enterpoint >= total))
+    return Status::Err(kErrIO, "inconsistent regular HNSW header");
+  HnswGraph g;
+  g.total = total;
+  g.dim = 0;
+  g.maxM = (int)maxM;
+  g.maxM0 = (int)maxM0;
+  g.maxlevel = maxlevel;
+  g.enterpoint = enterpoint;
+  g.dist_func = 0;
+  g.links0.assign((size_t)total * g.maxM0, -1);
+  g.links0_cnt.assign(total, 0);
+  g.upper_off.assign(total, -1);
+  std::vector<int32_t> levels(total, 0);
+  std::vector<int32_t> ids;
+  for (uint32_t i = 0; i < total; ++i) {
+    uint32_t level = 0;
+    if (!rd(f, &level) || level > 64) return Status::Err(kErrIO, "corrupt regular HNSW node record");
+    levels[i] = (int32_t)level;
+    if (level > 0) {
+      g.upper_off[i] = (int64_t)g.upper.size();
+      g.upper.resize(g.upper.size() + (size_t)level * (maxM + 1), 0);
+    }
+    for (uint32_t l = 0; l <= level; ++l) {
+      uint32_t cnt = 0;
+      if (!rd(f, &cnt) || cnt > (l == 0 ? maxM0 : maxM)) return Status::Err(kErrIO, "corrupt regular HNSW friend list");
+      ids.resize(cnt);
+      if (cnt && fread(ids.data(), 4, cnt, f) != cnt) return Status::Err(kErrIO, "truncated regular HNSW friend list");
+      for (uint32_t j = 0; j < cnt; ++j)
+        if ((uint32_t)ids[j] >= total) return Status::Err(kErrIO, "regular HNSW friend id out of range");
+      if (l == 0) {
+        g.links0_cnt[i] = (int32_t)cnt;
+        for (uint32_t j = 0; j < cnt; ++j) g.links0[(size_t)i * g.maxM0 + j] = ids[j];
+      } else {
+        int32_t* lk = &g.upper[g.upper_off[i] + (size_t)(l - 1) * (maxM + 1)];
+        lk[0] = (int32_t)cnt;
+        for (uint32_t j = 0; j < cnt; ++j) lk[1 + j] = ids[j];
+      }
+    }
+  }
+  // level consistency (see read_hnsw_file): the descent follows a level-l link only into nodes that have level l
+  if (total > 0 && levels[enterpoint] < maxlevel) {
+    // (hnsw.cc:824-828 notes that maxlevel_ may exceed the entry node's level; the pointer search starts from
+    //  enterpoint_->level, hnsw.cc:1183, so that is the level the descent must use)
+    g.maxlevel = levels[enterpoint];
+  }
+  for (uint32_t i = 0; i < total; ++i)
+    for (int32_t l = 1; l <= levels[i]; ++l) {
+      const int32_t* lk = &g.upper[g.upper_off[i] + (size_t)(l - 1) * (maxM + 1)];
+      for (int j = 1; j <= lk[0]; ++j)
+        if (levels[lk[j]] < l) return Status::Err(kErrIO, "regular HNSW friend does not reach that level");
+    }
+  *out = std::move(g);
+  return Status::OK();
+}
+}  // namespace
+
 Status read_hnsw_file(const std::string& path, HnswGraph* out) {
   FilePtr f(fopen(path.c_str(), "rb"));
   if (!f) return Status::Err(kErrIO, "cannot open HNSW index file " + path);
@@ -44,9 +113,8 @@ Status read_hnsw_file(const std::string& path, HnswGraph* out) {
   uint64_t mem_per_obj = 0, off_level0 = 0, off_data = 0, maxM = 0, maxM0 = 0, search_method = 0;
   int32_t maxlevel = 0, dist_func = 0;
   if (!rd(f.get(), &optimized)) return Status::Err(kErrIO, "truncated HNSW header");
-  if (optimized != 1)
-    return Status::Err(kErrIO,
-                       "not an optimized HNSW index (hnsw.cc:756 flag == 0): only the flat format is supported");
+  if (optimized == 0) return read_regular(f.get(), out);  // the pointer graph of Hnsw<int> / skip_optimized_index
+  if (optimized != 1) return Status::Err(kErrIO, "not an HNSW index file (hnsw.cc:756 flag)");
   if (!(rd(f.get(), &total) && rd(f.get(), &mem_per_obj) && rd(f.get(), &off_level0) &&
         rd(f.get(), &off_data) && rd(f.get(), &maxlevel) && rd(f.get(), &enterpoint) && rd(f.get(), &maxM) &&
         rd(f.get(), &maxM0) && rd(f.get(), &dist_func) && rd(f.get(), &search_method)))

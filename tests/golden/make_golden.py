@@ -115,13 +115,15 @@ def seq_case(name, space, data, queries, k, ids=None):
     print(f"seq_{name}: n={n} dim={data.shape[1]} nq={queries.shape[0]} k={k}")
 
 
-def hnsw_case(name, space, data, queries, k, params, efs, ids=None):
+def hnsw_case(name, space, data, queries, k, params, efs, ids=None, keep_data=False):
     n = data.shape[0]
     ids = np.arange(n, dtype=np.int32) if ids is None else np.asarray(ids, np.int32)
     r = O.RefIndex(space, "hnsw").add(data, ids).build(params)
     path = OUT / f"hnsw_{name}.hnsw"
     r.save(path)
     out = {"space": space, "queries": queries, "k": k, "efs": np.asarray(efs), "params": params}
+    if keep_data:  # the regular (pointer-graph) index file carries no vectors (hnsw.cc:810-842)
+        out["data"], out["ids"] = data, ids
     for ef in efs:
         r.set_query_params(f"efSearch={ef}")
         i, d, c = r.knn(queries, k)
@@ -147,11 +149,22 @@ def extra_spaces():
     seq_case("l1_ties", "l1", d, q, 10)
 
 
+def int_space_hnsw():
+    """l2sqr_sift + hnsw: Hnsw<int> keeps the pointer graph and saves it with SaveRegularIndexBin (hnsw.cc:810-842); the
+    searches are baseSearchAlgorithmV1Merge / Old (hnsw.cc:1076-1300).  `make_golden.py sift` regenerates only this."""
+    hnsw_case("sift_regular", "l2sqr_sift", synth.sift_like_u8(3000, 47), synth.sift_like_u8(64, 48), 10,
+              "M=8,efConstruction=100,indexThreadQty=1", [10, 50, 200, 1000], ids=np.arange(3000) * 2 + 5, keep_data=True)
+
+
 def main():
     assert O.ref_available(), "build oracle/_ref first: make -C oracle ref"
     if len(sys.argv) > 1 and sys.argv[1] == "extra":
         extra_spaces()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "sift":
+        int_space_hnsw()
+        return
+    int_space_hnsw()
     extra_spaces()
     rng = np.random.Generator(np.random.Philox(key=1234))
 

@@ -189,3 +189,37 @@ def test_team_kernel_answers_are_bit_identical_to_the_one_warp_kernel(tmp_path):
         subprocess.run([sys.executable, "-c", script, str(path), mode], check=True, timeout=600)
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_int_space_hnsw_same_graph_parity_with_the_reference():
+    """l2sqr_sift + hnsw is Hnsw<int> in the reference -- the pointer graph, saved by SaveRegularIndexBin
+    (hnsw.cc:810-842) and searched by baseSearchAlgorithmV1Merge / Old (hnsw.cc:1076-1300).  The golden file is that
+    index as the reference wrote it; the kernel must return the reference's ids on it (ties aside) with the exact
+    int32 distances, at every efSearch incl. the SearchOld regime."""
+    g = np.load(GOLDEN / "hnsw_sift_regular.npz")
+    data, ids, q = g["data"], g["ids"], g["queries"]
+    idx = nb.Index("l2sqr_sift", None, "hnsw", "DenseUInt8Vector", "Int")
+    idx.addUInt8Batch(data, ids)
+    idx.importHnsw(GOLDEN / "hnsw_sift_regular.hnsw")
+    exact = g["exact_ids"]
+    pos_of = {int(e): i for i, e in enumerate(ids)}
+    for ef in g["efs"]:
+        idx.setQueryTimeParams(nb.Params({"efSearch": int(ef)}))
+        r = idx.knnQueryBatch(q, 10)
+        ri, rd = g[f"ids_ef{ef}"], g[f"dists_ef{ef}"]
+        assert recall(r.ids, exact) >= recall(ri, exact) - 1e-9, f"ef={ef}"
+        assert agreement(r.ids, ri) >= 0.99, f"ef={ef}: agreement {agreement(r.ids, ri)}"
+        assert np.array_equal(np.sort(r.distances, axis=1), r.distances)
+        for qi in range(0, len(q), 7):                       # reported distances are the exact integer distances
+            for j in range(10):
+                x = data[pos_of[int(r.ids[qi, j])]].astype(np.int64)
+                assert int(r.distances[qi, j]) == int(np.sum((x - q[qi].astype(np.int64)) ** 2))
+        same = r.ids == ri
+        assert np.array_equal(r.distances[same], rd[same])
+    idx.deinit()
+    # a regular index needs its data set first (LoadRegularIndexBin CHECKs the counts, hnsw.cc:956-959)
+    empty = nb.Index("l2sqr_sift", None, "hnsw", "DenseUInt8Vector", "Int")
+    empty.addUInt8Batch(data[:10])
+    with pytest.raises(nb.NmslibError):
+        empty.importHnsw(GOLDEN / "hnsw_sift_regular.hnsw")
+    empty.deinit()

@@ -545,3 +545,27 @@ def test_large_k_has_no_cap_like_the_reference_queue(space, k):
     assert np.all(r.sizes == min(k, 300))
     idx.deinit()
     small.deinit()
+
+
+def test_cosine_error_against_float64_is_no_worse_than_the_reference():
+    """the cosine tolerance (1e-5 absolute on d = 1 - nsp) is justified by measuring both implementations
+    against a float64 ground truth on 960-D rows: the device's error is bounded by the reference's own fp32 error
+    (+1e-6), for every reported (query, neighbour) pair in aggregate and in the mean."""
+    n, nq, dim, k = 20_000, 200, 960, 10
+    data, q = synth.gist_like(n, dim, 5), synth.gist_like(nq, dim, 6)
+    idx = make_index("cosinesimil", data)
+    r = idx.knnQueryBatch(q, k)
+    idx.deinit()
+    x64, q64 = data.astype(np.float64), q.astype(np.float64)
+    err_gpu, err_ref = [], []
+    for qi in range(nq):
+        for j in range(k):
+            i = int(r.ids[qi, j])
+            nsp = float(np.dot(x64[i], q64[qi]) / np.sqrt(np.dot(x64[i], x64[i])) / np.sqrt(np.dot(q64[qi], q64[qi])))
+            d64 = max(0.0, 1.0 - max(-1.0, min(1.0, nsp)))
+            err_gpu.append(abs(float(r.distances[qi, j]) - d64))
+            err_ref.append(abs(O.pair_distance("cosinesimil", data[i], q[qi]) - d64))
+    err_gpu, err_ref = np.array(err_gpu), np.array(err_ref)
+    assert err_gpu.max() <= err_ref.max() + 1e-6, (err_gpu.max(), err_ref.max())
+    assert err_gpu.mean() <= err_ref.mean() + 2e-7, (err_gpu.mean(), err_ref.mean())
+    assert err_gpu.max() <= ATOL_COSINE / 2      # the tolerance the parity tests use has a factor of two to spare
