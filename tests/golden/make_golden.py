@@ -115,11 +115,11 @@ def seq_case(name, space, data, queries, k, ids=None):
     print(f"seq_{name}: n={n} dim={data.shape[1]} nq={queries.shape[0]} k={k}")
 
 
-def hnsw_case(name, space, data, queries, k, params, efs, ids=None, keep_data=False):
+def hnsw_case(name, space, data, queries, k, params, efs, ids=None, keep_data=False, prefix="hnsw_"):
     n = data.shape[0]
     ids = np.arange(n, dtype=np.int32) if ids is None else np.asarray(ids, np.int32)
     r = O.RefIndex(space, "hnsw").add(data, ids).build(params)
-    path = OUT / f"hnsw_{name}.hnsw"
+    path = OUT / f"{prefix}{name}.hnsw"
     r.save(path)
     out = {"space": space, "queries": queries, "k": k, "efs": np.asarray(efs), "params": params}
     if keep_data:  # the regular (pointer-graph) index file carries no vectors (hnsw.cc:810-842)
@@ -131,8 +131,8 @@ def hnsw_case(name, space, data, queries, k, params, efs, ids=None, keep_data=Fa
     # ground truth for recall: seq_search on the same data
     gi, gd, _ = O.RefIndex(space, "seq_search").add(data, ids).build("").knn(queries, k)
     out["exact_ids"], out["exact_dists"] = gi, gd
-    np.savez_compressed(OUT / f"hnsw_{name}.npz", **out)
-    print(f"hnsw_{name}: n={n} dim={data.shape[1]} file={path.stat().st_size} B")
+    np.savez_compressed(OUT / f"{prefix}{name}.npz", **out)
+    print(f"{prefix}{name}: n={n} dim={data.shape[1]} file={path.stat().st_size} B")
 
 
 def extra_spaces():
@@ -152,8 +152,9 @@ def extra_spaces():
 def int_space_hnsw():
     """l2sqr_sift + hnsw: Hnsw<int> keeps the pointer graph and saves it with SaveRegularIndexBin (hnsw.cc:810-842); the
     searches are baseSearchAlgorithmV1Merge / Old (hnsw.cc:1076-1300).  `make_golden.py sift` regenerates only this."""
-    hnsw_case("sift_regular", "l2sqr_sift", synth.sift_like_u8(3000, 47), synth.sift_like_u8(64, 48), 10,
-              "M=8,efConstruction=100,indexThreadQty=1", [10, 50, 200, 1000], ids=np.arange(3000) * 2 + 5, keep_data=True)
+    hnsw_case("hnsw_sift", "l2sqr_sift", synth.sift_like_u8(3000, 47), synth.sift_like_u8(64, 48), 10,
+              "M=8,efConstruction=100,indexThreadQty=1", [10, 50, 200, 1000], ids=np.arange(3000) * 2 + 5, keep_data=True,
+              prefix="regular_")  # (not hnsw_*: the oracle's port of the search reads the optimized flat format only)
 
 
 def main():

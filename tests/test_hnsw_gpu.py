@@ -196,11 +196,11 @@ def test_int_space_hnsw_same_graph_parity_with_the_reference():
     (hnsw.cc:810-842) and searched by baseSearchAlgorithmV1Merge / Old (hnsw.cc:1076-1300).  The golden file is that
     index as the reference wrote it; the kernel must return the reference's ids on it (ties aside) with the exact
     int32 distances, at every efSearch incl. the SearchOld regime."""
-    g = np.load(GOLDEN / "hnsw_sift_regular.npz")
+    g = np.load(GOLDEN / "regular_hnsw_sift.npz")
     data, ids, q = g["data"], g["ids"], g["queries"]
     idx = nb.Index("l2sqr_sift", None, "hnsw", "DenseUInt8Vector", "Int")
     idx.addUInt8Batch(data, ids)
-    idx.importHnsw(GOLDEN / "hnsw_sift_regular.hnsw")
+    idx.importHnsw(GOLDEN / "regular_hnsw_sift.hnsw")
     exact = g["exact_ids"]
     pos_of = {int(e): i for i, e in enumerate(ids)}
     for ef in g["efs"]:
@@ -221,5 +221,5 @@ def test_int_space_hnsw_same_graph_parity_with_the_reference():
     empty = nb.Index("l2sqr_sift", None, "hnsw", "DenseUInt8Vector", "Int")
     empty.addUInt8Batch(data[:10])
     with pytest.raises(nb.NmslibError):
-        empty.importHnsw(GOLDEN / "hnsw_sift_regular.hnsw")
+        empty.importHnsw(GOLDEN / "regular_hnsw_sift.hnsw")
     empty.deinit()
