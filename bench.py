@@ -443,9 +443,15 @@ def run_seq(args, w, rank, world, local_rank, dev, dist_on, steps, warmup, with_
     idx = nb.Index(w["space"], None, w["method"], w["dtype"], w["dist"])
     idx.setShard(lo)                                   # keys carry GLOBAL positions (tie order)
     shard_ids = np.arange(lo, hi, dtype=np.int32)
+    t_ing = time.perf_counter()
     (idx.addUInt8Batch if u8 else idx.addDenseBatch)(w["data"], shard_ids)   # (w["data"] is this rank's shard)
+    t_add = time.perf_counter() - t_ing
     idx.buildIndex()
-    idx.prepare()
+    idx.prepare()                                      # upload + operand preparation (the ingest path)
+    t_ing = time.perf_counter() - t_ing
+    ingest = {"rows": int(hi - lo), "seconds": t_ing, "add_seconds": t_add, "rows_per_s": (hi - lo) / t_ing,
+              "gbytes_per_s": w["data"].nbytes / t_ing / 1e9,
+              "what": "nmslib_add_data_point_batch (one slab copy on the host) + upload + operand preparation, one rank"}
 
     q_host = torch.from_numpy(w["queries"]).pin_memory()
     d_q = q_host.to(dev, non_blocking=False)
@@ -596,7 +602,7 @@ def run_seq(args, w, rank, world, local_rank, dev, dist_on, steps, warmup, with_
                        "l2_policy": f"inputs larger than L2 ({(hi - lo) * dim * (1 if u8 else 4) / 1e6:.0f} MB scanned per step)"},
             "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(q_np.nbytes), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "ingest": ingest,
             "uncertified_queries_per_step": (st1["fallback_queries"] - st0["fallback_queries"]) / steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s" if imma else "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "scan", "kernel_ms": scan_ms,

@@ -281,6 +281,7 @@ typedef struct {
   uint64_t build_prunes;     /* neighbour lists re-pruned because they overflowed */
   uint64_t split_queries;    /* queries re-run by the 3xTF32 (split operand) scan after a failed certificate */
   uint64_t u8_imma;          /* 1: uint8 rows are scanned on the integer tensor pipe (tcgen05.mma.kind::i8), 0: widened to TF32 */
+  uint64_t uploaded_rows;    /* rows copied host -> device so far (an append uploads only the new rows) */
 } nmslib_b200_stats_t;
 nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_stats_t* out);
 

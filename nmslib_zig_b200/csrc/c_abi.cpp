@@ -816,6 +816,7 @@ nmslib_error_t nmslib_b200_get_stats(nmslib_index_handle_t index, nmslib_b200_st
   out->build_batches = (uint64_t)bi.batches;
   out->build_prunes = bi.prunes;
   out->split_queries = s.split_queries;
+  out->uploaded_rows = s.uploaded_rows;
   out->u8_imma = (!index->group && index->engine->is_u8() && index->engine->method() == nb200::METHOD_SEQ &&
                   index->engine->u8_imma()) ? 1 : 0;
   return NMSLIB_SUCCESS;

@@ -83,6 +83,26 @@ cudaError_t DevBuf::ensure(size_t bytes, bool zero_new, cudaStream_t s) {
   if (zero_new) return cudaMemsetAsync(p, 0, want, s);
   return cudaSuccess;
 }
+// grow without losing the contents (append-only uploads): new allocation, device copy, old one freed
+cudaError_t DevBuf::ensure_keep(size_t bytes, cudaStream_t s) {
+  if (bytes <= cap) return cudaSuccess;
+  if (borrowed) return cudaErrorInvalidValue;
+  if (!p) return ensure(bytes);
+  const size_t want = std::max(round_up(bytes, 256), round_up(cap + cap / 2, 256));
+  void* np = nullptr;
+  cudaError_t e = cudaMalloc(&np, want);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    cudaFree(np);
+    return e;
+  }
+  cudaFree(p);
+  p = np;
+  cap = want;
+  return cudaSuccess;
+}
 void DevBuf::release() {
   if (p && !borrowed) cudaFree(p);
   p = nullptr;
@@ -162,6 +182,7 @@ Status Engine::check_cuda(cudaError_t e, const char* what) {
 // ------------------------------------------------------------------------------------ ingest
 Status Engine::add_rows(const void* rows, size_t count, size_t elem_count, const int32_t* ids) {
   if (!rows || count == 0 || elem_count == 0) return Status::Err(kErrInvalid, "empty batch");
+  if (borrowed_rows_) return Status::Err(kErrInvalid, "a shard that borrows its rows cannot grow");
   if (is_u8_ && elem_count != 128)  // space_l2sqr_sift.cc:137 CHECK (SIFT_DIM)
     return Status::Err(13, "SIFT vectors must have 128 elements");
   if (dim_ == 0) dim_ = (int)elem_count;
@@ -189,6 +210,19 @@ Status Engine::add_rows(const void* rows, size_t count, size_t elem_count, const
   return Status::OK();
 }
 
+Status Engine::borrow_host_rows(const void* rows, const int32_t* ids, size_t count, size_t elem_count) {
+  if (!rows || !ids || count == 0 || elem_count == 0) return Status::Err(kErrInvalid, "empty shard");
+  if (method_ != METHOD_SEQ) return Status::Err(kErrIncompat, "only seq_search shards borrow their rows");
+  if (n_ != 0) return Status::Err(kErrInvalid, "borrow_host_rows on a non-empty engine");
+  dim_ = (int)elem_count;
+  n_ = count;
+  borrowed_rows_ = rows;
+  borrowed_ids_ = ids;
+  data_dirty_ = true;
+  ++data_gen_;
+  return Status::OK();
+}
+
 Status Engine::add_row_ptrs(const void* const* ptrs, size_t count, size_t elem_count, const int32_t* ids) {
   if (!ptrs || count == 0) return Status::Err(kErrInvalid, "empty pointer batch");
   for (size_t i = 0; i < count; ++i) {
@@ -204,6 +238,8 @@ void Engine::reset() {
   h_f32_.clear();
   h_u8_.clear();
   h_ids_.clear();
+  borrowed_rows_ = nullptr;
+  borrowed_ids_ = nullptr;
   n_ = 0;
   dim_ = 0;
   built_ = false;
@@ -213,6 +249,8 @@ void Engine::reset() {
   rows_normalized_ = false;
   h_hnsw_rows_.clear();
   d_q_dim_ = -1;  // the staged-query buffer is re-zeroed before its next use (stale padding columns)
+  upload_valid_ = false;
+  n_up_ = 0;
   ++data_gen_;
 }
 
@@ -330,6 +368,7 @@ Status Engine::adopt_graph(HnswGraph&& g) {
   h_ids_ = graph_.ext_ids;
   graph_.vectors.clear();
   graph_.vectors.shrink_to_fit();
+  upload_valid_ = false;
   rows_normalized_ = true;  // the file stores cosine rows already normalised
   h_hnsw_rows_.clear();
   data_dirty_ = graph_dirty_ = true;
@@ -455,45 +494,57 @@ Status Engine::upload_data() {
   if (dev_u8 && dim_ % 4) return Status::Err(kErrInvalid, "uint8 dimension must be a multiple of 4");
   const size_t n_pad = round_up(n_, bn);
   const size_t row_bytes = (size_t)row_words_ * 4;
-  Status s = check_cuda(d_db_.ensure(n_pad * row_bytes), "cudaMalloc(data)");
+  // Append-only upload: rows [0, n_up_) of a seq_search index are already in HBM in this layout, only
+  // the rows added since travel (the reference copies every point once at add time, nmslib_c.cpp:755-871; round 1
+  // re-uploaded the whole database after any add).  Buffers grow keeping their contents.
+  const bool append = upload_valid_ && method_ == METHOD_SEQ && !rows_borrowed_ && n_up_ > 0 && n_ > n_up_ &&
+                      up_row_words_ == row_words_;
+  const size_t r0 = append ? n_up_ : 0;
+  auto grow = [&](DevBuf& b, size_t bytes) { return append ? b.ensure_keep(bytes, stream_) : b.ensure(bytes); };
+  Status s = check_cuda(grow(d_db_, n_pad * row_bytes), "cudaMalloc(data)");
   if (!s.ok()) return s;
-  if (!rows_borrowed_) s = check_cuda(cudaMemsetAsync(d_db_.p, 0, n_pad * row_bytes, stream_), "memset(data)");
+  if (!rows_borrowed_)
+    s = check_cuda(cudaMemsetAsync(d_db_.as<char>() + r0 * row_bytes, 0, (n_pad - r0) * row_bytes, stream_), "memset(data)");
   if (!s.ok()) return s;
   const size_t src_row = dev_u8 ? (size_t)dim_ : (size_t)dim_ * 4;
-  const void* src = dev_u8 ? (const void*)h_u8_.data() : (const void*)h_f32_.data();
+  const void* src = dev_u8 ? (const void*)base_u8() : (const void*)base_f32();
   if (method_ == METHOD_HNSW) src = hnsw_host_rows();  // float rows; cosine: unit-normalised (hnsw.cc:441-446)
   if (rows_borrowed_) {
     // (adopt_device_rows: the padded rows are already in HBM; ids = positions)
   } else if (u8_widened()) {  // bytes up in 1 M-row chunks, widened to fp32 rows on the device
     const size_t chunk = 1u << 20;
     if (!(s = check_cuda(d_u8tmp_.ensure(std::min(n_, chunk) * (size_t)dim_), "cudaMalloc(u8 staging)")).ok()) return s;
-    for (size_t r0 = 0; r0 < n_; r0 += chunk) {
-      const size_t cnt = std::min(chunk, n_ - r0);
-      s = check_cuda(cudaMemcpyAsync(d_u8tmp_.p, h_u8_.data() + r0 * dim_, cnt * dim_, cudaMemcpyHostToDevice, stream_),
+    for (size_t c0 = r0; c0 < n_; c0 += chunk) {
+      const size_t cnt = std::min(chunk, n_ - c0);
+      s = check_cuda(cudaMemcpyAsync(d_u8tmp_.p, base_u8() + c0 * dim_, cnt * dim_, cudaMemcpyHostToDevice, stream_),
                      "H2D(u8 data)");
       if (!s.ok()) return s;
       s = check_cuda(launch_widen_u8(d_u8tmp_.as<uint8_t>(), cnt, dim_, row_words_,
-                                     d_db_.as<float>() + r0 * (size_t)row_words_, stream_),
+                                     d_db_.as<float>() + c0 * (size_t)row_words_, stream_),
                      "widen_u8");
       if (!s.ok()) return s;
       ++stats_.kernel_launches;
     }
   } else {
-    s = check_cuda(cudaMemcpy2DAsync(d_db_.p, row_bytes, src, src_row, src_row, n_, cudaMemcpyHostToDevice, stream_),
+    s = check_cuda(cudaMemcpy2DAsync(d_db_.as<char>() + r0 * row_bytes, row_bytes, static_cast<const char*>(src) + r0 * src_row,
+                                     src_row, src_row, n_ - r0, cudaMemcpyHostToDevice, stream_),
                    "H2D(data)");
     if (!s.ok()) return s;
   }
   if (!rows_borrowed_) {
-    s = check_cuda(d_ids_.ensure(n_ * 4), "cudaMalloc(ids)");
+    s = check_cuda(grow(d_ids_, n_ * 4), "cudaMalloc(ids)");
     if (!s.ok()) return s;
-    s = check_cuda(cudaMemcpyAsync(d_ids_.p, h_ids_.data(), n_ * 4, cudaMemcpyHostToDevice, stream_), "H2D(ids)");
+    s = check_cuda(cudaMemcpyAsync(d_ids_.as<int32_t>() + r0, base_ids() + r0, (n_ - r0) * 4, cudaMemcpyHostToDevice, stream_),
+                   "H2D(ids)");
     if (!s.ok()) return s;
   }
+  stats_.uploaded_rows += n_ - r0;
   const bool cos_family = space_ == SPACE_COSINE || space_ == SPACE_ANGULAR;
   if (method_ == METHOD_SEQ && (cos_family || dev_u8)) {
-    s = check_cuda(d_aux_.ensure(n_pad * 4), "cudaMalloc(aux)");
+    s = check_cuda(grow(d_aux_, n_pad * 4), "cudaMalloc(aux)");
     if (!s.ok()) return s;
-    s = check_cuda(launch_row_aux(dev_u8, d_db_.p, (int)n_, row_words_, d_aux_.p, stream_), "row_aux");
+    s = check_cuda(launch_row_aux(dev_u8, d_db_.as<char>() + r0 * row_bytes, (int)(n_ - r0), row_words_,
+                                  d_aux_.as<char>() + r0 * 4, stream_), "row_aux");
     if (!s.ok()) return s;
     ++stats_.kernel_launches;
   }
@@ -508,6 +559,7 @@ Status Engine::upload_data() {
     stats_.kernel_launches += 1;
     if (max_norm2 > u8_imma_max_norm2()) {
       u8_imma_ = false;
+      upload_valid_ = false;  // (another row layout: everything travels again)
       return upload_data();
     }
     u8_m_half_ = (max_norm2 + 1) / 2;
@@ -523,24 +575,27 @@ Status Engine::upload_data() {
     // operands of the tensor-core scan: bias (|x|^2 or 0, +inf on padding rows), the unit-norm copy
     // for cosine, max operand-row norm and the "is TF32-exact" flag (both feed the certificate)
     const int mode = cos_family ? SCAN_COSINE : space_ == SPACE_NEGDOT ? SCAN_NEGDOT : SCAN_L2;
-    if (!(s = check_cuda(d_bias_.ensure(n_pad * 4), "cudaMalloc(bias)")).ok()) return s;
+    if (!(s = check_cuda(grow(d_bias_, n_pad * 4), "cudaMalloc(bias)")).ok()) return s;
     if (!(s = check_cuda(d_flags_.ensure(16), "cudaMalloc(flags)")).ok()) return s;
-    if (!(s = check_cuda(cudaMemsetAsync(d_flags_.p, 0, 16, stream_), "memset(flags)")).ok()) return s;
+    // (append: the max norm and the "not TF32-exact" flag of the rows already there keep accumulating)
+    if (!append && !(s = check_cuda(cudaMemsetAsync(d_flags_.p, 0, 16, stream_), "memset(flags)")).ok()) return s;
     float* unit = nullptr;
     if (mode == SCAN_COSINE) {
-      if (!(s = check_cuda(d_db_unit_.ensure(n_pad * row_bytes), "cudaMalloc(unit rows)")).ok()) return s;
-      if (!(s = check_cuda(cudaMemsetAsync(d_db_unit_.p, 0, n_pad * row_bytes, stream_), "memset(unit)")).ok()) return s;
-      unit = d_db_unit_.as<float>();
+      if (!(s = check_cuda(grow(d_db_unit_, n_pad * row_bytes), "cudaMalloc(unit rows)")).ok()) return s;
+      if (!(s = check_cuda(cudaMemsetAsync(d_db_unit_.as<char>() + r0 * row_bytes, 0, (n_pad - r0) * row_bytes, stream_),
+                           "memset(unit)")).ok()) return s;
+      unit = d_db_unit_.as<float>() + r0 * (size_t)row_words_;
     }
     // flags layout: [0] database inexact, [1] query batch inexact, [2] max-norm bits
     float* nblock = nullptr;
     if (mode == SCAN_L2) {  // |x|^2 as an extra K=8 MMA step: [n_pad][32] TF32 pieces + a constant tile of ones
-      if (!(s = check_cuda(d_nblock_.ensure(n_pad * (size_t)tc_kblock_words() * 4), "cudaMalloc(nblock)")).ok()) return s;
+      if (!(s = check_cuda(grow(d_nblock_, n_pad * (size_t)tc_kblock_words() * 4), "cudaMalloc(nblock)")).ok()) return s;
       if (!(s = check_cuda(d_ones_.ensure((size_t)128 * tc_kblock_words() * 4), "cudaMalloc(ones)")).ok()) return s;
-      nblock = d_nblock_.as<float>();
+      nblock = d_nblock_.as<float>() + r0 * (size_t)tc_kblock_words();
     }
-    s = check_cuda(launch_tc_prep_db(d_db_.as<float>(), (int)n_, (int)n_pad, row_words_, mode, d_bias_.as<float>(),
-                                     mode == SCAN_COSINE ? d_aux_.as<float>() : nullptr, unit, nblock,
+    s = check_cuda(launch_tc_prep_db(d_db_.as<float>() + r0 * (size_t)row_words_, (int)(n_ - r0), (int)(n_pad - r0), row_words_,
+                                     mode, d_bias_.as<float>() + r0,
+                                     mode == SCAN_COSINE ? d_aux_.as<float>() + r0 : nullptr, unit, nblock,
                                      nblock ? d_ones_.as<float>() : nullptr, d_flags_.as<unsigned>() + 2,
                                      d_flags_.as<int>(), stream_),
                    "tc_prep_db");
@@ -560,6 +615,9 @@ Status Engine::upload_data() {
   s = check_cuda(cudaStreamSynchronize(stream_), "upload sync");
   if (!s.ok()) return s;
   n_dev_ = n_;
+  n_up_ = n_;
+  up_row_words_ = row_words_;
+  upload_valid_ = !rows_borrowed_;
   data_dirty_ = false;
   stats_.device_bytes = d_db_.cap + d_ids_.cap + d_aux_.cap + d_bias_.cap + d_db_unit_.cap + d_nblock_.cap;
   return Status::OK();

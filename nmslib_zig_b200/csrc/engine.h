@@ -39,6 +39,7 @@ struct DevBuf {
   size_t cap = 0;
   bool borrowed = false;  // memory owned by someone else (hnsw_build_gpu.cu scans the rows of the index in place)
   cudaError_t ensure(size_t bytes, bool zero_new = false, cudaStream_t s = nullptr);
+  cudaError_t ensure_keep(size_t bytes, cudaStream_t s);  // grow, contents preserved
   void borrow(void* ptr, size_t bytes);
   void release();
   template <typename T>
@@ -114,7 +115,7 @@ struct Stats {
   uint64_t queries = 0, kernel_launches = 0, distance_evals = 0, hnsw_expansions = 0;
   double last_kernel_ms = 0, last_total_ms = 0, last_scan_ms = 0, scan_ms_sum = 0;
   uint64_t scan_count = 0;
-  uint64_t fallback_queries = 0, device_bytes = 0, split_queries = 0;
+  uint64_t fallback_queries = 0, device_bytes = 0, split_queries = 0, uploaded_rows = 0;
 };
 
 class Engine {
@@ -131,9 +132,13 @@ class Engine {
   bool is_u8() const { return is_u8_; }
   Space space() const { return space_; }
   Method method() const { return method_; }
-  const float* row_f32(size_t pos) const { return h_f32_.data() + pos * (size_t)dim_; }
-  const uint8_t* row_u8(size_t pos) const { return h_u8_.data() + pos * (size_t)dim_; }
-  int32_t ext_id(size_t pos) const { return h_ids_[pos]; }
+  const float* row_f32(size_t pos) const { return base_f32() + pos * (size_t)dim_; }
+  const uint8_t* row_u8(size_t pos) const { return base_u8() + pos * (size_t)dim_; }
+  int32_t ext_id(size_t pos) const { return base_ids()[pos]; }
+  const int32_t* ext_id_ptr(size_t pos) const { return base_ids() + pos; }
+  // A shard of a ShardGroup does not copy its rows: it borrows [lo, hi) of the group's host store (rows and ids stay
+  // valid until the group re-cuts its shards, which drops this engine first)
+  Status borrow_host_rows(const void* rows, const int32_t* ids, size_t count, size_t elem_count);
   float host_distance(size_t a, size_t b) const;  // Space::IndexTimeDistance (space.h:136-142)
 
   // ---- index state ----
@@ -229,6 +234,9 @@ class Engine {
   size_t n_ = 0;
   bool built_ = false;
   bool data_dirty_ = true, graph_dirty_ = true;
+  bool upload_valid_ = false;  // rows [0, n_up_) are in HBM in the layout of up_row_words_ (append-only uploads)
+  size_t n_up_ = 0;
+  int up_row_words_ = 0;
   std::vector<std::string> index_params_;
   size_t ef_ = 200;  // nmslib_c.cpp:330 default through the C ABI
   bool ef_user_set_ = false;
@@ -236,6 +244,11 @@ class Engine {
   std::vector<float> h_f32_;
   std::vector<uint8_t> h_u8_;
   std::vector<int32_t> h_ids_;
+  const void* borrowed_rows_ = nullptr;    // set by borrow_host_rows: the rows / ids live in another engine's host store
+  const int32_t* borrowed_ids_ = nullptr;
+  const float* base_f32() const { return borrowed_rows_ ? static_cast<const float*>(borrowed_rows_) : h_f32_.data(); }
+  const uint8_t* base_u8() const { return borrowed_rows_ ? static_cast<const uint8_t*>(borrowed_rows_) : h_u8_.data(); }
+  const int32_t* base_ids() const { return borrowed_ids_ ? borrowed_ids_ : h_ids_.data(); }
   std::vector<float> h_hnsw_rows_, h_q_widen_;  // float / normalised rows for hnsw; widened uint8 queries
   bool rows_normalized_ = false;
   HnswGraph graph_;

@@ -220,11 +220,11 @@ Status ShardGroup::prepare(Engine* host, size_t nq, size_t k) {
       const size_t lo = n * (size_t)g / G, hi = n * (size_t)(g + 1) / G;
       std::unique_ptr<Engine> e(new Engine(m.space, METHOD_SEQ, m.is_u8, m.devices[g]));
       if (hi > lo) {
-        // ids travel with their rows; positions are global (lo + local row) so that ties order as on one GPU
-        std::vector<int32_t> ids(hi - lo);
-        for (size_t i = lo; i < hi; ++i) ids[i - lo] = host->ext_id(i);
+        // no second host copy: the shard borrows rows [lo, hi) and their ids from the host store (they stay put until
+        // the next add / reset, which re-cuts the shards first); positions are global (lo + local row) so that ties
+        // order as on one GPU
         const void* rows = m.is_u8 ? (const void*)host->row_u8(lo) : (const void*)host->row_f32(lo);
-        Status as = e->add_rows(rows, hi - lo, (size_t)host->dim(), ids.data());
+        Status as = e->borrow_host_rows(rows, host->ext_id_ptr(lo), hi - lo, (size_t)host->dim());
         if (!as.ok()) return as;
       }
       e->set_pos_base((uint32_t)lo);
@@ -324,6 +324,7 @@ Stats ShardGroup::stats() {
     out.fallback_queries += s.fallback_queries;
     out.split_queries += s.split_queries;
     out.device_bytes += s.device_bytes;
+    out.uploaded_rows += s.uploaded_rows;
     out.last_scan_ms = std::max(out.last_scan_ms, s.last_scan_ms);
     out.scan_ms_sum += s.scan_ms_sum;
     out.scan_count += s.scan_count;

@@ -67,7 +67,7 @@ class Stats(C.Structure):
                 ("scan_ms_sum", C.c_double), ("scan_count", C.c_uint64), ("build_total_ms", C.c_double),
                 ("build_scan_ms", C.c_double), ("build_select_ms", C.c_double), ("build_link_ms", C.c_double),
                 ("build_batches", C.c_uint64), ("build_prunes", C.c_uint64), ("split_queries", C.c_uint64),
-                ("u8_imma", C.c_uint64)]
+                ("u8_imma", C.c_uint64), ("uploaded_rows", C.c_uint64)]
 
 
 # every symbol include/nmslib_b200.h declares (the CPU-side test checks this list against the header)

@@ -569,3 +569,29 @@ def test_cosine_error_against_float64_is_no_worse_than_the_reference():
     assert err_gpu.max() <= err_ref.max() + 1e-6, (err_gpu.max(), err_ref.max())
     assert err_gpu.mean() <= err_ref.mean() + 2e-7, (err_gpu.mean(), err_ref.mean())
     assert err_gpu.max() <= ATOL_COSINE / 2      # the tolerance the parity tests use has a factor of two to spare
+
+
+@pytest.mark.parametrize("space", ["l2", "cosinesimil", "negdotprod", "l2sqr_sift"])
+def test_appended_rows_are_uploaded_alone_and_answers_equal_a_fresh_index(space):
+    """adding rows to an index that already lives in HBM uploads only the new rows (buffers grow keeping
+    their contents, operands of the tensor-core scan are prepared for the new rows only); the answers are those of an
+    index built from all rows at once, bit for bit."""
+    u8 = space == "l2sqr_sift"
+    n1, n2, nq, k = 5_003, 2_222, 200, 10
+    data = synth.sift_like_u8(n1 + n2, 7) if u8 else synth.uniform(n1 + n2, 40, 1) - 0.2
+    q = synth.sift_like_u8(nq, 8) if u8 else synth.uniform(nq, 40, 2) - 0.2
+    ids = np.arange(n1 + n2, dtype=np.int32) + 100
+    idx = make_index(space, data[:n1], ids[:n1])
+    idx.knnQueryBatch(q, k)
+    assert idx.stats()["uploaded_rows"] == n1
+    (idx.addUInt8Batch if u8 else idx.addDenseBatch)(data[n1:], ids[n1:])
+    r = idx.knnQueryBatch(q, k)
+    assert idx.stats()["uploaded_rows"] == n1 + n2                     # not n1 + (n1 + n2)
+    fresh = make_index(space, data, ids)
+    f = fresh.knnQueryBatch(q, k)
+    assert np.array_equal(r.ids, f.ids) and np.array_equal(r.distances.view(np.int32), f.distances.view(np.int32))
+    oi, od, oc = O.seq_knn(space, data, q, k, ids)
+    assert_knn_matches(r.ids, r.distances, r.sizes, oi, od, oc, exact=u8, what=f"append/{space}",
+                       atol=ATOL_COSINE if space == "cosinesimil" else None)
+    idx.deinit()
+    fresh.deinit()
