@@ -1302,6 +1302,8 @@ Status Engine::knn_host_slice(const void* queries, size_t nq, size_t elem_count,
     if (!(s = check_cuda(cudaMemcpyAsync(h_counts + q0, d_out_counts_.as<int32_t>() + q0, cnt * 4, cudaMemcpyDeviceToHost, stream_), "D2H(counts)")).ok()) return s;
   }
   s = check_cuda(cudaStreamSynchronize(stream_), "sharded query batch");
+  if (s.ok() && sharded() && xch_take_error(xch_))
+    s = Status::Err(kErrQuery, "shard exchange: a peer did not publish its lists within 10 s (ranks must make the same calls)");
   if (s.ok()) {
     stats_.queries += nq;
     stats_.distance_evals += (uint64_t)nq * n_dev_;
@@ -1398,6 +1400,8 @@ Status Engine::knn_host(const void* queries, size_t nq, size_t elem_count, size_
   cudaEventRecord(ev_[3], stream_);
   s = check_cuda(cudaStreamSynchronize(stream_), "query batch");
   if (!s.ok()) return s;
+  if (sharded() && xch_take_error(xch_))
+    return Status::Err(kErrQuery, "shard exchange: a peer did not publish its lists within 10 s (ranks must make the same calls)");
   float ms = 0;
   if (cudaEventElapsedTime(&ms, ev_[1], ev_[2]) == cudaSuccess) stats_.last_kernel_ms = ms;
   if (cudaEventElapsedTime(&ms, ev_[0], ev_[3]) == cudaSuccess) stats_.last_total_ms = ms;

@@ -161,3 +161,31 @@ def test_hnsw_file_import_and_rewrite_is_byte_identical(golden_dir, tmp_path):
     v = cos.getDataPoint(5)
     assert abs(float(np.dot(v, v)) - 1.0) < 1e-5     # cosine rows are stored normalised (hnsw.cc:441-446)
     cos.deinit()
+
+
+def test_sharding_entry_points_validate_without_a_device():
+    """include/nmslib_b200.h section "row-sharded multi-GPU search": argument validation and the b200_devices parser
+    need no GPU; anything that would touch a device fails loudly (there is no CPU fallback)."""
+    text = (ROOT / "include" / "nmslib_b200.h").read_text()
+    assert "#define NMSLIB_B200_SHARD_BLOB_BYTES 256" in text
+    idx = nb.Index("l2", None, "seq_search")
+    idx.addDenseBatch(np.eye(4, dtype=np.float32))
+    for bad in ("0,,1", "x", "3-1", "-1"):
+        with pytest.raises(nb.NmslibError) as e:
+            idx.buildIndex(nb.Params({"b200_devices": bad}))
+        assert e.value.name == "IndexBuildFailed"
+    idx.buildIndex(nb.Params({"b200_devices": "0"}))          # one device: an ordinary index
+    with pytest.raises(nb.NmslibError):
+        idx.shardConnect(0, 2, b"\0" * 512)                    # no exported window
+    if not nb.device_available():
+        with pytest.raises(nb.NmslibError):
+            idx.shardExport(16, 4)
+    idx.deinit()
+    hn = nb.Index("l2", None, "hnsw")
+    hn.addDenseBatch(np.eye(4, dtype=np.float32))
+    with pytest.raises(nb.NmslibError):                        # hnsw does not shard by rows (SURVEY 8e): unknown parameter
+        hn.buildIndex(nb.Params({"b200_devices": "0,1"}))
+    hn.deinit()
+    with pytest.raises(nb.NmslibError):
+        nb.set_option("no_such_option", 1)
+    nb.set_option("tc_pair", 1)
