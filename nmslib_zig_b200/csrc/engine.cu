@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <sstream>
+#include <thread>
 
 namespace nb200 {
 
@@ -61,6 +62,37 @@ bool device_available() {
   }
   return cnt > 0;
 }
+
+template <typename T>
+bool HostSlab<T>::append(const T* src, size_t count) {
+  if (count == 0) return true;
+  if (n_ + count > cap_) {
+    size_t want = std::max(n_ + count, cap_ + cap_ / 2);
+    T* np = static_cast<T*>(realloc(p_, want * sizeof(T)));  // (realloc moves pages instead of copying when it can)
+    if (!np) return false;
+    p_ = np;
+    cap_ = want;
+  }
+  T* dst = p_ + n_;
+  const size_t bytes = count * sizeof(T);
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t threads = bytes < (64u << 20) ? 1 : std::min<size_t>(std::min<unsigned>(hw, 16), bytes / (16u << 20));
+  if (threads <= 1) {
+    memcpy(dst, src, bytes);
+  } else {
+    std::vector<std::thread> pool;
+    const size_t chunk = (count + threads - 1) / threads;
+    for (size_t t = 0; t < threads; ++t) {
+      const size_t a = t * chunk, b = std::min(count, a + chunk);
+      if (b > a) pool.emplace_back([=] { memcpy(dst + a, src + a, (b - a) * sizeof(T)); });
+    }
+    for (auto& th : pool) th.join();
+  }
+  n_ += count;
+  return true;
+}
+template class HostSlab<float>;
+template class HostSlab<uint8_t>;
 
 cudaError_t DevBuf::ensure(size_t bytes, bool zero_new, cudaStream_t s) {
   if (bytes <= cap) return cudaSuccess;
@@ -192,12 +224,14 @@ Status Engine::add_rows(const void* rows, size_t count, size_t elem_count, const
   if (n_ + count > 0xFFFFFFF0ull) return Status::Err(kErrTooLarge, "more than 2^32 rows in one shard");
   if (is_u8_) {
     const uint8_t* src = static_cast<const uint8_t*>(rows);
-    h_u8_.insert(h_u8_.end(), src, src + count * elem_count);
+    if (!h_u8_.append(src, count * elem_count)) return Status::Err(kErrOOM, "out of host memory");
   } else {
     const float* src = static_cast<const float*>(rows);
-    h_f32_.insert(h_f32_.end(), src, src + count * elem_count);
+    if (!h_f32_.append(src, count * elem_count)) return Status::Err(kErrOOM, "out of host memory");
   }
-  for (size_t i = 0; i < count; ++i) h_ids_.push_back(ids ? ids[i] : (int32_t)i);  // nmslib_c.cpp:768
+  if (ids) h_ids_.insert(h_ids_.end(), ids, ids + count);
+  else
+    for (size_t i = 0; i < count; ++i) h_ids_.push_back((int32_t)i);  // nmslib_c.cpp:768
   n_ += count;
   ++data_gen_;
   data_dirty_ = true;
@@ -364,7 +398,7 @@ Status Engine::adopt_graph(HnswGraph&& g) {
   // the file carries the (for cosine: normalised) vectors and the external ids
   dim_ = graph_.dim;
   n_ = graph_.total;
-  h_f32_ = graph_.vectors;
+  if (!h_f32_.assign(graph_.vectors.data(), graph_.vectors.size())) return Status::Err(kErrOOM, "out of host memory");
   h_ids_ = graph_.ext_ids;
   graph_.vectors.clear();
   graph_.vectors.shrink_to_fit();
