@@ -1,3 +1,7 @@
+import os as _os
+from pathlib import Path as _Path
+# the NB200_* switches exist only in the experiments build (python -m nmslib_zig_b200.build --experiments)
+_os.environ.setdefault("NB200_LIB", str(_Path(__file__).resolve().parents[1] / "nmslib_zig_b200" / "lib" / "libnmslib_b200_exp.so"))
 import os, sys
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np

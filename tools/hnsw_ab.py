@@ -2,6 +2,11 @@
     python tools/hnsw_ab.py build [n] [dim]     # device-built cosine graph -> /tmp/nb200_ab.hnsw (+ queries)
     NB200_HNSW_PF=0 python tools/hnsw_ab.py run  # loads it, efSearch 100 / 400, kernel ms over 10 K queries
 The switches are read once per process, hence one process per setting."""
+import os as _os
+from pathlib import Path as _Path
+# the NB200_* switches exist only in the experiments build (python -m nmslib_zig_b200.build --experiments)
+_os.environ.setdefault("NB200_LIB", str(_Path(__file__).resolve().parents[1] / "nmslib_zig_b200" / "lib" / "libnmslib_b200_exp.so"))
+
 import os
 import sys
 import time

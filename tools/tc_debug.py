@@ -1,4 +1,9 @@
 """Quick A/B of the tensor-core scan against the exact scan on the same inputs (GPU box only)."""
+import os as _os
+from pathlib import Path as _Path
+# the NB200_* switches exist only in the experiments build (python -m nmslib_zig_b200.build --experiments)
+_os.environ.setdefault("NB200_LIB", str(_Path(__file__).resolve().parents[1] / "nmslib_zig_b200" / "lib" / "libnmslib_b200_exp.so"))
+
 import os
 import sys
 import time
@@ -12,7 +17,7 @@ from nmslib_zig_b200 import synth
 
 
 def run(space, data, q, k, force_exact):
-    os.environ["NB200_FORCE_EXACT"] = "1" if force_exact else "0"
+    nb.set_option("force_exact", 1 if force_exact else 0)
     idx = nb.Index(space, None, "seq_search")
     idx.addDenseBatch(data)
     idx.buildIndex()
