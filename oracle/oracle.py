@@ -244,3 +244,54 @@ class RefIndex:
             self.close()
         except Exception:
             pass
+
+
+def regular_to_flat_hnsw(regular_path, data: np.ndarray, ids, out_path):
+    """TEST INFRASTRUCTURE.  Rewrite the reference's REGULAR index file (Hnsw::SaveRegularIndexBin, hnsw.cc:810-842:
+    links of the pointer graph, what Hnsw<int> = l2sqr_sift + hnsw saves) plus its uint8 data set as an optimized flat
+    file (hnsw.cc:774-806) with the rows widened to float: the C port of the flat search then walks the same graph
+    with distances that are exact integers in fp32 -- the claim the device path makes for SURVEY row a18
+    (baseSearchAlgorithmV1Merge / Old, hnsw.cc:1076-1300, use the same beam rule as the flat searches)."""
+    import struct
+    raw = Path(regular_path).read_bytes()
+    flag, total, maxlevel, enter = struct.unpack_from("<IIiI", raw, 0)
+    M, maxM, maxM0 = struct.unpack_from("<QQQ", raw, 16)
+    assert flag == 0 and total == data.shape[0]
+    pos = 40
+    dim = data.shape[1]
+    vec = np.ascontiguousarray(data, np.float32)
+    ids = np.ascontiguousarray(ids, np.int32)
+    off0 = 16 + 4 * dim
+    mem = off0 + 4 * (maxM0 + 1)
+    recs = bytearray(b"\x01" * (mem * total))
+    uppers = []
+    levels = []
+    for i in range(total):
+        level, = struct.unpack_from("<I", raw, pos)
+        pos += 4
+        levels.append(level)
+        up = bytearray()
+        for l in range(level + 1):
+            cnt, = struct.unpack_from("<I", raw, pos)
+            pos += 4
+            fr = raw[pos:pos + 4 * cnt]
+            pos += 4 * cnt
+            if l == 0:
+                struct.pack_into("<i", recs, i * mem + off0, cnt)
+                recs[i * mem + off0 + 4:i * mem + off0 + 4 + 4 * cnt] = fr
+            else:
+                blk = bytearray(4 * (maxM + 1))
+                struct.pack_into("<i", blk, 0, cnt)
+                blk[4:4 + 4 * cnt] = fr
+                up += blk
+        struct.pack_into("<iiQ", recs, i * mem, int(ids[i]), -1, 4 * dim)
+        recs[i * mem + 16:i * mem + 16 + 4 * dim] = vec[i].tobytes()
+        uppers.append(bytes(up))
+    maxlevel = min(maxlevel, levels[enter]) if total else maxlevel   # the pointer search starts at enterpoint_->level
+    with open(out_path, "wb") as f:
+        f.write(struct.pack("<IIQQQiIQQiQ", 1, total, mem, off0, 0, maxlevel, enter, maxM, maxM0, 1 if dim % 16 == 0 else 2, 3))
+        f.write(recs)
+        for up in uppers:
+            f.write(struct.pack("<I", len(up)))
+            f.write(up)
+    return out_path

@@ -118,3 +118,21 @@ def test_hnsw_oracle_matches_live_reference(space, dim, params, tmp_path):
         pi, pd, pc, _ = h.knn(q, 10, ef)
         assert_knn_matches(pi, pd, pc, ri, rd, rc, what=f"{space} ef={ef}")
     h.close()
+
+
+def test_int_space_hnsw_golden_is_the_flat_search_over_exact_integer_distances(tmp_path):
+    """SURVEY a18 pinned on the CPU: the reference's answers for l2sqr_sift + hnsw (Hnsw<int>: pointer graph,
+    baseSearchAlgorithmV1Merge / Old, hnsw.cc:1076-1300; golden made by the reference itself) equal the oracle's port
+    of the FLAT search run over the same links with the rows widened to float -- ids (ties aside) and int32 distances,
+    at every efSearch incl. the SearchOld regime.  That equivalence is what the device path relies on."""
+    g = np.load(GOLDEN / "regular_hnsw_sift.npz")
+    flat = O.regular_to_flat_hnsw(GOLDEN / "regular_hnsw_sift.hnsw", g["data"], g["ids"], tmp_path / "flat.hnsw")
+    h = O.PortHnsw(flat)
+    assert (h.total, h.dim) == (3000, 128)
+    k = int(g["k"])
+    q = g["queries"].astype(np.float32)
+    for ef in g["efs"]:
+        ids, d, c, _ = h.knn(q, k, int(ef))
+        assert_knn_matches(ids, d, c, g[f"ids_ef{ef}"], g[f"dists_ef{ef}"], g[f"counts_ef{ef}"], exact=True,
+                           what=f"int-space hnsw ef={ef}")
+    h.close()
