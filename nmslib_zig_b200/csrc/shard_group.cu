@@ -100,7 +100,16 @@ struct ShardGroup::Impl {
         seen = job_gen;
         fn = job;
       }
-      Status s = g < active ? fn(g) : Status::OK();
+      Status s;
+      try {
+        s = g < active ? fn(g) : Status::OK();
+      } catch (const std::bad_alloc&) {
+        s = Status::Err(3, "out of host memory in a shard worker");
+      } catch (const std::exception& e) {
+        s = Status::Err(kErrQuery, std::string("shard worker: ") + e.what());
+      } catch (...) {
+        s = Status::Err(kErrQuery, "shard worker: unknown error");
+      }
       if (!s.ok() && barrier) barrier->poison();  // (peers waiting for this device at the exchange must not hang)
       {
         std::lock_guard<std::mutex> lk(mu);
