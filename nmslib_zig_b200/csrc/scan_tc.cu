@@ -1847,16 +1847,17 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, int items_pow2) {
+__global__ void __launch_bounds__(256) tc_rerank_kernel(const RerankParams p, int items_pow2) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);          // [items_pow2] exact keys
   float* srank = reinterpret_cast<float*>(sk + items_pow2);       // [items_pow2] exact rank (certificate domain)
   uint32_t* spos = reinterpret_cast<uint32_t*>(srank);            // (the same words first hold the live positions)
   __shared__ int s_cnt[64];
-  __shared__ int s_red[4];
+  __shared__ int s_red[8];
   __shared__ int s_live;
   __shared__ float s_wmin[2], s_qn2;
   const int q = p.q_begin + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;  // 4, or 8 for long rows / large k (more candidate rows in flight)
   const int qb = q / TC_QB, row = q % TC_QB;
   const float* qv = p.queries + (size_t)q * p.row_words;
 
@@ -1896,7 +1897,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   // the certificate below holds, every true neighbour has pass-1 rank < minthr, and if it does not
   // hold the query is re-run anyway.  With shared thresholds this is ~k' keys out of the few hundred appended.
   // One warp per slot (round robin), so the slots' lists are read concurrently.
-  for (int s = warp; s < p.n_lists; s += 4) {
+  for (int s = warp; s < p.n_lists; s += nwarps) {
     const size_t slot = ((size_t)qb * p.n_split + s) * TC_QB + row;
     const uint64_t* cb = p.cand + slot * (size_t)p.cap;
     const int c = s_cnt[s];
@@ -1932,7 +1933,8 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
         c = __reduce_add_sync(FULL, c);
         if (lane == 0) s_red[warp] = c;
         __syncthreads();
-        c = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        c = 0;
+        for (int w = 0; w < nwarps; ++w) c += s_red[w];
         __syncthreads();
         if (c >= p.k) hi = mid; else lo = mid + 1;
       }
@@ -1959,7 +1961,8 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
     __syncthreads();
     int off = incl - mine;
     for (int w = 0; w < warp; ++w) off += s_red[w];
-    const int kept = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    int kept = 0;
+    for (int w = 0; w < nwarps; ++w) kept += s_red[w];
     for (int j = 0, i = tid; i < total; ++j, i += blockDim.x)
       if (mask >> j & 1ull) spos[off++] = (uint32_t)sk[i];
     __syncthreads();
@@ -1974,7 +1977,7 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const RerankParams p, in
   const float4* q4 = reinterpret_cast<const float4*>(qv);
 
   // exact fp32 distance of every live candidate: one warp per candidate, 128-bit loads
-  for (int i0 = warp; i0 < total; i0 += 4) {
+  for (int i0 = warp; i0 < total; i0 += nwarps) {
     const uint32_t pos = spos[i0];
     const size_t local = (size_t)(pos - p.pos_base);
     if (p.db_u8) {  // sum (x - y)^2 over 128 bytes in int32: the reference's n1 + n2 - 2 x.y (distcomp_l2sqr_sift.cc:41-50)
@@ -2850,7 +2853,9 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
     fprintf(stderr, "nmslib_b200: tc_rerank cudaFuncSetAttribute(%zu) failed: %s\n", smem, cudaGetErrorString(e));
     return e;
   }
-  tc_rerank_kernel<<<q_count, 128, smem, stream>>>(p, p2);
+  // 8 warps when the exact evaluation dominates (long rows, many candidates): twice the candidate rows in flight
+  const int rr_threads = (row_words > 128 || k >= 32) ? 256 : 128;
+  tc_rerank_kernel<<<q_count, rr_threads, smem, stream>>>(p, p2);
   e = cudaGetLastError();
   if (e != cudaSuccess)
     fprintf(stderr, "nmslib_b200: tc_rerank launch (grid %d, smem %zu, items %d) failed: %s\n", nq, smem, p2,
