@@ -423,6 +423,20 @@ def main():
                 line["workloads"][name] = rec
             except Exception as e:  # a sub-record must not take the headline line down with it
                 line["workloads"][name] = {"error": f"{type(e).__name__}: {e}"}
+    # config 5 (10 M x 768 negdotprod, 100 K queries, k = 100) is the one BASELINE configuration that needs the whole
+    # box: on the default 8-GPU run it is reported as a sub-record, with its own parity sample, next to config 2
+    if (world == 8 and args.workload == "c2" and args.n is None and args.nq is None and "none" not in args.workloads
+            and time.perf_counter() - t_start < args.budget_s):
+        rec = None
+        try:
+            args.parity_sample = min(args.parity_sample, 64)
+            rec = run("c5", steps=3, warmup=3, cpu=False)
+        except Exception as e:
+            rec = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and line is not None and rec is not None:
+            for drop in ("metric", "unit", "higher_is_better", "vs_baseline", "data", "n_gpus", "clocks"):
+                rec.pop(drop, None)
+            line.setdefault("workloads", {})["c5"] = rec
     if rank == 0 and line is not None:
         line["wall_s"] = time.perf_counter() - t_start
         print(json.dumps(line))
