@@ -1084,9 +1084,17 @@ Status Engine::run_seq_tc(const void* dq, size_t nq, size_t k, uint64_t* out_key
     while (b0 < q_blocks) {
       int lists = s_max, b1 = q_blocks;
       if ((ts || pair) && (int)plan_block_slots_.size() == q_blocks) {
+        // (runs are merged while the launches would use the same sort buffer: lists 3 and 4 of config 2 both need
+        //  1 024 slots -- one launch instead of two; an unused list has count -1 and is skipped by the kernel)
         lists = std::max(1, plan_block_slots_[b0]) * lpp;
+        const int p2 = tc_rerank_pow2(std::min(lists, s_max), cap, (int)k, (int)n_dev_);
         b1 = b0 + 1;
-        while (b1 < q_blocks && std::max(1, plan_block_slots_[b1]) * lpp == lists) ++b1;
+        while (b1 < q_blocks) {
+          const int l1 = std::max(1, plan_block_slots_[b1]) * lpp;
+          if (tc_rerank_pow2(std::min(l1, s_max), cap, (int)k, (int)n_dev_) != p2) break;
+          lists = std::max(lists, l1);
+          ++b1;
+        }
       }
       const size_t q0 = (size_t)b0 * qb, q1 = std::min(nq, (size_t)b1 * qb);
       if (q1 > q0) {

@@ -118,6 +118,7 @@ cudaError_t launch_tc_scan(const float* qa, size_t q_pad, const float* dbB, size
                            const float* ones, int n, int nq, int row_words, int k, uint32_t pos_base, int n_cta,
                            int work_per_cta, int s_max, int aligned, int kprime, uint64_t* cand, int* cand_cnt,
                            float* cand_thr, uint32_t* gthr, cudaStream_t stream);
+int tc_rerank_pow2(int n_lists, int cap, int k, int n);  // sort-buffer size of a re-rank launch (a power of two)
 cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int n, int nq,
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,

@@ -2803,6 +2803,17 @@ cudaError_t launch_tc_scan_ts(const float* q, const float* dbB, size_t n_pad, co
   return e;
 }
 
+// live keys the re-rank's sort buffer must hold for a query with n_lists candidate lists of `cap` keys
+int tc_rerank_items(int n_lists, int cap, int k, int n) {
+  return std::min(n_lists * cap, std::max(std::max(2048, 4 * k), std::min(n, 8192)));  // (small shards: all rows)
+}
+int tc_rerank_pow2(int n_lists, int cap, int k, int n) {
+  int p2 = 32;
+  const int items = tc_rerank_items(n_lists, cap, k, n);
+  while (p2 < items || p2 < k) p2 <<= 1;
+  return p2;
+}
+
 cudaError_t launch_tc_rerank(const float* db, const float* queries, const float* db_norm2, int n, int nq,
                              int row_words, int k, int n_split, int mode, uint32_t pos_base, const uint64_t* cand,
                              const int* cand_cnt, const float* cand_thr, float x_max, const int* inexact_flags,
@@ -2850,7 +2861,7 @@ cudaError_t launch_tc_rerank(const float* db, const float* queries, const float*
   if (n_split > 64) return cudaErrorInvalidValue;
   // sort buffer: the live keys (pass-1 rank below the final threshold) are a few times k'; a query with more
   // than this many is left uncertified and re-run exactly
-  int items = std::min(n_lists * p.cap, std::max(std::max(2048, 4 * k), std::min(n, 8192)));  // (small shards: all rows)
+  int items = tc_rerank_items(n_lists, p.cap, k, n);
   int p2 = 1;
   while (p2 < items || p2 < k) p2 <<= 1;
   const size_t smem = (size_t)p2 * 12 + 16;
