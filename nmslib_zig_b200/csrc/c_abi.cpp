@@ -172,7 +172,8 @@ nmslib_error_t nmslib_create_index(nmslib_index_handle_t index, nmslib_params_ha
                                           "b200_devices"};  // + row shards over several GPUs (extension)
         static const char* hnsw_names[] = {"M", "efConstruction", "maxM", "maxM0", "mult", "delaunay_type", "post",
                                            "indexThreadQty", "skip_optimized_index", "searchMethod",
-                                           "b200_build"};  // hnsw.cc:189-208 + where to build (extension)
+                                           "b200_build",     // hnsw.cc:189-208 + where to build (extension)
+                                           "b200_devices"};  // + replicas on several GPUs, queries split (extension)
         for (const std::string& p : params_of(index_params)) {
           const std::string name = p.substr(0, p.find('='));
           bool known = false;
@@ -198,7 +199,7 @@ nmslib_error_t nmslib_create_index(nmslib_index_handle_t index, nmslib_params_ha
           Status ds = nb200::ShardGroup::parse_devices(devices, &devs);
           if (!ds.ok()) return NB_ERR(NMSLIB_ERROR_INDEX_BUILD_FAILED, "Failed to create index: " + ds.msg);
           if (devs.size() > 1) {
-            index->group = new nb200::ShardGroup(index->engine->space(), index->engine->is_u8(), devs);
+            index->group = new nb200::ShardGroup(index->engine->space(), index->engine->method(), index->engine->is_u8(), devs);
             index->group->set_index_params(kept);
           }
         }
@@ -286,6 +287,7 @@ nmslib_error_t nmslib_set_query_time_params(nmslib_index_handle_t index, nmslib_
       [&]() -> nmslib_error_t {
         std::lock_guard<std::mutex> lock(index->engine->mutex());
         Status s = index->engine->set_query_params(params_of(params));
+        if (s.ok() && index->group) s = index->group->set_query_params(params_of(params));
         if (!s.ok()) return NB_STATUS(s);
         return NB_OK("Query time params set");
       },

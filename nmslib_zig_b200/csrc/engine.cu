@@ -274,6 +274,7 @@ void Engine::reset() {
   h_ids_.clear();
   borrowed_rows_ = nullptr;
   borrowed_ids_ = nullptr;
+  replica_rows_ = false;
   n_ = 0;
   dim_ = 0;
   built_ = false;
@@ -386,6 +387,7 @@ Status Engine::adopt_graph(HnswGraph&& g) {
     graph_ = std::move(g);
     graph_dirty_ = true;
     built_ = true;
+    ++data_gen_;  // (replicas of this index, shard_group.cu, are cut again)
     return Status::OK();
   }
   if (is_u8_) return Status::Err(kErrIncompat, "the optimized HNSW index holds float vectors only");
@@ -405,6 +407,24 @@ Status Engine::adopt_graph(HnswGraph&& g) {
   upload_valid_ = false;
   rows_normalized_ = true;  // the file stores cosine rows already normalised
   h_hnsw_rows_.clear();
+  data_dirty_ = graph_dirty_ = true;
+  built_ = true;
+  ++data_gen_;
+  return Status::OK();
+}
+
+Status Engine::adopt_replica(const HnswGraph& g, const float* search_rows, const int32_t* ids, int dim) {
+  if (method_ != METHOD_HNSW) return Status::Err(kErrIncompat, "graph replica needs method hnsw");
+  if (g.empty() || !search_rows || !ids) return Status::Err(kErrInvalid, "empty graph replica");
+  graph_ = g;
+  graph_.vectors.clear();
+  dim_ = dim;
+  n_ = g.total;
+  borrowed_rows_ = search_rows;   // float rows whatever the index's element type (see hnsw_host_rows)
+  borrowed_ids_ = ids;
+  replica_rows_ = true;
+  rows_normalized_ = true;
+  upload_valid_ = false;
   data_dirty_ = graph_dirty_ = true;
   built_ = true;
   return Status::OK();
@@ -458,7 +478,8 @@ Stats Engine::stats() {
 // Rows as the HNSW kernels want them: float32, unit-normalised for cosine (the reference normalises its
 // flat index once at build time, hnsw.cc:441-446), uint8 widened to float (distances stay exact integers).
 const float* Engine::hnsw_host_rows() {
-  if (!is_u8_ && (space_ != SPACE_COSINE || rows_normalized_)) return h_f32_.data();
+  if (replica_rows_) return static_cast<const float*>(borrowed_rows_);  // search-ready rows of the engine replicated
+  if (!is_u8_ && (space_ != SPACE_COSINE || rows_normalized_)) return base_f32();
   if (h_hnsw_rows_.size() == n_ * (size_t)dim_) return h_hnsw_rows_.data();
   h_hnsw_rows_.resize(n_ * (size_t)dim_);
   for (size_t i = 0; i < n_; ++i) {

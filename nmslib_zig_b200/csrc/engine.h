@@ -177,6 +177,9 @@ class Engine {
   Status set_query_params(const std::vector<std::string>& params);  // hnsw.cc:474-507
   Status import_graph(const std::string& path);
   Status adopt_graph(HnswGraph&& g);
+  // replica of another engine's hnsw index (ShardGroup): a copy of the links over BORROWED search-ready float rows
+  // (cosine: already unit-normalised; uint8: already widened) and ids
+  Status adopt_replica(const HnswGraph& g, const float* search_rows, const int32_t* ids, int dim);
   const HnswGraph& graph() const { return graph_; }
   const float* hnsw_rows_for_save() { return hnsw_host_rows(); }
   void set_pos_base(uint32_t b) { pos_base_ = b; }
@@ -276,6 +279,7 @@ class Engine {
   std::vector<int32_t> h_ids_;
   const void* borrowed_rows_ = nullptr;    // set by borrow_host_rows: the rows / ids live in another engine's host store
   const int32_t* borrowed_ids_ = nullptr;
+  bool replica_rows_ = false;              // adopt_replica: borrowed_rows_ are search-ready FLOAT rows of an hnsw replica
   const float* base_f32() const { return borrowed_rows_ ? static_cast<const float*>(borrowed_rows_) : h_f32_.data(); }
   const uint8_t* base_u8() const { return borrowed_rows_ ? static_cast<const uint8_t*>(borrowed_rows_) : h_u8_.data(); }
   const int32_t* base_ids() const { return borrowed_ids_ ? borrowed_ids_ : h_ids_.data(); }

@@ -66,7 +66,10 @@ class HostBarrier {
 
 struct ShardGroup::Impl {
   Space space;
+  Method method = METHOD_SEQ;
   bool is_u8;
+  std::vector<std::string> query_params;
+  bool query_params_set = false;
   std::vector<int> devices;
   int active = 0;                      // shards in use (1 when the index holds fewer than two rows per device)
   std::vector<std::unique_ptr<Engine>> shards;
@@ -136,8 +139,9 @@ struct ShardGroup::Impl {
   }
 };
 
-ShardGroup::ShardGroup(Space space, bool is_u8, const std::vector<int>& devices) : impl_(new Impl()) {
+ShardGroup::ShardGroup(Space space, Method method, bool is_u8, const std::vector<int>& devices) : impl_(new Impl()) {
   impl_->space = space;
+  impl_->method = method;
   impl_->is_u8 = is_u8;
   impl_->devices = devices;
   impl_->results.resize(devices.size());
@@ -208,11 +212,48 @@ Status ShardGroup::parse_devices(const std::string& spec, std::vector<int>* out)
 
 void ShardGroup::set_index_params(const std::vector<std::string>& p) { impl_->index_params = p; }
 
+Status ShardGroup::set_query_params(const std::vector<std::string>& p) {
+  impl_->query_params = p;
+  impl_->query_params_set = true;
+  for (auto& e : impl_->shards)
+    if (e) {
+      std::lock_guard<std::mutex> lock(e->mutex());
+      Status s = e->set_query_params(p);
+      if (!s.ok()) return s;
+    }
+  return Status::OK();
+}
+
 // (Re)distribute the host store's rows over the devices and connect the exchange windows.
 Status ShardGroup::prepare(Engine* host, size_t nq, size_t k) {
   Impl& m = *impl_;
   if (!device_available()) return Status::Err(kErrQuery, "no CUDA device available (there is no CPU fallback)");
   const size_t n_rows = host->size();
+  if (m.method == METHOD_HNSW) {
+    // hnsw: one graph does not shard without changing its answers -- every device holds a REPLICA of the
+    // index (links copied, rows and ids borrowed from the host store) and takes 1/G of a batch's queries; no exchange
+    if (m.built_gen == host->data_generation() && m.shards.size() == m.devices.size()) return Status::OK();
+    if (n_rows == 0) return Status::Err(kErrQuery, "index holds no data");
+    Status gs = host->ensure_graph();  // built once (on the device when the parameters say so), or imported
+    if (!gs.ok()) return gs;
+    const float* rows = host->hnsw_rows_for_save();
+    const size_t G = m.devices.size();
+    m.shards.clear();
+    m.shards.resize(G);
+    m.active = (int)G;
+    m.barrier.reset();
+    Status s = m.run_all([&](int g) -> Status {
+      std::unique_ptr<Engine> e(new Engine(m.space, METHOD_HNSW, m.is_u8, m.devices[g]));
+      Status as = e->adopt_replica(host->graph(), rows, host->ext_id_ptr(0), host->dim());
+      if (!as.ok()) return as;
+      if (m.query_params_set && !(as = e->set_query_params(m.query_params)).ok()) return as;
+      m.shards[g] = std::move(e);
+      return m.shards[g]->prepare();
+    });
+    if (!s.ok()) return s;
+    m.built_gen = host->data_generation();
+    return Status::OK();
+  }
   // (an index of fewer than two rows per device is served by the first device alone)
   const size_t G = n_rows >= 2 * m.devices.size() ? m.devices.size() : 1;
   const bool rebuild = m.built_gen != host->data_generation() || m.shards.size() != G;
@@ -308,6 +349,28 @@ Status ShardGroup::knn_host(Engine* host, const void* queries, size_t nq, size_t
     memcpy(m.h_q.p, queries, qbytes);
     src = m.h_q.p;
   }
+  if (m.method == METHOD_HNSW) {
+    const size_t esz = m.is_u8 ? 1 : 4;
+    s = m.run_all([&](int g) -> Status {
+      const size_t q0 = nq * (size_t)g / G, q1 = nq * (size_t)(g + 1) / G;
+      if (q1 <= q0) return Status::OK();
+      std::lock_guard<std::mutex> lock(m.shards[g]->mutex());
+      const int32_t *ri, *rc;
+      const float* rd;
+      Status rs = m.shards[g]->knn_host(static_cast<const char*>(src) + q0 * elem_count * esz, q1 - q0, elem_count, k, &ri, &rd, &rc);
+      if (!rs.ok()) return rs;
+      memcpy(m.h_ids.as<int32_t>() + q0 * k, ri, (q1 - q0) * k * 4);
+      memcpy(m.h_dists.as<float>() + q0 * k, rd, (q1 - q0) * k * 4);
+      memcpy(m.h_counts.as<int32_t>() + q0, rc, (q1 - q0) * 4);
+      return Status::OK();
+    });
+    if (!s.ok()) return s;
+    m.stats.queries += nq;
+    *ids = m.h_ids.as<int32_t>();
+    *dists = m.h_dists.as<float>();
+    *counts = m.h_counts.as<int32_t>();
+    return Status::OK();
+  }
   s = m.run_all([&](int g) -> Status {
     const size_t q0 = nq * (size_t)g / G, q1 = nq * (size_t)(g + 1) / G;
     std::lock_guard<std::mutex> lock(m.shards[g]->mutex());
@@ -330,6 +393,7 @@ Stats ShardGroup::stats() {
     const Stats s = e->stats();
     out.kernel_launches += s.kernel_launches;
     out.distance_evals += s.distance_evals;
+    out.hnsw_expansions += s.hnsw_expansions;
     out.fallback_queries += s.fallback_queries;
     out.split_queries += s.split_queries;
     out.device_bytes += s.device_bytes;

@@ -183,8 +183,12 @@ def test_sharding_entry_points_validate_without_a_device():
     idx.deinit()
     hn = nb.Index("l2", None, "hnsw")
     hn.addDenseBatch(np.eye(4, dtype=np.float32))
-    with pytest.raises(nb.NmslibError):                        # hnsw does not shard by rows: unknown parameter
-        hn.buildIndex(nb.Params({"b200_devices": "0,1"}))
+    hn.buildIndex(nb.Params({"b200_devices": "0,1"}))          # hnsw: replicas of the graph, queries split
+    with pytest.raises(nb.NmslibError):
+        hn.buildIndex(nb.Params({"b200_devices": "0,,1"}))
+    if not nb.device_available():
+        with pytest.raises(nb.NmslibError):                    # no device: the query fails, nothing falls back to the host
+            hn.knnQueryBatch(np.eye(4, dtype=np.float32), 2)
     hn.deinit()
     with pytest.raises(nb.NmslibError):
         nb.set_option("no_such_option", 1)

@@ -4,6 +4,7 @@ oracle's unsharded answer, and equal the single-GPU answer bit for bit."""
 import os
 import socket
 import sys
+import tempfile
 from pathlib import Path
 
 import numpy as np
@@ -174,3 +175,50 @@ def test_shard_group_on_two_gpus_equals_the_single_index():
         pytest.skip("needs 2 GPUs")
     _group_matches_single("l2", 50_001, 128, 1000, 10, "0,1")
     _group_matches_single("l2sqr_sift", 40_000, 128, 300, 10, "0-1")
+
+
+def _hnsw_group_matches_single(space, devices):
+    """method hnsw + b200_devices: every device holds a replica of the graph and takes a slice of the batch; the answers
+    are those of the one-device index (same graph: the group's host index builds it once, the plain index imports it)."""
+    import nmslib_zig_b200 as nb
+    from nmslib_zig_b200 import synth
+    n, dim, nq, k = 6000, 48, 301, 10
+    data, q = synth.uniform(n, dim, 1), synth.uniform(nq, dim, 2)
+    ext = np.arange(n, dtype=np.int32) * 2 + 11
+    grp = nb.Index(space, None, "hnsw")
+    grp.addDenseBatch(data, ext)
+    grp.buildIndex(nb.Params({"M": 12, "efConstruction": 80, "b200_build": "host", "b200_devices": devices}))
+    grp.setQueryTimeParams(nb.Params({"efSearch": 64}))
+    b = grp.knnQueryBatch(q, k)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "g.hnsw")
+        grp.save(path)                                     # the graph the replicas search
+        one = nb.Index.load(path)
+    one.setQueryTimeParams(nb.Params({"efSearch": 64}))
+    a = one.knnQueryBatch(q, k)
+    assert np.array_equal(a.ids, b.ids) and np.array_equal(a.distances.view(np.int32), b.distances.view(np.int32))
+    assert np.array_equal(a.sizes, b.sizes)
+    grp.setQueryTimeParams(nb.Params({"efSearch": 200}))   # reaches every replica
+    one.setQueryTimeParams(nb.Params({"efSearch": 200}))
+    a, b = one.knnQueryBatch(q[:50], k), grp.knnQueryBatch(q[:50], k)
+    assert np.array_equal(a.ids, b.ids)
+    single = grp.knnQuery(q[1], k)
+    assert np.array_equal(single.ids, a.ids[1][:len(single.ids)])
+    st = grp.stats()
+    assert st["kernel_launches"] > 0 and st["queries"] >= nq
+    one.deinit()
+    grp.deinit()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("space", ["l2", "cosinesimil"])
+def test_hnsw_replicas_on_one_device_match_plain_index(space):
+    _hnsw_group_matches_single(space, "0,0")
+
+
+@pytest.mark.gpu
+def test_hnsw_replicas_on_two_devices_match_plain_index():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _hnsw_group_matches_single("l2", "0,1")
