@@ -386,45 +386,63 @@ __device__ __forceinline__ float group_min8(const float (&r)[32], int q) {
               fminf(r[8 * q + 6], r[8 * q + 7]));
 }
 
-// Per-lane selection of one 32-column chunk whose group minima are g[0..3] (divergent: only lanes that hold a
-// survivor work).  About a third of all (warp, tile) pairs of config 2 have a survivor in SOME lane, so this path is
-// hot for the instruction cache and has to stay small: one copy of the insertion code per group of 8 values, walked
-// by a bit mask (two other shapes were measured and rejected: fully unrolled over the 64 registers -- 40 KB of code,
-// 2 x slower, stall_no_inst -- and a per-thread scratch array in local memory walked with dynamic indices -- 3 x
-// slower, the stores delay the next tile's tensor-memory drain).
+// Per-lane selection over one 64-column tile whose group minima are g0[0..3], g1[0..3] (divergent: only lanes that
+// hold a survivor work).  A lane walks ITS OWN groups with a survivor (bit mask over the tile's 8 groups) and fetches
+// the group's 8 values through three levels of selects, so the warp runs max-over-lanes(groups with a survivor) rounds.
+// The first version walked the groups warp-uniformly (static register names, one round for every group in which ANY
+// lane had a survivor): in a piece's start-up phase and on short shards nearly every tile has a handful of survivors
+// scattered over lanes and groups -- 6-8 rounds of ~115 instructions with one or two lanes active each, where this
+// shape needs 1-2 rounds of ~170.  Measured (tools/tc_exp.py, release build): 125 K-row shard 0.678 -> 0.526 ms,
+// config 2 3.03 -> 2.82 ms, config 1 0.113 -> 0.086 ms.  The path is hot for the instruction cache and has to stay
+// small: ONE copy of the insertion code, walked by bit masks (also measured and rejected: fully unrolled over the 64
+// registers -- 40 KB of code, 2 x slower, stall_no_inst -- and a per-thread scratch array in local memory walked with
+// dynamic indices -- 3 x slower, the stores delay the next tile's tensor-memory drain).
 template <bool REG>
-__device__ __forceinline__ void epi_select(const float (&r)[32], const float (&g)[4], uint32_t pos0, uint64_t* buf, int& cnt,
-                                           float& thr, float (&tk)[TS_RK], uint32_t* gthr) {
+__device__ __forceinline__ void epi_select_tile(const float (&r0)[32], const float (&r1)[32], const float (&g0)[4],
+                                                const float (&g1)[4], uint32_t pos0, uint64_t* buf, int& cnt, float& thr,
+                                                float (&tk)[TS_RK], uint32_t* gthr) {
+  unsigned gm = 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    if (g[q] < thr) {
-      unsigned mk = 0;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] < thr ? 1u : 0u) << jj;
+    gm |= (g0[q] < thr ? 1u : 0u) << q;
+    gm |= (g1[q] < thr ? 1u : 0u) << (q + 4);
+  }
 #pragma unroll 1
-      while (mk) {
-        const int jj = __ffs(mk) - 1;
-        mk &= mk - 1;
-        const float lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
-        const float hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
-        const float x = (jj & 4) ? hi4 : lo4;
-        if (!REG || x < thr) {  // (REG: the threshold may have moved since the mask was made)
-          buf[cnt] = ((uint64_t)__float_as_uint(x) << 32) | (uint64_t)(pos0 + 8 * q + jj);
-          ++cnt;
-          if constexpr (REG) {
-            // sorted insertion with every slot computed independently (depth 2 instead of a 16-step chain):
-            // new tk[i] = max(tk[i-1], min(tk[i], x)); x < thr <= tk[15], so the old tk[15] drops out
-            float prev = __int_as_float(0xFF800000);
+  while (gm) {
+    const int q = __ffs(gm) - 1;
+    gm &= gm - 1;
+    const bool b0 = q & 1, b1 = q & 2, b2 = q & 4;
+    float v[8];
+    unsigned mk = 0;
 #pragma unroll
-            for (int i = 0; i < TS_RK; ++i) {
-              const float cur = tk[i];
-              tk[i] = fmaxf(prev, fminf(cur, x));
-              prev = cur;
-            }
-            if (tk[TS_RK - 1] < thr) {
-              thr = tk[TS_RK - 1];
-              atomicMin(gthr, f32_ordered(thr));  // (result unused: a fire-and-forget reduction)
-            }
+    for (int j = 0; j < 8; ++j) {
+      const float a = b0 ? r0[8 + j] : r0[j], b = b0 ? r0[24 + j] : r0[16 + j];
+      const float c = b0 ? r1[8 + j] : r1[j], d = b0 ? r1[24 + j] : r1[16 + j];
+      const float ab = b1 ? b : a, cd = b1 ? d : c;
+      v[j] = b2 ? cd : ab;
+      mk |= (v[j] < thr ? 1u : 0u) << j;
+    }
+#pragma unroll 1
+    while (mk) {
+      const int jj = __ffs(mk) - 1;
+      mk &= mk - 1;
+      const float lo4 = (jj & 2) ? ((jj & 1) ? v[3] : v[2]) : ((jj & 1) ? v[1] : v[0]);
+      const float hi4 = (jj & 2) ? ((jj & 1) ? v[7] : v[6]) : ((jj & 1) ? v[5] : v[4]);
+      const float x = (jj & 4) ? hi4 : lo4;
+      if (!REG || x < thr) {  // (REG: the threshold may have moved since the mask was made)
+        buf[cnt] = ((uint64_t)__float_as_uint(x) << 32) | (uint64_t)(pos0 + 8 * q + jj);
+        ++cnt;
+        if constexpr (REG) {
+          float prev = __int_as_float(0xFF800000);
+#pragma unroll
+          for (int i = 0; i < TS_RK; ++i) {
+            const float cur = tk[i];
+            tk[i] = fmaxf(prev, fminf(cur, x));
+            prev = cur;
+          }
+          if (tk[TS_RK - 1] < thr) {
+            thr = tk[TS_RK - 1];
+            atomicMin(gthr, f32_ordered(thr));  // (result unused: a fire-and-forget reduction)
           }
         }
       }
@@ -1405,8 +1423,7 @@ tc_scan_ts_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         ++ctr[1];
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TS_BN);
         if (mm < thr || vtile < TS_BN) {
-          epi_select<REG>(r0, g0, pos_tile, buf, cnt, thr, tk, gthr);
-          epi_select<REG>(r1, g1, pos_tile + 32, buf, cnt, thr, tk, gthr);
+          epi_select_tile<REG>(r0, r1, g0, g1, pos_tile, buf, cnt, thr, tk, gthr);
         }
         if constexpr (REG) continue;
         // deferred compaction: a row past the high-water mark is compacted here, at most one row per warp and
@@ -1521,38 +1538,53 @@ __device__ __forceinline__ int u8_acc_of_rank(float rank, int m_half) {  // pass
   return m_half - (__float2int_rd(rank) >> 1) - ((__float2int_rd(rank) & 1) ? 1 : 0) + 0;
 }
 
-// per-lane selection of one 32-column chunk (integer twin of epi_select): acc > thr passes
+// per-lane selection over one 64-column tile (integer twin of epi_select_tile): acc > thr passes
 template <bool REG>
-__device__ __forceinline__ void epi_select_i(const int (&r)[32], const int (&g)[4], uint32_t pos0, uint64_t* buf, int& cnt,
-                                             int& thr, int (&tk)[TS_RK], uint32_t* gthr, int m_half) {
+__device__ __forceinline__ void epi_select_tile_i(const int (&r0)[32], const int (&r1)[32], const int (&g0)[4],
+                                                  const int (&g1)[4], uint32_t pos0, uint64_t* buf, int& cnt, int& thr,
+                                                  int (&tk)[TS_RK], uint32_t* gthr, int m_half) {
+  unsigned gm = 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    if (g[q] > thr) {
-      unsigned mk = 0;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) mk |= (r[8 * q + jj] > thr ? 1u : 0u) << jj;
+    gm |= (g0[q] > thr ? 1u : 0u) << q;
+    gm |= (g1[q] > thr ? 1u : 0u) << (q + 4);
+  }
 #pragma unroll 1
-      while (mk) {
-        const int jj = __ffs(mk) - 1;
-        mk &= mk - 1;
-        const int lo4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 3] : r[8 * q + 2]) : ((jj & 1) ? r[8 * q + 1] : r[8 * q]);
-        const int hi4 = (jj & 2) ? ((jj & 1) ? r[8 * q + 7] : r[8 * q + 6]) : ((jj & 1) ? r[8 * q + 5] : r[8 * q + 4]);
-        const int x = (jj & 4) ? hi4 : lo4;
-        if (!REG || x > thr) {
-          buf[cnt] = ((uint64_t)__float_as_uint(u8_rank_of(x, m_half)) << 32) | (uint64_t)(pos0 + 8 * q + jj);
-          ++cnt;
-          if constexpr (REG) {  // 16 best accumulators, descending; every slot computed independently
-            int prev = 0x7FFFFFFF;
+  while (gm) {
+    const int q = __ffs(gm) - 1;
+    gm &= gm - 1;
+    const bool b0 = q & 1, b1 = q & 2, b2 = q & 4;
+    int v[8];
+    unsigned mk = 0;
 #pragma unroll
-            for (int i = 0; i < TS_RK; ++i) {
-              const int cur = tk[i];
-              tk[i] = min(prev, max(cur, x));
-              prev = cur;
-            }
-            if (tk[TS_RK - 1] > thr) {
-              thr = tk[TS_RK - 1];
-              atomicMin(gthr, f32_ordered(u8_rank_of(thr, m_half)));
-            }
+    for (int j = 0; j < 8; ++j) {
+      const int a = b0 ? r0[8 + j] : r0[j], b = b0 ? r0[24 + j] : r0[16 + j];
+      const int c = b0 ? r1[8 + j] : r1[j], d = b0 ? r1[24 + j] : r1[16 + j];
+      const int ab = b1 ? b : a, cd = b1 ? d : c;
+      v[j] = b2 ? cd : ab;
+      mk |= (v[j] > thr ? 1u : 0u) << j;
+    }
+#pragma unroll 1
+    while (mk) {
+      const int jj = __ffs(mk) - 1;
+      mk &= mk - 1;
+      const int lo4 = (jj & 2) ? ((jj & 1) ? v[3] : v[2]) : ((jj & 1) ? v[1] : v[0]);
+      const int hi4 = (jj & 2) ? ((jj & 1) ? v[7] : v[6]) : ((jj & 1) ? v[5] : v[4]);
+      const int x = (jj & 4) ? hi4 : lo4;
+      if (!REG || x > thr) {
+        buf[cnt] = ((uint64_t)__float_as_uint(u8_rank_of(x, m_half)) << 32) | (uint64_t)(pos0 + 8 * q + jj);
+        ++cnt;
+        if constexpr (REG) {  // 16 best accumulators, descending; every slot computed independently
+          int prev = 0x7FFFFFFF;
+#pragma unroll
+          for (int i = 0; i < TS_RK; ++i) {
+            const int cur = tk[i];
+            tk[i] = min(prev, max(cur, x));
+            prev = cur;
+          }
+          if (tk[TS_RK - 1] > thr) {
+            thr = tk[TS_RK - 1];
+            atomicMin(gthr, f32_ordered(u8_rank_of(thr, m_half)));
           }
         }
       }
@@ -1757,9 +1789,10 @@ tc_scan_u8_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         }
         const int mm = max3i(max(max3i(g0[0], g0[1], g0[2]), max3i(g0[3], g1[0], g1[1])), g1[2], g1[3]);
         const int vtile = p.n - tile * TS_BN;
-        const bool uni = (((tile - t_begin) & p.refresh_mask) == 0) | (vtile < TS_BN);
+        const bool uni = ((((tile - t_begin) & p.refresh_mask) == 0) & !NB200_DBG(p.debug, 4)) | (vtile < TS_BN);
         const bool mine = (mm > thr) | (cnt > guard);
         if (!uni && !__any_sync(FULL, mine)) continue;
+        if (NB200_DBG(p.debug, 2) && tile - t_begin > 64) continue;  // timing experiment: the fast path only
         // ------------------------------------------------------------------ slow path
         if (((tile - t_begin) & p.refresh_mask) == 0 && row_valid)
           thr = max(thr, u8_acc_of_rank(f32_from_ordered(*gthr), p.m_half));
@@ -1787,8 +1820,7 @@ tc_scan_u8_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         ++ctr[1];
         const uint32_t pos_tile = p.pos_base + (uint32_t)(tile * TS_BN);
         if (mm > thr || vtile < TS_BN) {
-          epi_select_i<REG>(r0, g0, pos_tile, buf, cnt, thr, tk, gthr, p.m_half);
-          epi_select_i<REG>(r1, g1, pos_tile + 32, buf, cnt, thr, tk, gthr, p.m_half);
+          epi_select_tile_i<REG>(r0, r1, g0, g1, pos_tile, buf, cnt, thr, tk, gthr, p.m_half);
         }
         if constexpr (REG) continue;
         const unsigned pend = __ballot_sync(FULL, cnt > p.hwm);

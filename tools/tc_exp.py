@@ -32,7 +32,10 @@ KNOBS = ("NB200_TC_DEBUG", "NB200_TC_HWM", "NB200_TC_WARM", "NB200_TC_REFRESH", 
 for s in settings:
     for kk in KNOBS:
         os.environ.pop(kk, None)
-    os.environ.update(s)
+    os.environ.update({a: b for a, b in s.items() if not a.startswith("opt:")})
+    for a, b in s.items():       # "opt:<name>": a documented variant selector (nmslib_b200_set_option)
+        if a.startswith("opt:"):
+            nb.set_option(a[4:], int(b))
     idx = (nb.Index(space, None, "seq_search", "DenseUInt8Vector", "Int") if u8 else nb.Index(space, None, "seq_search"))
     (idx.addUInt8Batch if u8 else idx.addDenseBatch)(data)
     idx.buildIndex()
