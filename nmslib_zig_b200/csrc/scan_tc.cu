@@ -1894,6 +1894,7 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const RerankParams p, in
   __shared__ int s_cnt[64];
   __shared__ int s_red[8];
   __shared__ int s_live;
+  __shared__ uint32_t s_ak, s_worst;
   __shared__ float s_wmin[2], s_qn2;
   const int q = p.q_begin + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = blockDim.x >> 5;  // 4, or 8 for long rows / large k (more candidate rows in flight)
@@ -1915,7 +1916,11 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const RerankParams p, in
     for (int o = 16; o > 0; o >>= 1) mt = fminf(mt, __shfl_xor_sync(FULL, mt, o));
     if (lane == 0) s_wmin[warp] = mt;
   }
-  if (tid == 0) s_live = 0;
+  if (tid == 0) {
+    s_live = 0;
+    s_ak = 0xFFFFFFFFu;
+    s_worst = 0u;
+  }
   if (warp == 2) {
     float s = 0.f;
     if (p.q_u8) {  // 128 bytes: one uchar4 per lane, exact integer sum
@@ -1965,6 +1970,23 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const RerankParams p, in
     uint32_t cut = 0xFFFFFFFFu;
     if (total > p.k) {
       uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+      if (total <= 256) {
+        // the usual case, a few dozen live keys: every thread counts the keys below / at its own one -- no barrier per
+        // step (the 32-step bisection below, two barriers each, was 42 % of this kernel's stall samples on a short
+        // shard, profiles/README.md).  Exactly one VALUE v has #(ord < v) < k <= #(ord <= v).
+        for (int i = tid; i < total; i += blockDim.x) {
+          const uint32_t v = sord[i];
+          int lt = 0, le = 0;
+          for (int j = 0; j < total; ++j) {
+            const uint32_t u = sord[j];
+            lt += u < v ? 1 : 0;
+            le += u <= v ? 1 : 0;
+          }
+          if (lt < p.k && le >= p.k) s_ak = v;
+        }
+        __syncthreads();
+        lo = hi = s_ak;
+      }
       while (lo < hi) {  // smallest v with #(ord <= v) >= k
         const uint32_t mid = lo + ((hi - lo) >> 1);
         int c = 0;
@@ -2089,11 +2111,28 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const RerankParams p, in
     }
   }
   __syncthreads();
-  for (int t = total + tid; t < p2e; t += blockDim.x) srank[t] = __int_as_float(0x7F800000);
+  const bool rank_sort = total <= 128;
+  if (rank_sort) {
+    // few candidates (the usual case after the second filter): a key's place in the answer is the number of keys
+    // below it (keys are distinct: the position is part of the key) -- no barriers, where the bitonic network below
+    // spends 15 of them on 32 keys
+    for (int i = tid; i < total; i += blockDim.x) {
+      const uint64_t key = sk[i];
+      int r = 0;
+      for (int j = 0; j < total; ++j) r += sk[j] < key ? 1 : 0;
+      if (r < p.k) {
+        p.out_keys[(size_t)q * p.k + r] = key;
+        atomicMax(&s_worst, f32_ordered(srank[i]));
+      }
+    }
+    for (int e = total + tid; e < p.k; e += blockDim.x) p.out_keys[(size_t)q * p.k + e] = KEY_MAX;
+    __syncthreads();
+  }
+  for (int t = total + tid; t < p2e && !rank_sort; t += blockDim.x) srank[t] = __int_as_float(0x7F800000);
   __syncthreads();
 
   // sort (key, rank) ascending by key
-  for (int size = 2; size <= p2e; size <<= 1) {
+  for (int size = 2; size <= p2e && !rank_sort; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = tid; t < p2e / 2; t += blockDim.x) {
         const int lo = 2 * t - (t & (stride - 1));
@@ -2111,7 +2150,7 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const RerankParams p, in
       __syncthreads();
     }
   }
-  for (int e = tid; e < p.k; e += blockDim.x) p.out_keys[(size_t)q * p.k + e] = e < p2e ? sk[e] : KEY_MAX;
+  for (int e = tid; e < p.k && !rank_sort; e += blockDim.x) p.out_keys[(size_t)q * p.k + e] = e < p2e ? sk[e] : KEY_MAX;
 
   if (tid == 0) {
     // certificate: every non-candidate has approximate rank >= s_minthr, exact rank >= s_minthr - E
@@ -2126,7 +2165,9 @@ __global__ void __launch_bounds__(256) tc_rerank_kernel(const RerankParams p, in
       const float E = E_q;
       // worst exact rank among the k answers (ranks are not exactly monotone in the key for cosine)
       float worst = __int_as_float(0xFF800000);
-      for (int e = 0; e < p.k; ++e) worst = fmaxf(worst, srank[e]);
+      if (rank_sort) worst = f32_from_ordered(s_worst);
+      else
+        for (int e = 0; e < p.k; ++e) worst = fmaxf(worst, srank[e]);
       cert = (worst + E + fabsf(worst) * 1e-6f < minthr) ? 1 : 0;
     }
     p.out_cert[q] = cert;
