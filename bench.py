@@ -454,6 +454,14 @@ def run_seq(args, w, rank, world, local_rank, dev, dist_on, steps, warmup, with_
     n, nq, dim, k = w["n"], w["nq"], w["dim"], w["k"]
     u8 = w["dtype"] == "DenseUInt8Vector"
     lo, hi = w["lo"], w["hi"]
+    # (the CUDA context, the library's stream and its upload kernels exist before the ingest clock starts: a throw-away
+    # index of the same kind goes through the same calls once)
+    torch.zeros(1, device=dev)
+    tiny = nb.Index(w["space"], None, w["method"], w["dtype"], w["dist"])
+    (tiny.addUInt8Batch if u8 else tiny.addDenseBatch)(w["data"][:256])
+    tiny.buildIndex()
+    tiny.prepare()
+    tiny.deinit()
     idx = nb.Index(w["space"], None, w["method"], w["dtype"], w["dist"])
     idx.setShard(lo)                                   # keys carry GLOBAL positions (tie order)
     shard_ids = np.arange(lo, hi, dtype=np.int32)
@@ -465,7 +473,7 @@ def run_seq(args, w, rank, world, local_rank, dev, dist_on, steps, warmup, with_
     t_ing = time.perf_counter() - t_ing
     ingest = {"rows": int(hi - lo), "seconds": t_ing, "add_seconds": t_add, "rows_per_s": (hi - lo) / t_ing,
               "gbytes_per_s": w["data"].nbytes / t_ing / 1e9,
-              "what": "nmslib_add_data_point_batch (one slab copy on the host) + upload + operand preparation, one rank"}
+              "what": "nmslib_add_data_point_batch (one slab copy on the host) + upload + operand preparation, one rank; CUDA context and kernels loaded beforehand by a 256-row index"}
 
     q_host = torch.from_numpy(w["queries"]).pin_memory()
     d_q = q_host.to(dev, non_blocking=False)

@@ -448,9 +448,14 @@ nmslib_error_t nmslib_knn_query_batch(nmslib_index_handle_t index, const void* q
   if (!index || !queries || query_count == 0 || !results || elem_count == 0)
     return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Invalid batch knn inputs");
   if (k == 0) return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "k must be positive");
-  for (size_t i = 0; i < query_count; ++i)
+  // (two result slabs cut into rows of k, the batch shape INTEGRATION.md gives lib.zig: filled by two copies below)
+  bool slabs = true;
+  for (size_t i = 0; i < query_count; ++i) {
     if (!results[i].ids || !results[i].distances || results[i].capacity == 0)
       return NB_ERR(NMSLIB_ERROR_INVALID_ARGUMENT, "Result buffers invalid");
+    slabs = slabs && results[i].capacity >= k && results[i].ids == results[0].ids + i * k &&
+            results[i].distances == results[0].distances + i * k;
+  }
   return guarded(
       [&]() -> nmslib_error_t {
         Engine* e = index->engine;
@@ -462,6 +467,12 @@ nmslib_error_t nmslib_knn_query_batch(nmslib_index_handle_t index, const void* q
         if (!s.ok()) {
           for (size_t i = 0; i < query_count; ++i) results[i].size = 0;
           return NB_STATUS(s);
+        }
+        if (slabs) {  // (entries past a row's size are the engine's padding: id -1, distance +inf)
+          memcpy(results[0].ids, ids, query_count * k * sizeof(int32_t));
+          memcpy(results[0].distances, dists, query_count * k * sizeof(float));
+          for (size_t i = 0; i < query_count; ++i) results[i].size = (size_t)counts[i];
+          return NB_OK("Batch knn query executed");
         }
         bool too_small = false;
         for (size_t i = 0; i < query_count; ++i) {  // extract_knn_results, ref :293-328

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <sstream>
+#include <atomic>
 #include <thread>
 
 namespace nb200 {
@@ -201,6 +202,13 @@ Engine::~Engine() {
   for (auto& e : copy_ev_)
     if (e) cudaEventDestroy(e);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
+  h_stage_.release();
+  if (stage_ready_) cudaEventDestroy(stage_ready_);
+  for (int t = 0; t < kStageThreads; ++t) {
+    for (auto& e : stage_ev_[t])
+      if (e) cudaEventDestroy(e);
+    if (stage_stream_[t]) cudaStreamDestroy(stage_stream_[t]);
+  }
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -581,9 +589,7 @@ Status Engine::upload_data() {
       ++stats_.kernel_launches;
     }
   } else {
-    s = check_cuda(cudaMemcpy2DAsync(d_db_.as<char>() + r0 * row_bytes, row_bytes, static_cast<const char*>(src) + r0 * src_row,
-                                     src_row, src_row, n_ - r0, cudaMemcpyHostToDevice, stream_),
-                   "H2D(data)");
+    s = upload_rows(d_db_.as<char>() + r0 * row_bytes, row_bytes, static_cast<const char*>(src) + r0 * src_row, src_row, n_ - r0);
     if (!s.ok()) return s;
   }
   if (!rows_borrowed_) {
@@ -676,6 +682,56 @@ Status Engine::upload_data() {
   data_dirty_ = false;
   stats_.device_bytes = d_db_.cap + d_ids_.cap + d_aux_.cap + d_bias_.cap + d_db_unit_.cap + d_nblock_.cap;
   return Status::OK();
+}
+
+// Host rows -> padded device rows.  The host slab is pageable (it is the index's own copy of the caller's data,
+// nmslib_c.cpp:755-871 copies every point as well): a plain cudaMemcpy from it goes through the driver's staging buffer
+// on the calling thread, 7-10 GB/s measured (tools/ingest_split.py).  From 256 MB up the rows travel through pinned
+// staging buffers instead: kStageThreads host threads each copy 4 MB chunks into their own pair of pinned buffers and
+// queue the H2D on their own stream, so the host copies of some chunks overlap the bus transfers of others.
+Status Engine::upload_rows(char* dst, size_t dst_pitch, const char* src, size_t src_row, size_t rows) {
+  const size_t bytes = rows * src_row;
+  if (bytes < (256u << 20) || src_row > kStageBytes)
+    return check_cuda(cudaMemcpy2DAsync(dst, dst_pitch, src, src_row, src_row, rows, cudaMemcpyHostToDevice, stream_), "H2D(data)");
+  Status s = check_cuda(h_stage_.ensure((size_t)kStageThreads * 2 * kStageBytes), "cudaMallocHost(staging)");
+  if (!s.ok()) return s;
+  if (!stage_ready_) {
+    if (!(s = check_cuda(cudaEventCreateWithFlags(&stage_ready_, cudaEventDisableTiming), "cudaEventCreate")).ok()) return s;
+    for (int t = 0; t < kStageThreads; ++t) {
+      if (!(s = check_cuda(cudaStreamCreateWithFlags(&stage_stream_[t], cudaStreamNonBlocking), "cudaStreamCreate")).ok()) return s;
+      for (auto& e : stage_ev_[t])
+        if (!(s = check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")).ok()) return s;
+    }
+  }
+  // the copy streams start behind what stream_ has queued for the destination (the padding memset)
+  if (!(s = check_cuda(cudaEventRecord(stage_ready_, stream_), "cudaEventRecord")).ok()) return s;
+  const size_t chunk_rows = std::max<size_t>(1, kStageBytes / src_row);
+  const size_t n_chunks = (rows + chunk_rows - 1) / chunk_rows;
+  std::atomic<size_t> next{0};
+  std::atomic<int> err{(int)cudaSuccess};
+  std::vector<std::thread> pool;
+  for (int t = 0; t < kStageThreads; ++t)
+    pool.emplace_back([&, t] {
+      cudaError_t e = cudaSetDevice(device_);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(stage_stream_[t], stage_ready_, 0);
+      for (int it = 0; e == cudaSuccess; ++it) {
+        const size_t c = next.fetch_add(1);
+        if (c >= n_chunks) break;
+        const int b = it & 1;
+        char* st = h_stage_.as<char>() + ((size_t)t * 2 + b) * kStageBytes;
+        if (it >= 2) e = cudaEventSynchronize(stage_ev_[t][b]);  // the transfer that last used this buffer
+        if (e != cudaSuccess) break;
+        const size_t c0 = c * chunk_rows, cnt = std::min(chunk_rows, rows - c0);
+        memcpy(st, src + c0 * src_row, cnt * src_row);
+        e = cudaMemcpy2DAsync(dst + c0 * dst_pitch, dst_pitch, st, src_row, src_row, cnt, cudaMemcpyHostToDevice, stage_stream_[t]);
+        if (e == cudaSuccess) e = cudaEventRecord(stage_ev_[t][b], stage_stream_[t]);
+      }
+      const cudaError_t e2 = cudaStreamSynchronize(stage_stream_[t]);
+      if (e == cudaSuccess) e = e2;
+      if (e != cudaSuccess) err.store((int)e);
+    });
+  for (auto& th : pool) th.join();
+  return check_cuda((cudaError_t)err.load(), "H2D(data, staged)");
 }
 
 // No imported graph: build one on the host cores (hnsw_build.cpp) with the index-time parameters

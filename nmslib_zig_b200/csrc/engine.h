@@ -339,6 +339,14 @@ class Engine {
   int hnsw_slots_ = 0;
   DevBuf d_q_, d_qaux_, d_partial_, d_keys_, d_out_ids_, d_out_dists_, d_out_counts_;
   PinBuf h_out_ids_, h_out_dists_, h_out_counts_, h_q_;
+  // large uploads: pinned staging, kStageThreads host threads x 2 buffers each, one copy stream per thread
+  static constexpr int kStageThreads = 4;
+  static constexpr size_t kStageBytes = 4u << 20;  // (pinning memory is slow, ~0.5 GB/s: 32 MB in all)
+  PinBuf h_stage_;
+  cudaStream_t stage_stream_[kStageThreads] = {};
+  cudaEvent_t stage_ev_[kStageThreads][2] = {};
+  cudaEvent_t stage_ready_ = nullptr;
+  Status upload_rows(char* dst, size_t dst_pitch, const char* src, size_t src_row, size_t rows);
   Stats stats_;
   PeerExchange* xch_ = nullptr;
   std::function<Status(cudaStream_t)> xch_hook_;

@@ -374,20 +374,28 @@ class Index:
         nq, dim = q.shape
         if nq == 0:
             return BatchResult(np.empty((0, k), np.int32), np.empty((0, k), np.float32), np.empty(0, np.int64))
-        ids = np.full((nq, k), -1, np.int32)
-        dists = np.full((nq, k), np.inf, np.float32)
-        results = (Result * nq)()
-        ip = ids.ctypes.data
-        dp = dists.ctypes.data
-        # fill the descriptor table without a Python-level loop over ctypes objects
-        tbl = np.frombuffer(results, dtype=np.uint64).reshape(nq, 4)
-        tbl[:, 0] = ip + np.arange(nq, dtype=np.uint64) * np.uint64(4 * k)
-        tbl[:, 1] = dp + np.arange(nq, dtype=np.uint64) * np.uint64(4 * k)
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        # the descriptor table of a batch shape is kept between calls (taken out while in use: a concurrent caller
+        # builds its own) and filled without a Python-level loop over ctypes objects
+        cached, self._batch_tbl = getattr(self, "_batch_tbl", None), None
+        if cached is None or cached[0] != (nq, k):
+            results = (Result * nq)()
+            tbl = np.frombuffer(results, dtype=np.uint64).reshape(nq, 4)
+            tbl[:, 3] = k
+            cached = ((nq, k), results, tbl, np.arange(nq, dtype=np.uint64) * np.uint64(4 * k))
+        _, results, tbl, off = cached
+        tbl[:, 0] = off + np.uint64(ids.ctypes.data)
+        tbl[:, 1] = off + np.uint64(dists.ctypes.data)
         tbl[:, 2] = 0
-        tbl[:, 3] = k
         _check(L.nmslib_knn_query_batch(self.handle, q.ctypes.data, nq, dim, k, results, None,
                                         thread_pool_size or 0))
         sizes = tbl[:, 2].astype(np.int64)
+        self._batch_tbl = cached
+        if sizes.min() < k:                        # rows with fewer than k answers: id -1 / distance +inf behind them
+            short = np.arange(k)[None, :] >= sizes[:, None]
+            ids[short] = -1
+            dists[short] = np.inf
         return BatchResult(ids, dists, sizes)
 
     def rangeQuery(self, query, radius: float, capacity: Optional[int] = None):

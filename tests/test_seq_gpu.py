@@ -595,3 +595,31 @@ def test_appended_rows_are_uploaded_alone_and_answers_equal_a_fresh_index(space)
                        atol=ATOL_COSINE if space == "cosinesimil" else None)
     idx.deinit()
     fresh.deinit()
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_large_upload_through_pinned_staging_lands_every_chunk_in_place(u8):
+    """Uploads of 256 MB and more travel in 4 MB chunks through pinned staging buffers, several host threads and copy
+    streams (engine.cu upload_rows): every row must arrive at its own position -- rows on both sides of
+    every chunk boundary are queried for themselves."""
+    if u8:
+        n, dim = 2_200_000, 128                      # 282 MB of byte rows (32 768 rows per chunk)
+        rng = np.random.default_rng(5)
+        data = rng.integers(0, 256, (n, dim), dtype=np.uint8)
+        idx = nb.Index("l2sqr_sift", None, "seq_search", "DenseUInt8Vector", "Int")
+        idx.addUInt8Batch(data)
+        per_chunk = (4 << 20) // dim
+    else:
+        n, dim = 600_000, 120                        # 288 MB; rows of 480 bytes padded to 512 on the device
+        data = synth.uniform(n, dim, 9)
+        idx = nb.Index("l2", None, "seq_search")
+        idx.addDenseBatch(data)
+        per_chunk = (4 << 20) // (dim * 4)
+    idx.buildIndex()
+    pos = np.unique(np.concatenate([np.arange(0, n, per_chunk), np.arange(per_chunk - 1, n, per_chunk), [n - 1],
+                                    np.random.default_rng(1).integers(0, n, 64)]))
+    r = idx.knnQueryBatch(data[pos], 1)
+    assert np.array_equal(r.ids[:, 0], pos.astype(np.int32))
+    assert np.all(r.distances[:, 0] == 0)
+    assert idx.stats()["uploaded_rows"] == n
+    idx.deinit()
