@@ -1,5 +1,5 @@
 """Three config-2 query batches (the ncu target: `-k regex:tc_scan -s 1 -c 1` captures a warm launch).
-usage: tc_prof.py [dim] [n] [nq] [k] [space]   (space negdotprod: the embedding-shaped rows of config 5)"""
+usage: tc_prof.py [dim] [n] [nq] [k] [space]   (space negdotprod: the embedding-shaped rows of config 5; l2sqr_sift: uint8 rows)"""
 import sys
 from pathlib import Path
 
@@ -18,8 +18,13 @@ elif space == "cosinesimil":
     data, q = synth.gist_like(n, dim, 5), synth.gist_like(nq, dim, 6)
 else:
     data, q = synth.sift_like_f32(n, 3, dim), synth.sift_like_f32(nq, 4, dim)
-idx = nb.Index(space, None, "seq_search")
-idx.addDenseBatch(data)
+if space == "l2sqr_sift":
+    data, q = synth.sift_like_u8(n, 7), synth.sift_like_u8(nq, 8)
+    idx = nb.Index(space, None, "seq_search", "DenseUInt8Vector", "Int")
+    idx.addUInt8Batch(data)
+else:
+    idx = nb.Index(space, None, "seq_search")
+    idx.addDenseBatch(data)
 idx.buildIndex()
 for _ in range(3):
     idx.knnQueryBatch(q, k)
