@@ -299,7 +299,9 @@ size_t nmslib_b200_scan_plan_pairs(size_t query_count, size_t n, size_t k, int s
                                    size_t capacity, int* n_pairs, int* s_max);
 
 /* ---- row-sharded multi-GPU search behind this ABI (the reference's chunk-and-merge, seqsearch.cc:151-175,
- * with a GPU per chunk).  seq_search / brute_force only; an hnsw graph does not shard without changing its answers.
+ * with a GPU per chunk).  Row shards are for seq_search / brute_force; an hnsw graph does not shard without changing its
+ * answers, so under (A) an hnsw index gets one REPLICA of the graph per device and every device takes a contiguous
+ * slice of each batch (no exchange; nmslib_set_query_time_params reaches every replica); (B) is seq_search only.
  *
  * (A) ONE process, several devices: pass the index parameter  b200_devices=0,1,2,3  ("0-7", "all") to
  *     nmslib_create_index.  nmslib_add_data_point* and nmslib_knn_query_batch / _fill are used unchanged: the rows are
