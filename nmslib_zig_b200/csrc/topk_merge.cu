@@ -27,11 +27,13 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ keys, const int32
                                   int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                                   int32_t* __restrict__ out_counts, const int* __restrict__ d_nq) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  if (d_nq && (int)blockIdx.x >= *d_nq) return;  // (query count decided on the device)
+  // (query count decided on the device: launched with a small grid that strides over the -- normally zero -- queries,
+  // so the launch that finds nothing to do costs ~2 us instead of scheduling nq blocks that leave at once)
+  if (d_nq) nq = min(nq, *d_nq);
   uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
   int32_t* sid = reinterpret_cast<int32_t*>(sk + items_pow2);
-  const int q = blockIdx.x;
   const int items = lists * k;
+  for (int q = blockIdx.x; q < nq; q += gridDim.x) {
 
   for (int t = threadIdx.x; t < items_pow2; t += blockDim.x) {
     uint64_t key = KEY_MAX;
@@ -95,6 +97,8 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ keys, const int32
     __syncthreads();
     if (threadIdx.x == 0) out_counts[q] = total;
   }
+  __syncthreads();  // (the next query of this block reuses the shared arrays)
+  }
 }
 
 }  // namespace
@@ -104,22 +108,17 @@ namespace {
 // zero-filled so that the consumer's last query block reads defined padding, blocks past that leave at once
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, int count,
                                    int row_vec, uint4* __restrict__ dst, const int* __restrict__ d_count, int pad) {
-  const int r = blockIdx.x;
-  if (d_count) {
-    const int c = min(count, *d_count);
+  const int c = d_count ? min(count, *d_count) : count;
+  const int lim = d_count ? (c + pad - 1) / pad * pad : count;  // (a small grid strides over the rows)
+  for (int r = blockIdx.x; r < lim; r += gridDim.x) {
+    uint4* d = dst + (size_t)r * row_vec;
     if (r >= c) {
-      if (r < (c + pad - 1) / pad * pad) {
-        uint4* d = dst + (size_t)r * row_vec;
-        for (int j = threadIdx.x; j < row_vec; j += blockDim.x) d[j] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      return;
+      for (int j = threadIdx.x; j < row_vec; j += blockDim.x) d[j] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
     }
-  } else if (r >= count) {
-    return;
+    const uint4* s = src + (size_t)idx[r] * row_vec;
+    for (int j = threadIdx.x; j < row_vec; j += blockDim.x) d[j] = s[j];
   }
-  const uint4* s = src + (size_t)idx[r] * row_vec;
-  uint4* d = dst + (size_t)r * row_vec;
-  for (int c = threadIdx.x; c < row_vec; c += blockDim.x) d[c] = s[c];
 }
 __global__ void scatter_keys_kernel(const uint64_t* __restrict__ src, const int* __restrict__ idx, int count, int k,
                                     uint64_t* __restrict__ dst, const int* __restrict__ d_count, int f2i) {
@@ -161,7 +160,7 @@ cudaError_t launch_widen_u8(const uint8_t* src, size_t rows, int dim, int row_wo
 cudaError_t launch_gather_rows(const uint32_t* src, const int* idx, int count, int row_words, uint32_t* dst,
                                cudaStream_t stream, const int* d_count, int pad) {
   if (count <= 0) return cudaSuccess;
-  const int blocks = d_count ? (count + pad - 1) / pad * pad : count;
+  const int blocks = std::min(d_count ? (count + pad - 1) / pad * pad : count, 1184);
   gather_rows_kernel<<<blocks, 64, 0, stream>>>(reinterpret_cast<const uint4*>(src), idx, count, row_words / 4,
                                                 reinterpret_cast<uint4*>(dst), d_count, pad);
   return cudaGetLastError();
@@ -192,7 +191,8 @@ cudaError_t launch_merge_topk(const uint64_t* keys, const int32_t* ids_in, int l
   cudaError_t e =
       cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_ITEMS * 12 + 16));
   if (e != cudaSuccess) return e;
-  merge_topk_kernel<<<nq, threads, smem, stream>>>(keys, ids_in, lists, list_stride, query_stride, nq, k, p2,
+  const int blocks = d_nq ? std::min(nq, 1184) : nq;
+  merge_topk_kernel<<<blocks, threads, smem, stream>>>(keys, ids_in, lists, list_stride, query_stride, nq, k, p2,
                                                    finalize, ext_ids, pos_base, out_keys, out_ids, out_dists,
                                                    out_counts, d_nq);
   return cudaGetLastError();
