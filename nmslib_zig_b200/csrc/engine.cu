@@ -178,10 +178,14 @@ Engine::Engine(Space space, Method method, bool is_u8, int device)
   if (const char* e = nb200_env("NB200_TC_MARGIN")) tc_margin_ = std::max(1, atoi(e));
 }
 
-Engine::~Engine() {
-  if (xch_) xch_destroy(xch_);
-  xch_ = nullptr;
-  if (stream_ || d_db_.p) cudaSetDevice(device_);
+// Device memory back to the driver; the next prepare() uploads again.  (A group of hnsw replicas uses it on the handle's
+// own engine once the graph is built: that engine stays the host store, its device copy would only double device 0's.)
+void Engine::release_device() {
+  if (stream_ || d_db_.p) {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    absorb_async_counts(false);  // (counts of device-resident batches still in the pinned ring)
+  }
   for (DevBuf* b : {&d_db_, &d_aux_, &d_ids_, &d_links0_, &d_links0_cnt_, &d_upper_, &d_upper_off_, &d_visited_,
                     &d_epoch_, &d_counters_, &d_q_, &d_qaux_, &d_partial_, &d_keys_, &d_out_ids_, &d_out_dists_,
                     &d_out_counts_, &d_bias_, &d_db_unit_, &d_flags_, &d_qa_, &d_cand_, &d_cand_cnt_, &d_cand_thr_,
@@ -191,6 +195,20 @@ Engine::~Engine() {
   d_fb_cnt_.release();
   d_digits_.release();
   d_glists_.release();
+  upload_valid_ = false;
+  n_up_ = 0;
+  n_dev_ = 0;
+  d_q_dim_ = 0;
+  data_dirty_ = true;
+  if (!graph_.empty()) graph_dirty_ = true;
+  for (auto& f : fb_pending_) f = false;
+  stats_.device_bytes = 0;
+}
+
+Engine::~Engine() {
+  if (xch_) xch_destroy(xch_);
+  xch_ = nullptr;
+  release_device();
   for (PinBuf* b : {&h_out_ids_, &h_out_dists_, &h_out_counts_, &h_q_, &h_cert_, &h_fb_cnt_}) b->release();
   for (auto& e : fb_ev_)
     if (e) cudaEventDestroy(e);

@@ -180,6 +180,7 @@ class Engine {
   // replica of another engine's hnsw index (ShardGroup): a copy of the links over BORROWED search-ready float rows
   // (cosine: already unit-normalised; uint8: already widened) and ids
   Status adopt_replica(const HnswGraph& g, const float* search_rows, const int32_t* ids, int dim);
+  void release_device();  // frees every device buffer; the next prepare() uploads again
   const HnswGraph& graph() const { return graph_; }
   const float* hnsw_rows_for_save() { return hnsw_host_rows(); }
   void set_pos_base(uint32_t b) { pos_base_ = b; }

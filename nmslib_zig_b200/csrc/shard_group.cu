@@ -236,6 +236,7 @@ Status ShardGroup::prepare(Engine* host, size_t nq, size_t k) {
     if (n_rows == 0) return Status::Err(kErrQuery, "index holds no data");
     Status gs = host->ensure_graph();  // built once (on the device when the parameters say so), or imported
     if (!gs.ok()) return gs;
+    host->release_device();            // (the handle's engine stays the host store; the replicas hold the device copies)
     const float* rows = host->hnsw_rows_for_save();
     const size_t G = m.devices.size();
     m.shards.clear();
