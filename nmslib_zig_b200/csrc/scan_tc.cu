@@ -17,17 +17,23 @@
 //        the TF32 error of pass 1.  If the exact k-th rank + E < thr the answer is provably the
 //        exact top-k; otherwise the query is re-run by the exact scan (scan_exact.cu).
 //
-// Two kernels share the TMA / mbarrier / tcgen05 plumbing and the epilogue (epi_process):
-//   tc_scan_ts_kernel  rows of <= 128 floats: the CTA's 256 prepared queries live in TENSOR MEMORY (TS-mode MMA),
-//                      one stage = one whole 64-row database tile, N = 64 accumulators double buffered
-//   tc_scan_kernel     longer rows: query and database k-blocks stream through shared memory together (SS mode),
-//                      N = 128 accumulators double buffered
-// Both: one CTA per SM, 320 threads, warp-specialised -- a TMA producer warp (cp.async.bulk.tensor, 128B swizzle,
-// mbarrier complete_tx), an MMA warp (TMEM allocation + tcgen05.mma.kind::tf32 issued by one elected lane of a
-// warp-uniform loop) and eight epilogue warps (thread = TMEM lane = query row): tcgen05.ld 32 columns at a
-// time, min tree, one compare per 32 values with the row's threshold; survivors (rare once the threshold is
-// warm) go to the row's candidate buffer.  Thresholds: exact 16th best in a register list for k <= 12,
-// otherwise tightened by warp-cooperative compaction of the buffer; shared between the CTAs of one query.
+// Four kernels share the TMA / mbarrier / tcgen05 plumbing:
+//   tc_scan_ts_kernel    rows of <= 128 floats (configs 1, 2): the CTA's 256 prepared queries live in TENSOR MEMORY
+//                        (TS-mode MMA), one stage = one whole 64-row database tile (+ the |x|^2 k-block), N = 64
+//                        accumulators double buffered per 128-query half; 352 threads: TMA producer, TWO MMA issuer
+//                        warps (one per half), eight epilogue warps
+//   tc_scan_u8_kernel    uint8 rows (config 4) on the INTEGER tensor pipe (kind::i8): byte rows + base-255 norm
+//                        digits, three accumulator buffers per half, int32 epilogue; same roles
+//   tc_scan_pair_kernel  longer rows (configs 3, 5) on CTA PAIRS: cta_group::2 M256 x N256 MMAs, both operands
+//                        through shared memory, the tensor cores read B from both SMs
+//   tc_scan_kernel       the single-CTA long-row kernel (SS mode, N = 128), kept behind option tc_pair=0 for A/B
+// All: one CTA per SM, warp-specialised -- a TMA producer warp (cp.async.bulk.tensor, 128B swizzle, mbarrier
+// complete_tx), MMA issue by one elected lane of a warp-uniform loop, epilogue warps with thread = TMEM lane = query
+// row.  The TS / u8 epilogues drain a tile with one tcgen05.ld.x64, reduce the row's 64 values with a 3-input
+// min / max tree and take ONE warp-uniform branch; survivors (a per-lane walk over the tile's groups of 8 values, see
+// epi_select_tile) go to the row's candidate buffer.  The long-row kernels use the round-1 epilogue (epi_process, 32
+// columns at a time).  Thresholds: the exact 16th best in a register list for k <= 12, otherwise tightened by
+// warp-cooperative compaction of the buffer; shared between the CTAs of one query through a per-query word.
 #include <cuda.h>
 
 #include <algorithm>
