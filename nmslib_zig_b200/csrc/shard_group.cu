@@ -8,6 +8,11 @@
 // into its exchange window, and finalises 1/G of the queries by merging all devices' lists over NVLink peer memory
 // (exchange.cu); the slices land in one pinned result array.  An unmodified caller of nmslib_add_data_point_batch +
 // nmslib_knn_query_batch therefore uses G GPUs and gets bit-identical answers to the one-GPU index.
+//
+// method hnsw: one graph does not shard without changing its answers, so the group holds one REPLICA per
+// device -- the graph is built (or imported) once by the handle's own engine, every replica copies the links and
+// borrows the search-ready rows and ids from the host store -- and every device takes a contiguous slice of each
+// batch; no exchange.  The handle's engine frees its own device copy once the graph exists.
 #include <cuda_runtime.h>
 #include <string.h>
 
